@@ -1,0 +1,151 @@
+/*
+ * ballbot_b200.h -- C ABI of the B200 batched ballbot engine (libballbot_b200.so).
+ *
+ * This is the drop-in boundary for the reference's hot path: patched-MuJoCo mj_step driven through
+ * Stable-Baselines3 SubprocVecEnv.  Every entry point names the reference interface
+ * it replaces (paths relative to the reference repo root).  Plain C types only; device pointers are owned
+ * by the caller (PyTorch tensors) for I/O, the engine owns the persistent simulation state and terrains.
+ * All functions return 0 on success or a negative bb_status; the message is available via bb_last_error().
+ * No function allocates or synchronises inside bb_step/bb_reset (stream-ordered, CUDA-graph capturable).
+ * An engine is not thread-safe (like mjData); one engine per device.
+ */
+#ifndef BALLBOT_B200_H
+#define BALLBOT_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_ABI_VERSION 1
+#define BB_HFIELD_N 293 /* ballbot_gym/models/ballbot.xml:23 (nrow = ncol = 293) */
+#define BB_NQ 17
+#define BB_NV 15
+
+typedef enum bb_status {
+  BB_OK = 0,
+  BB_ERR_INVALID = -1,   /* bad argument / config */
+  BB_ERR_CUDA = -2,      /* CUDA runtime error */
+  BB_ERR_NO_DEVICE = -3, /* no usable CUDA device: the engine has NO CPU fallback */
+  BB_ERR_STATE = -4
+} bb_status;
+
+typedef enum bb_terrain { BB_TERRAIN_FLAT = 0, BB_TERRAIN_PERLIN = 1, BB_TERRAIN_EXTERNAL = 2 } bb_terrain;
+typedef enum bb_reward { BB_REWARD_DIRECTIONAL = 0, BB_REWARD_DISTANCE = 1, BB_REWARD_EXTERNAL = 2 } bb_reward;
+
+/* Replaces the constructor arguments / YAML knobs of BBotSimulation.__init__ (ballbot_gym/envs/ballbot_env.py:157-231)
+ * plus the terrain generator arguments of generate_perlin_terrain (ballbot_gym/terrain/perlin.py:8-16). */
+typedef struct bb_config {
+  int32_t abi_version;       /* BB_ABI_VERSION */
+  int32_t num_envs;          /* envs simulated by this engine (this rank's shard) */
+  int64_t env_offset;        /* global index of env 0 (multi-GPU sharding: rank * num_envs) */
+  int32_t device;            /* CUDA device ordinal */
+  int32_t precision;         /* 64 (parity mode, MuJoCo mjtNum=double) or 32 */
+  int32_t terrain_type;      /* bb_terrain */
+  int32_t terrain_seed;      /* >=0: fixed seed from terrain config; <0: per-reset U{0..9999} (ballbot_env.py:505-510) */
+  float perlin_scale, perlin_persistence, perlin_lacunarity, perlin_amplitude;
+  int32_t perlin_octaves;
+  float hfield_zscale;       /* hfield_size[0,2] (2.0; ramp/gradient change it, ballbot_env.py:486-495) */
+  int32_t cameras;           /* 0 == disable_cameras=True */
+  int32_t im_h, im_w;        /* camera.height / camera.width (64 x 64) */
+  float camera_frame_rate;   /* ballbot_env.py:224 (90 Hz) */
+  int32_t max_ep_steps;      /* ballbot_env.py:221 (4000) */
+  float max_allowed_tilt;    /* ballbot_env.py:222 (20 deg) */
+  float max_wheel_velocity;  /* ballbot_env.py:223 (10) */
+  int32_t reward_type;       /* bb_reward */
+  float reward_scale;        /* ballbot_env.py:229 (0.01) */
+  float action_reg_coef;     /* ballbot_env.py:230 (-1e-4) */
+  float survival_bonus;      /* ballbot_env.py:231 (0.02) */
+  float target_direction[2]; /* rewards/directional.py:33 */
+  float goal_position[2];    /* rewards/distance.py:33 */
+  float distance_scale;
+  uint64_t seed;             /* base seed of the counter-based per-env terrain-seed generator */
+  int32_t auto_reset;        /* 1: VecEnv semantics (done envs are reset inside bb_step) */
+} bb_config;
+
+/* Caller-owned device buffers written by bb_step / bb_reset.  Layouts follow the observation dict of
+ * BBotSimulation._get_obs (ballbot_env.py:803-827) stacked per key like SubprocVecEnv does. */
+typedef struct bb_io {
+  float* orientation;      /* [N,3]  obs["orientation"] */
+  float* angular_vel;      /* [N,3]  obs["angular_vel"] */
+  float* vel;              /* [N,3]  obs["vel"] */
+  float* motor_state;      /* [N,3]  obs["motor_state"] */
+  float* actions;          /* [N,3]  obs["actions"] */
+  float* rel_image_ts;     /* [N,1]  obs["relative_image_timestamp"] */
+  float* rgbd_0;           /* [N,1,H,W] obs["rgbd_0"] (NULL when cameras are disabled) */
+  float* rgbd_1;           /* [N,1,H,W] obs["rgbd_1"] */
+  float* reward;           /* [N]    step() reward (for BB_REWARD_EXTERNAL: everything but the plugin term) */
+  uint8_t* terminated;     /* [N]    step() terminated */
+  uint8_t* failure;        /* [N]    info["failure"] */
+  float* pos2d;            /* [N,2]  info["pos2d"] */
+  float* terminal_obs;     /* [N,16] proprio obs before auto-reset (info["terminal_observation"]), valid where terminated */
+  float* episode_return;   /* [N]    Monitor info["episode"]["r"], valid where terminated */
+  int32_t* episode_length; /* [N]    Monitor info["episode"]["l"], valid where terminated */
+  int32_t* status;         /* [N]    bit0: numerical failure (NaN / |x|>1e10) -> env was reset; bits 8..: max contacts seen */
+} bb_io;
+
+typedef struct bb_engine bb_engine;
+
+/* replaces gym.make("ballbot-v0.1", ...) x N inside SubprocVecEnv (ballbot_rl/training/train.py:82-97) */
+int bb_create(const bb_config* cfg, bb_engine** out);
+int bb_destroy(bb_engine* e);
+void bb_default_config(bb_config* cfg);
+const char* bb_last_error(const bb_engine* e); /* e may be NULL: error of the last failed bb_create */
+int bb_num_envs(const bb_engine* e);
+
+/* replaces VecEnv.reset() / BBotSimulation.reset (ballbot_env.py:567-671) for the envs selected by mask
+ * (device uint8[N], NULL = all). Writes the reset observation into io. */
+int bb_reset(bb_engine* e, const uint8_t* mask_dev, const bb_io* io, void* cuda_stream);
+
+/* replaces VecEnv.step_async+step_wait / BBotSimulation.step (ballbot_env.py:854-1036): one patched-MuJoCo
+ * mj_step (RK4, 2 ms) per env + observation + reward + termination (+ auto-reset). actions_dev: float[N,3]. */
+int bb_step(bb_engine* e, const float* actions_dev, const bb_io* io, void* cuda_stream);
+
+/* adds a caller-computed plugin reward term (custom BaseReward, rewards/base.py:7-21) AFTER bb_step when
+ * reward_type == BB_REWARD_EXTERNAL: reward += scale*term and the episode-return accumulators are fixed up. */
+int bb_add_reward(bb_engine* e, const float* term_dev, const bb_io* io, void* cuda_stream);
+
+/* state injection / readback for parity tests (mjData.qpos/qvel/qacc_warmstart/time); double[N,17|15|15], all
+ * pointers are DEVICE pointers, any may be NULL */
+int bb_set_state(bb_engine* e, const double* qpos, const double* qvel, const double* warm, void* cuda_stream);
+int bb_get_state(bb_engine* e, double* qpos, double* qvel, double* warm, void* cuda_stream);
+
+/* replaces `model.hfield_data = terrain_gen(nrows, seed=r_seed)` (ballbot_env.py:513) for host-generated plugin
+ * terrains: env_ids int32[n] (device), hfield float[n,293*293] (device). Only for BB_TERRAIN_EXTERNAL. */
+int bb_set_hfield(bb_engine* e, const int32_t* env_ids_dev, int32_t n, const float* hfield_dev, void* cuda_stream);
+/* copies the heightfield of one env to a device buffer float[293*293] */
+int bb_get_hfield(bb_engine* e, int32_t env, float* hfield_dev, void* cuda_stream);
+/* terrain seeds currently in use, int32[N] (ballbot_env.py:507 last_r_seed) */
+int bb_get_terrain_seeds(bb_engine* e, int32_t* seeds_dev, void* cuda_stream);
+
+/* on-device replacement of generate_perlin_terrain (terrain/perlin.py:8-74): out float[n_seeds,293*293] */
+int bb_perlin_terrain(bb_engine* e, const int32_t* seeds_dev, int32_t n_seeds, float* out_dev, void* cuda_stream);
+/* depth ray-cast of both cameras for every env at its CURRENT state (sensors/rgbd.py:46-82), ignoring the cadence */
+int bb_render_depth(bb_engine* e, float* rgbd_0, float* rgbd_1, void* cuda_stream);
+
+/* Host-buffer convenience path == what SubprocVecEnv.step does for numpy callers: H2D copy of actions, bb_step,
+ * D2H copy of the proprio observation block [N,16] (orientation, angular_vel, vel, motor_state, actions, rel ts),
+ * reward, terminated, failure, pos2d (+ images when img_0/img_1 are non-NULL), then a stream synchronise. */
+typedef struct bb_host_io {
+  float* obs16;        /* [N,16] */
+  float* reward;       /* [N] */
+  uint8_t* terminated; /* [N] */
+  uint8_t* failure;    /* [N] */
+  float* pos2d;        /* [N,2] */
+  float* terminal_obs; /* [N,16] */
+  float* episode_return;   /* [N] */
+  int32_t* episode_length; /* [N] */
+  float* img_0;        /* [N,H*W] or NULL */
+  float* img_1;
+} bb_host_io;
+int bb_step_host(bb_engine* e, const float* actions_host, const bb_host_io* out);
+int bb_reset_host(bb_engine* e, const uint8_t* mask_host, const bb_host_io* out);
+
+/* number of kernel launches issued by this engine so far (bench.py's gpu_launches claim) */
+int64_t bb_launch_count(const bb_engine* e);
+/* engine model constants for tests: dA[4], meaninertia, masses (m0, mw, mL) */
+int bb_model_constants(double* dA4, double* meaninertia, double* masses3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,119 @@
+"""ctypes loader for the C-ABI engine library (include/ballbot_b200.h).
+
+The product path is CUDA only: if ``libballbot_b200.so`` is missing or cannot be loaded this module raises -- there is
+no CPU or PyTorch fallback.  ``build()`` compiles the library in-tree with nvcc for sm_100a.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG, "csrc")
+LIB_PATH = os.path.join(_PKG, "libballbot_b200.so")
+_SOURCES = ["bb_engine.cu", "bb_core.cuh", "bb_model.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC"]
+
+HFIELD_N = 293
+NQ, NV = 17, 15
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    """bb_config (include/ballbot_b200.h)."""
+    _fields_ = [
+        ("abi_version", C.c_int32), ("num_envs", C.c_int32), ("env_offset", C.c_int64), ("device", C.c_int32),
+        ("precision", C.c_int32), ("terrain_type", C.c_int32), ("terrain_seed", C.c_int32),
+        ("perlin_scale", C.c_float), ("perlin_persistence", C.c_float), ("perlin_lacunarity", C.c_float),
+        ("perlin_amplitude", C.c_float), ("perlin_octaves", C.c_int32), ("hfield_zscale", C.c_float),
+        ("cameras", C.c_int32), ("im_h", C.c_int32), ("im_w", C.c_int32), ("camera_frame_rate", C.c_float),
+        ("max_ep_steps", C.c_int32), ("max_allowed_tilt", C.c_float), ("max_wheel_velocity", C.c_float),
+        ("reward_type", C.c_int32), ("reward_scale", C.c_float), ("action_reg_coef", C.c_float),
+        ("survival_bonus", C.c_float), ("target_direction", C.c_float * 2), ("goal_position", C.c_float * 2),
+        ("distance_scale", C.c_float), ("seed", C.c_uint64), ("auto_reset", C.c_int32),
+    ]
+
+
+class IO(C.Structure):
+    """bb_io: caller-owned device output pointers."""
+    _fields_ = [(n, C.c_void_p) for n in (
+        "orientation", "angular_vel", "vel", "motor_state", "actions", "rel_image_ts", "rgbd_0", "rgbd_1", "reward",
+        "terminated", "failure", "pos2d", "terminal_obs", "episode_return", "episode_length", "status")]
+
+
+class HostIO(C.Structure):
+    """bb_host_io: host output pointers of the numpy path."""
+    _fields_ = [(n, C.c_void_p) for n in (
+        "obs16", "reward", "terminated", "failure", "pos2d", "terminal_obs", "episode_return", "episode_length",
+        "img_0", "img_1")]
+
+
+EXPORTED = ["bb_create", "bb_destroy", "bb_default_config", "bb_last_error", "bb_num_envs", "bb_reset", "bb_step",
+            "bb_add_reward", "bb_set_state", "bb_get_state", "bb_set_hfield", "bb_get_hfield", "bb_get_terrain_seeds",
+            "bb_perlin_terrain", "bb_render_depth", "bb_step_host", "bb_reset_host", "bb_launch_count",
+            "bb_model_constants"]
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    srcs = [os.path.join(_CSRC, s) for s in _SOURCES] + [os.path.join(_PKG, "..", "include", "ballbot_b200.h")]
+    return any(os.path.exists(s) and os.path.getmtime(s) > t for s in srcs)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/bb_engine.cu for sm_100a into libballbot_b200.so (nvcc cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(_CSRC, "bb_engine.cu")]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load libballbot_b200.so; raises EngineError when the CUDA library is absent (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). The ballbot engine has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.bb_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.bb_destroy.argtypes = [vp]
+    L.bb_default_config.argtypes = [C.POINTER(Config)]
+    L.bb_default_config.restype = None
+    L.bb_last_error.argtypes = [vp]
+    L.bb_last_error.restype = C.c_char_p
+    L.bb_num_envs.argtypes = [vp]
+    L.bb_reset.argtypes = [vp, vp, C.POINTER(IO), vp]
+    L.bb_step.argtypes = [vp, vp, C.POINTER(IO), vp]
+    L.bb_add_reward.argtypes = [vp, vp, C.POINTER(IO), vp]
+    L.bb_set_state.argtypes = [vp, vp, vp, vp, vp]
+    L.bb_get_state.argtypes = [vp, vp, vp, vp, vp]
+    L.bb_set_hfield.argtypes = [vp, vp, C.c_int32, vp, vp]
+    L.bb_get_hfield.argtypes = [vp, C.c_int32, vp, vp]
+    L.bb_get_terrain_seeds.argtypes = [vp, vp, vp]
+    L.bb_perlin_terrain.argtypes = [vp, vp, C.c_int32, vp, vp]
+    L.bb_render_depth.argtypes = [vp, vp, vp, vp]
+    L.bb_step_host.argtypes = [vp, vp, C.POINTER(HostIO)]
+    L.bb_reset_host.argtypes = [vp, vp, C.POINTER(HostIO)]
+    L.bb_launch_count.argtypes = [vp]
+    L.bb_launch_count.restype = C.c_int64
+    L.bb_model_constants.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def default_config():
+    cfg = Config()
+    lib().bb_default_config(C.byref(cfg))
+    return cfg

@@ -1,0 +1,784 @@
+// bb_engine.cu -- CUDA kernels (sm_100a) and the C ABI (include/ballbot_b200.h) of the batched ballbot engine.
+//
+// Kernels (all fixed-grid, device-side work lists => no host sync inside bb_step, CUDA-graph capturable):
+//   k_step<T>      one thread per env: action map, RK4 mj_step equivalent (4 x forward dynamics with contact
+//                  generation and the elliptic-cone Newton solve), proprio obs, reward, termination, episode
+//                  statistics, work-list append for auto-reset and camera refresh        (ballbot_env.py:854-1036)
+//   k_terrain      simplex-fBm heightfield regeneration for the envs in the reset list    (terrain/perlin.py:8-74)
+//   k_reset<T>     spawn-height window max, state reset, reset observation                (ballbot_env.py:528-565,612-634)
+//   k_depth<T>     2 x HxW depth ray-cast per refreshing env (hfield DDA + analytic prims) (sensors/rgbd.py:46-82)
+// State is structure-of-arrays [field][env] so that a warp's loads/stores are fully coalesced.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "../../include/ballbot_b200.h"
+#include "bb_model.h"
+
+using namespace bb;
+
+namespace {
+
+constexpr int NST = NQ + NV + NV;  // qpos, qvel, qacc_warmstart
+constexpr int HF_CELLS = HN * HN;
+
+__constant__ ModelConst<double> c_mc64;
+__constant__ ModelConst<float> c_mc32;
+template <typename T> __device__ __forceinline__ const ModelConst<T>& cmc();
+template <> __device__ __forceinline__ const ModelConst<double>& cmc<double>() { return c_mc64; }
+template <> __device__ __forceinline__ const ModelConst<float>& cmc<float>() { return c_mc32; }
+
+struct EnvParams {
+  int N; long long env_offset;
+  int cameras, im_h, im_w, cam_period;
+  int max_ep_steps; float max_tilt, max_wheel_vel;
+  int reward_type; float reward_scale, action_reg, survival, tdir[2], goal[2], dist_scale;
+  float zscale; int terrain_type, terrain_seed; unsigned long long seed;
+  int auto_reset, hf_per_env;
+  float pscale, ppers, plac, pamp; int poct;
+};
+struct DevState {
+  void* st;        // T[NST][N]
+  void* camq;      // T[NQ][N]  configuration the cameras see (last RK stage / reset state)
+  int* step_count; int* cam_steps; unsigned* episode; int* tseed;
+  float* hfield;   // [N][HF_CELLS] (hf_per_env) or [HF_CELLS]
+  float* ep_ret; int* ep_len;
+  int* counters;   // [0] reset-list length, [1] refresh-list length
+  int* reset_list; int* refresh_list;
+};
+
+__device__ __forceinline__ unsigned long long splitmix(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31);
+}
+// counter-based replacement of self._np_random.integers(0, 10000) (ballbot_env.py:506): U{0..9999} per (env, episode)
+__device__ __forceinline__ int drawTerrainSeed(const EnvParams& p, int env, unsigned episode) {
+  if (p.terrain_seed >= 0) return p.terrain_seed;
+  unsigned long long h = splitmix(p.seed ^ splitmix((unsigned long long)(p.env_offset + env) * 0x100000001B3ull + episode));
+  return (int)(h % 10000ull);
+}
+
+// --------------------------------------------------------------------------------------------- step
+template <typename T>
+__global__ void __launch_bounds__(64) k_step(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.N) return;
+  T* st = (T*)d.st;
+  T qpos[NQ], qvel[NV], warm[NV];
+#pragma unroll
+  for (int k = 0; k < NQ; k++) qpos[k] = st[(size_t)k * p.N + i];
+#pragma unroll
+  for (int k = 0; k < NV; k++) { qvel[k] = st[(size_t)(NQ + k) * p.N + i]; warm[k] = st[(size_t)(NQ + NV + k) * p.N + i]; }
+  const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
+  T ctrl[3];
+  {  // ballbot_env.py:903-907
+    const float av[3] = {a0, a1, a2};
+    for (int k = 0; k < 3; k++) { T u = (T)av[k] * (T)p.max_wheel_vel; u = u > (T)p.max_wheel_vel ? (T)p.max_wheel_vel : (u < -(T)p.max_wheel_vel ? -(T)p.max_wheel_vel : u); ctrl[k] = -u; }
+  }
+  bool bad = false;  // mj_checkPos / mj_checkVel
+  for (int k = 0; k < NQ; k++) bad |= !(babs(qpos[k]) < (T)1e10);
+  for (int k = 0; k < NV; k++) bad |= !(babs(qvel[k]) < (T)1e10);
+  KinOut<T> kin;
+  T qlast[NQ];
+  int status = 0;
+  if (!bad) {
+    Scratch<T> s;
+    const float* hf = d.hfield + (p.hf_per_env ? (size_t)i * HF_CELLS : 0);
+    rk4Step(cmc<T>(), qpos, qvel, warm, ctrl, hf, (T)p.zscale, s, &kin, qlast);
+    for (int k = 0; k < NQ; k++) bad |= !(babs(qpos[k]) < (T)1e10);
+    for (int k = 0; k < NV; k++) bad |= !(babs(qvel[k]) < (T)1e10);
+    status = kin.ncon << 8;
+  }
+  if (bad) {  // numerical failure: flag, report a terminated+failed step with a zero observation; the env is reset
+    status |= 1;
+    kin.quatB[0] = 1; kin.quatB[1] = kin.quatB[2] = kin.quatB[3] = 0;
+    for (int k = 0; k < 3; k++) { kin.cvel_ang[k] = 0; kin.cvel_lin[k] = 0; kin.posB[k] = 0; }
+    for (int k = 0; k < NV; k++) qvel[k] = 0;
+  }
+#pragma unroll
+  for (int k = 0; k < NQ; k++) st[(size_t)k * p.N + i] = qpos[k];
+#pragma unroll
+  for (int k = 0; k < NV; k++) { st[(size_t)(NQ + k) * p.N + i] = qvel[k]; st[(size_t)(NQ + NV + k) * p.N + i] = warm[k]; }
+
+  // ---- observation (ballbot_env.py:772-827)
+  float ob[16];
+  proprioObs(kin, qvel, (T)p.max_wheel_vel, ob, ob + 3, ob + 6, ob + 9);
+  ob[12] = a0; ob[13] = a1; ob[14] = a2;
+  int cs = d.cam_steps[i] + 1;
+  bool refresh = false;
+  if (p.cameras && cs >= p.cam_period) { refresh = true; cs = 0; }
+  ob[15] = p.cameras ? (float)((double)cs * 0.002) : 0.f;
+  // ---- reward (ballbot_env.py:929-937), float32 arithmetic as NumPy >= 2
+  float r = 0.f;
+  if (p.reward_type == BB_REWARD_DIRECTIONAL) r = (ob[6] * p.tdir[0] + ob[7] * p.tdir[1]) * p.reward_scale;
+  else if (p.reward_type == BB_REWARD_DISTANCE) {
+    const float dx = p.goal[0] - (float)kin.posB[0], dy = p.goal[1] - (float)kin.posB[1];
+    r = (-p.dist_scale * sqrtf(dx * dx + dy * dy)) * p.reward_scale;
+  }
+  const float nrm = sqrtf(a0 * a0 + a1 * a1 + a2 * a2);
+  r += p.action_reg * (nrm * nrm);
+  // ---- termination (ballbot_env.py:977-1020)
+  const int sc = d.step_count[i] + 1;
+  bool term = sc >= p.max_ep_steps, fail = false;
+  const double tilt = tiltDegrees(ob);
+  if (tilt > (double)p.max_tilt || bad) { fail = true; term = true; } else r += p.survival;
+  const float eret = d.ep_ret[i] + r; const int elen = d.ep_len[i] + 1;
+  // ---- outputs
+  for (int k = 0; k < 3; k++) {
+    io.orientation[3 * i + k] = ob[k]; io.angular_vel[3 * i + k] = ob[3 + k]; io.vel[3 * i + k] = ob[6 + k];
+    io.motor_state[3 * i + k] = ob[9 + k]; io.actions[3 * i + k] = ob[12 + k];
+  }
+  io.rel_image_ts[i] = ob[15];
+  io.reward[i] = r; io.terminated[i] = term; io.failure[i] = fail;
+  io.pos2d[2 * i] = (float)kin.posB[0]; io.pos2d[2 * i + 1] = (float)kin.posB[1];
+  if (io.status) io.status[i] = status;
+  if (term) {
+    if (io.terminal_obs) for (int k = 0; k < 16; k++) io.terminal_obs[16 * i + k] = ob[k];
+    if (io.episode_return) io.episode_return[i] = eret;
+    if (io.episode_length) io.episode_length[i] = elen;
+  }
+  d.step_count[i] = sc; d.cam_steps[i] = cs; d.ep_ret[i] = eret; d.ep_len[i] = elen;
+  if (term && p.auto_reset) {
+    const unsigned ep = d.episode[i] + 1; d.episode[i] = ep;
+    d.tseed[i] = drawTerrainSeed(p, i, ep);
+    d.reset_list[atomicAdd(&d.counters[0], 1)] = i;
+  } else if (refresh) {
+    T* cq = (T*)d.camq;
+    for (int k = 0; k < NQ; k++) cq[(size_t)k * p.N + i] = qlast[k];
+    d.refresh_list[atomicAdd(&d.counters[1], 1)] = i;
+  }
+}
+
+// explicit reset: mask -> reset list (+ new terrain seed)
+__global__ void k_mask_to_list(EnvParams p, DevState d, const uint8_t* __restrict__ mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.N) return;
+  if (mask && !mask[i]) return;
+  const unsigned ep = d.episode[i] + 1; d.episode[i] = ep;
+  d.tseed[i] = drawTerrainSeed(p, i, ep);
+  d.reset_list[atomicAdd(&d.counters[0], 1)] = i;
+}
+__global__ void k_clear_counters(DevState d) { d.counters[0] = 0; d.counters[1] = 0; }
+
+// --------------------------------------------------------------------------------------------- simplex fBm terrain
+__constant__ unsigned char c_perm[256];
+__device__ __forceinline__ int dperm(int i) { return c_perm[i & 255]; }
+__device__ __forceinline__ float grad4(int gi, float x, float y, float z, float w) {
+  // 32 gradient directions of 4-D simplex noise: one zero component (gi>>3 selects which), signs from the low bits
+  const int zc = gi >> 3;
+  const float s0 = (gi & 4) ? -1.f : 1.f, s1 = (gi & 2) ? -1.f : 1.f, s2 = (gi & 1) ? -1.f : 1.f;
+  switch (zc) {
+    case 0: return s0 * y + s1 * z + s2 * w;
+    case 1: return s0 * x + s1 * z + s2 * w;
+    case 2: return s0 * x + s1 * y + s2 * w;
+    default: return s0 * x + s1 * y + s2 * z;
+  }
+}
+__device__ float simplex4(float x, float y, float z, float w) {
+  const float F4 = 0.309016994f, G4 = 0.138196601f;
+  const float sk = (x + y + z + w) * F4;
+  const float fi = floorf(x + sk), fj = floorf(y + sk), fk = floorf(z + sk), fl = floorf(w + sk);
+  const float t = (fi + fj + fk + fl) * G4;
+  const float x0 = x - (fi - t), y0 = y - (fj - t), z0 = z - (fk - t), w0 = w - (fl - t);
+  const int rx = (x0 > y0) + (x0 > z0) + (x0 > w0);
+  const int ry = !(x0 > y0) + (y0 > z0) + (y0 > w0);
+  const int rz = !(x0 > z0) + !(y0 > z0) + (z0 > w0);
+  const int rw = 6 - rx - ry - rz;
+  const int I = (int)fi & 255, J = (int)fj & 255, K = (int)fk & 255, L = (int)fl & 255;
+  float total = 0.f;
+#pragma unroll
+  for (int c = 0; c < 5; c++) {
+    const int thr = 4 - c;   // corner c steps along the c highest-ranked axes
+    const int i1 = c == 0 ? 0 : (rx >= thr), j1 = c == 0 ? 0 : (ry >= thr), k1 = c == 0 ? 0 : (rz >= thr), l1 = c == 0 ? 0 : (rw >= thr);
+    const float xc = x0 - i1 + c * G4, yc = y0 - j1 + c * G4, zc = z0 - k1 + c * G4, wc = w0 - l1 + c * G4;
+    float tt = 0.6f - xc * xc - yc * yc - zc * zc - wc * wc;
+    if (tt >= 0.f) {
+      const int gi = dperm(I + i1 + dperm(J + j1 + dperm(K + k1 + dperm(L + l1)))) & 31;
+      tt *= tt;
+      total += tt * tt * grad4(gi, xc, yc, zc, wc);
+    }
+  }
+  return 27.f * total;
+}
+// snoise2(x, y, octaves, persistence, lacunarity, repeatx=1024, repeaty=1024, base=seed): tiled branch = 4-D fBm on two circles
+__device__ float perlinHeight(int i, int j, int seed, float scale, int oct, float pers, float lac, float amp) {
+  float x = (float)((double)i / (double)scale), y = (float)((double)j / (double)scale);
+  float z = (float)seed, w = z;
+  const float rr = (float)(1024.0 * 0.3183098861837907 * 0.5);
+  const float yf = (float)((double)y * 2.0 / 1024.0), xf = (float)((double)x * 2.0 / 1024.0);
+  y = sinf(yf) * rr; w += cosf(yf) * rr;
+  x = sinf(xf) * rr; z += cosf(xf) * rr;
+  float freq = 1.f, a = 1.f, mx = 1.f, total = simplex4(x, y, z, w);
+  for (int o = 1; o < oct; o++) { freq *= lac; a *= pers; mx += a; total += simplex4(x * freq, y * freq, z * freq, w * freq) * a; }
+  const double v = ((double)(total / mx) + 1.0) / 2.0 * (double)amp;
+  return (float)(v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v));
+}
+// grid.x covers the cells of one heightfield, grid.y strides over the work list
+__global__ void __launch_bounds__(256) k_terrain(EnvParams p, DevState d, const int* __restrict__ list, const int* __restrict__ count,
+                                                 int fixed_count, const int* __restrict__ seeds, float* __restrict__ out) {
+  const int n = count ? *count : fixed_count;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= HF_CELLS) return;
+  const int r = cell / HN, c = cell - r * HN;
+  for (int k = blockIdx.y; k < n; k += gridDim.y) {
+    const int env = list ? list[k] : k;
+    const int seed = seeds ? seeds[k] : d.tseed[env];
+    float* dst = out ? out + (size_t)k * HF_CELLS : d.hfield + (size_t)env * HF_CELLS;
+    dst[cell] = perlinHeight(r, c, seed, p.pscale, p.poct, p.ppers, p.plac, p.pamp);
+  }
+}
+
+// --------------------------------------------------------------------------------------------- reset
+template <typename T>
+__global__ void k_reset(EnvParams p, DevState d, bb_io io) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= d.counters[0]) return;
+  const int i = d.reset_list[k];
+  // spawn height: max of hfield rows/cols 140..151 (ballbot_env.py:546-563, cell_size = 5/293 quirk)
+  const float* hf = d.hfield + (p.hf_per_env ? (size_t)i * HF_CELLS : 0);
+  float mx = -1e30f;
+  for (int r = 140; r < 152; r++) for (int c = 140; c < 152; c++) mx = fmaxf(mx, hf[r * HN + c]);
+  const double off = (double)mx * (double)p.zscale + 0.01;
+  const double q0[NQ] = {0, 0, 0.24 + off, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.26 + off, 1, 0, 0, 0};
+  T* st = (T*)d.st; T* cq = (T*)d.camq;
+  for (int j = 0; j < NQ; j++) { st[(size_t)j * p.N + i] = (T)q0[j]; cq[(size_t)j * p.N + i] = (T)q0[j]; }
+  for (int j = NQ; j < NST; j++) st[(size_t)j * p.N + i] = (T)0;
+  d.step_count[i] = 0; d.cam_steps[i] = 0; d.ep_ret[i] = 0.f; d.ep_len[i] = 0;
+  // reset observation: mj_forward at rest => zero rotation vector and velocities (ballbot_env.py:634)
+  for (int j = 0; j < 3; j++) {
+    io.orientation[3 * i + j] = 0.f; io.angular_vel[3 * i + j] = 0.f; io.vel[3 * i + j] = 0.f; io.motor_state[3 * i + j] = 0.f; io.actions[3 * i + j] = 0.f;
+  }
+  io.rel_image_ts[i] = 0.f;
+  if (p.cameras) d.refresh_list[atomicAdd(&d.counters[1], 1)] = i;
+}
+
+// --------------------------------------------------------------------------------------------- depth ray cast
+struct F3 { float x, y, z; };
+__device__ __forceinline__ F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ F3 operator+(F3 a, F3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ F3 operator-(F3 a, F3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ F3 operator*(F3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float fdot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ F3 fcross(F3 a, F3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+struct Prim { F3 c, u; float r, hl; int type; };  // type 0 sphere, 1 capsule, 2 cylinder
+struct Scene { F3 cam_o[2]; F3 cam_x[2], cam_y[2], cam_z[2]; Prim prim[7]; };
+
+__device__ __forceinline__ float hitSphere(F3 o, F3 dir, F3 c, float rad) {
+  const F3 oc = o - c; const float a = fdot(dir, dir), b = fdot(oc, dir), cc = fdot(oc, oc) - rad * rad;
+  const float disc = b * b - a * cc; if (disc < 0.f) return -1.f;
+  return (-b - sqrtf(disc)) / a;   // entry point only (back faces are culled by the rasteriser)
+}
+__device__ __forceinline__ float hitSide(F3 o, F3 dir, const Prim& p) {
+  const F3 oc = o - p.c; const float od = fdot(oc, p.u), dd = fdot(dir, p.u);
+  const F3 op = oc - p.u * od, dp = dir - p.u * dd;
+  const float a = fdot(dp, dp), b = fdot(op, dp), cc = fdot(op, op) - p.r * p.r;
+  if (a < 1e-18f) return -1.f;
+  const float disc = b * b - a * cc; if (disc < 0.f) return -1.f;
+  const float t = (-b - sqrtf(disc)) / a; const float zz = od + t * dd;
+  return (zz < -p.hl || zz > p.hl) ? -1.f : t;
+}
+__device__ float hitPrim(F3 o, F3 dir, const Prim& p) {
+  if (p.type == 0) return hitSphere(o, dir, p.c, p.r);
+  float best = -1.f; float t = hitSide(o, dir, p); if (t > 0.f) best = t;
+  const F3 oc = o - p.c;
+  for (int s = -1; s <= 1; s += 2) {
+    if (p.type == 1) {
+      const F3 e = p.c + p.u * ((float)s * p.hl);
+      t = hitSphere(o, dir, e, p.r);
+      if (t > 0.f) { const F3 hp = oc + dir * t; if ((float)s * fdot(hp, p.u) >= p.hl && (best < 0.f || t < best)) best = t; }
+    } else {
+      const float od = fdot(oc, p.u), dd = fdot(dir, p.u);
+      if (fabsf(dd) < 1e-18f || (float)s * dd >= 0.f) continue;
+      t = ((float)s * p.hl - od) / dd; if (t <= 0.f) continue;
+      const F3 hp = oc + dir * t - p.u * ((float)s * p.hl);
+      if (fdot(hp, hp) <= p.r * p.r && (best < 0.f || t < best)) best = t;
+    }
+  }
+  return best;
+}
+__device__ __forceinline__ float hitTri(F3 o, F3 dir, F3 a, F3 b, F3 c) {
+  const F3 e1 = b - a, e2 = c - a, pv = fcross(dir, e2); const float det = fdot(e1, pv);
+  if (fabsf(det) < 1e-18f) return -1.f;
+  const float inv = 1.f / det; const F3 tv = o - a; const float u = fdot(tv, pv) * inv; if (u < 0.f || u > 1.f) return -1.f;
+  const F3 q = fcross(tv, e1); const float v = fdot(dir, q) * inv; if (v < 0.f || u + v > 1.f) return -1.f;
+  const float t = fdot(e2, q) * inv; return t > 0.f ? t : -1.f;
+}
+// ray vs heightfield: 2-D DDA over the cells, both triangles of each visited cell
+__device__ float hitHfield(F3 o, F3 dir, const float* __restrict__ hf, float sx, float sz, float tmax) {
+  const int n = HN; const float dx = 2.f * sx / (n - 1);
+  float t0 = 0.f, t1 = tmax;
+  {
+    const float oo[2] = {o.x, o.y}, dv[2] = {dir.x, dir.y};
+    for (int ax = 0; ax < 2; ax++) {
+      if (fabsf(dv[ax]) < 1e-18f) { if (oo[ax] < -sx || oo[ax] > sx) return -1.f; }
+      else { float ta = (-sx - oo[ax]) / dv[ax], tb = (sx - oo[ax]) / dv[ax]; if (ta > tb) { const float q = ta; ta = tb; tb = q; } t0 = fmaxf(t0, ta); t1 = fminf(t1, tb); }
+    }
+  }
+  if (t0 >= t1) return -1.f;
+  const float px = o.x + (t0 + 1e-6f) * dir.x, py = o.y + (t0 + 1e-6f) * dir.y;
+  int cx = (int)floorf((px + sx) / dx), cy = (int)floorf((py + sx) / dx);
+  cx = min(max(cx, 0), n - 2); cy = min(max(cy, 0), n - 2);
+  const int stx = dir.x > 0.f ? 1 : -1, sty = dir.y > 0.f ? 1 : -1;
+  const float tdx = fabsf(dir.x) < 1e-18f ? 3e38f : dx / fabsf(dir.x), tdy = fabsf(dir.y) < 1e-18f ? 3e38f : dx / fabsf(dir.y);
+  float tmx = fabsf(dir.x) < 1e-18f ? 3e38f : (-sx + (cx + (stx > 0 ? 1 : 0)) * dx - o.x) / dir.x;
+  float tmy = fabsf(dir.y) < 1e-18f ? 3e38f : (-sx + (cy + (sty > 0 ? 1 : 0)) * dx - o.y) / dir.y;
+  float tcur = t0;
+  for (int it = 0; it < 4 * n; it++) {
+    if (cx < 0 || cx > n - 2 || cy < 0 || cy > n - 2 || tcur > t1) return -1.f;
+    const float x0 = -sx + cx * dx, y0 = -sx + cy * dx;
+    const F3 v00 = f3(x0, y0, hf[cy * n + cx] * sz), v10 = f3(x0 + dx, y0, hf[cy * n + cx + 1] * sz);
+    const F3 v01 = f3(x0, y0 + dx, hf[(cy + 1) * n + cx] * sz), v11 = f3(x0 + dx, y0 + dx, hf[(cy + 1) * n + cx + 1] * sz);
+    const float ta = hitTri(o, dir, v01, v00, v11), tb = hitTri(o, dir, v00, v11, v10);
+    float best = -1.f; if (ta > 0.f) best = ta; if (tb > 0.f && (best < 0.f || tb < best)) best = tb;
+    if (best > 0.f && best <= tmax) return best;
+    if (tmx < tmy) { cx += stx; tcur = tmx; tmx += tdx; } else { cy += sty; tcur = tmy; tmy += tdy; }
+  }
+  return -1.f;
+}
+template <typename T>
+__device__ void buildScene(const ModelConst<float>& mc, const T* __restrict__ cq, int N, int i, Scene& sc) {
+  float q[NQ]; for (int k = 0; k < NQ; k++) q[k] = (float)cq[(size_t)k * N + i];
+  const Rot<float> RB = quat2rot(q[3], q[4], q[5], q[6]), RL = quat2rot(q[13], q[14], q[15], q[16]);
+  const V3<float> pB = mk(q[0], q[1], q[2]), pL = mk(q[10], q[11], q[12]);
+  auto toF = [](const V3<float>& v) { return f3(v.x, v.y, v.z); };
+  for (int c = 0; c < 2; c++) {
+    sc.cam_o[c] = toF(pB + rot(RB, ld3(mc.cam_pos[c])));
+    const float* m = mc.cam_rot[c];   // row-major camera->base rotation
+    sc.cam_x[c] = toF(rot(RB, mk(m[0], m[3], m[6]))); sc.cam_y[c] = toF(rot(RB, mk(m[1], m[4], m[7]))); sc.cam_z[c] = toF(rot(RB, mk(m[2], m[5], m[8])));
+  }
+  Prim& b = sc.prim[0]; b.type = 0; b.c = toF(pL + rot(RL, mk(0.f, 0.f, mc.dz))); b.r = mc.ball_r; b.hl = 0.f; b.u = f3(0, 0, 1);
+  for (int w = 0; w < 3; w++) {
+    float sq, cq2; sincosf(q[7 + w], &sq, &cq2);
+    const V3<float> a = ld3(mc.ax[w]);
+    const V3<float> si = rodrigues(a, ld3(mc.s0[w]), sq, cq2), ui = rodrigues(a, ld3(mc.u0[w]), sq, cq2);
+    Prim& pr = sc.prim[1 + w]; pr.type = 1; pr.r = mc.wheel_r; pr.hl = mc.wheel_hl;
+    pr.c = toF(pB + rot(RB, ld3(mc.anc[w]) + si)); pr.u = toF(rot(RB, ui));
+  }
+  Prim& tw = sc.prim[4]; tw.type = 2; tw.r = mc.tower_r; tw.hl = mc.tower_hl; tw.c = toF(pB + rot(RB, ld3(mc.tower_c))); tw.u = toF(RB.c2);
+  for (int k = 0; k < 2; k++) {
+    Prim& pr = sc.prim[5 + k]; pr.type = 1; pr.r = mc.stick_r; pr.hl = mc.stick_hl;
+    pr.c = toF(pB + rot(RB, ld3(mc.stick_c[k]))); pr.u = toF(rot(RB, ld3(mc.stick_u[k])));
+  }
+}
+// block = (env from work list, camera); threads stride over the pixels
+template <typename T>
+__global__ void __launch_bounds__(256) k_depth(EnvParams p, DevState d, const int* __restrict__ list, const int* __restrict__ count,
+                                               int fixed_count, const T* __restrict__ cfgq, float* __restrict__ img0, float* __restrict__ img1) {
+  __shared__ Scene sc;
+  const int n = count ? *count : fixed_count;
+  const int cam = blockIdx.y;
+  const int npix = p.im_h * p.im_w;
+  for (int k = blockIdx.x; k < n; k += gridDim.x) {
+    const int env = list ? list[k] : k;
+    __syncthreads();
+    if (threadIdx.x == 0) buildScene(c_mc32, cfgq, p.N, env, sc);
+    __syncthreads();
+    const float* hf = d.hfield + (p.hf_per_env ? (size_t)env * HF_CELLS : 0);
+    float* out = (cam ? img1 : img0) + (size_t)env * npix;
+    const F3 o = sc.cam_o[cam];
+    for (int px = threadIdx.x; px < npix; px += blockDim.x) {
+      const int r = px / p.im_w, c = px - r * p.im_w;
+      const float xn = (2.f * (c + 0.5f) / p.im_w - 1.f) * ((float)p.im_w / p.im_h), yn = 1.f - 2.f * (r + 0.5f) / p.im_h;  // fovy 90
+      const F3 dir = sc.cam_x[cam] * xn + sc.cam_y[cam] * yn - sc.cam_z[cam];
+      float best = 1.0f;   // depth >= 1 is clipped to 1 (sensors/rgbd.py:74)
+#pragma unroll 1
+      for (int g = 0; g < 7; g++) { const float t = hitPrim(o, dir, sc.prim[g]); if (t > 1e-4f && t < best) best = t; }
+      const float t = hitHfield(o, dir, hf, c_mc32.hx, p.zscale, best);
+      if (t > 1e-4f && t < best) best = t;
+      out[px] = best;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------- misc kernels
+template <typename T> __global__ void k_set_state(int N, T* st, const double* qpos, const double* qvel, const double* warm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= N) return;
+  if (qpos) for (int k = 0; k < NQ; k++) st[(size_t)k * N + i] = (T)qpos[(size_t)i * NQ + k];
+  if (qvel) for (int k = 0; k < NV; k++) st[(size_t)(NQ + k) * N + i] = (T)qvel[(size_t)i * NV + k];
+  if (warm) for (int k = 0; k < NV; k++) st[(size_t)(NQ + NV + k) * N + i] = (T)warm[(size_t)i * NV + k];
+}
+template <typename T> __global__ void k_get_state(int N, const T* st, double* qpos, double* qvel, double* warm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= N) return;
+  if (qpos) for (int k = 0; k < NQ; k++) qpos[(size_t)i * NQ + k] = (double)st[(size_t)k * N + i];
+  if (qvel) for (int k = 0; k < NV; k++) qvel[(size_t)i * NV + k] = (double)st[(size_t)(NQ + k) * N + i];
+  if (warm) for (int k = 0; k < NV; k++) warm[(size_t)i * NV + k] = (double)st[(size_t)(NQ + NV + k) * N + i];
+}
+template <typename T> __global__ void k_copy_camq(int N, const T* st, T* cq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= N) return;
+  for (int k = 0; k < NQ; k++) cq[(size_t)k * N + i] = st[(size_t)k * N + i];
+}
+__global__ void k_scatter_hfield(const int* __restrict__ ids, int n, const float* __restrict__ src, float* __restrict__ dst) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)n * HF_CELLS) return;
+  const int k = (int)(t / HF_CELLS); const int cell = (int)(t - (size_t)k * HF_CELLS);
+  dst[(size_t)ids[k] * HF_CELLS + cell] = src[t];
+}
+__global__ void k_add_reward(int N, float scale, const float* __restrict__ term, bb_io io, float* ep_ret) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= N) return;
+  const float add = term[i] * scale;
+  io.reward[i] += add;
+  if (io.terminated[i]) { if (io.episode_return) io.episode_return[i] += add; } else ep_ret[i] += add;
+}
+__global__ void k_pack_obs16(int N, bb_io io, float* __restrict__ obs16) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= N) return;
+  for (int k = 0; k < 3; k++) {
+    obs16[16 * i + k] = io.orientation[3 * i + k]; obs16[16 * i + 3 + k] = io.angular_vel[3 * i + k]; obs16[16 * i + 6 + k] = io.vel[3 * i + k];
+    obs16[16 * i + 9 + k] = io.motor_state[3 * i + k]; obs16[16 * i + 12 + k] = io.actions[3 * i + k];
+  }
+  obs16[16 * i + 15] = io.rel_image_ts[i];
+}
+
+const unsigned char h_perm[256] = {
+    151, 160, 137, 91, 90, 15, 131, 13, 201, 95, 96, 53, 194, 233, 7, 225, 140, 36, 103, 30, 69, 142, 8, 99, 37, 240, 21, 10, 23,
+    190, 6, 148, 247, 120, 234, 75, 0, 26, 197, 62, 94, 252, 219, 203, 117, 35, 11, 32, 57, 177, 33, 88, 237, 149, 56, 87, 174, 20,
+    125, 136, 171, 168, 68, 175, 74, 165, 71, 134, 139, 48, 27, 166, 77, 146, 158, 231, 83, 111, 229, 122, 60, 211, 133, 230, 220,
+    105, 92, 41, 55, 46, 245, 40, 244, 102, 143, 54, 65, 25, 63, 161, 1, 216, 80, 73, 209, 76, 132, 187, 208, 89, 18, 169, 200, 196,
+    135, 130, 116, 188, 159, 86, 164, 100, 109, 198, 173, 186, 3, 64, 52, 217, 226, 250, 124, 123, 5, 202, 38, 147, 118, 126, 255,
+    82, 85, 212, 207, 206, 59, 227, 47, 16, 58, 17, 182, 189, 28, 42, 223, 183, 170, 213, 119, 248, 152, 2, 44, 154, 163, 70, 221,
+    153, 101, 155, 167, 43, 172, 9, 129, 22, 39, 253, 19, 98, 108, 110, 79, 113, 224, 232, 178, 185, 112, 104, 218, 246, 97, 228,
+    251, 34, 242, 193, 238, 210, 144, 12, 191, 179, 162, 241, 81, 51, 145, 235, 249, 14, 239, 107, 49, 192, 214, 31, 181, 199, 106,
+    157, 184, 84, 204, 176, 115, 121, 50, 45, 127, 4, 150, 254, 138, 236, 205, 93, 222, 114, 67, 29, 24, 72, 243, 141, 128, 195, 78,
+    66, 215, 61, 156, 180};
+
+char g_create_error[256] = "";
+
+}  // namespace
+
+// ================================================================================================= engine object
+struct bb_engine {
+  bb_config cfg;
+  EnvParams p;
+  DevState d;
+  int N;
+  size_t tsize;
+  int64_t launches;
+  char err[256];
+  // host-path staging (allocated lazily)
+  bool host_ready;
+  cudaStream_t hstream;
+  float *h_act, *d_act;            // pinned / device actions
+  bb_io dio;                       // device output buffers of the host path
+  float *d_obs16, *h_obs16, *h_reward, *h_pos2d, *h_term_obs, *h_epret;
+  uint8_t *h_term, *h_fail, *d_mask, *h_mask;
+  int32_t* h_eplen;
+};
+
+#define BB_CUDA(call)                                                                                         \
+  do {                                                                                                        \
+    cudaError_t _e = (call);                                                                                  \
+    if (_e != cudaSuccess) {                                                                                  \
+      snprintf(e->err, sizeof(e->err), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return BB_ERR_CUDA;                                                                                     \
+    }                                                                                                         \
+  } while (0)
+
+static int fail(bb_engine* e, int code, const char* msg) { snprintf(e->err, sizeof(e->err), "%s", msg); return code; }
+static inline int blocksFor(int n, int b) { return (n + b - 1) / b; }
+
+static int checkIo(bb_engine* e, const bb_io* io) {
+  if (!io || !io->orientation || !io->angular_vel || !io->vel || !io->motor_state || !io->actions || !io->rel_image_ts || !io->reward ||
+      !io->terminated || !io->failure || !io->pos2d)
+    return fail(e, BB_ERR_INVALID, "bb_io: required output pointer is NULL");
+  if (e->cfg.cameras && (!io->rgbd_0 || !io->rgbd_1)) return fail(e, BB_ERR_INVALID, "bb_io: rgbd_0/rgbd_1 required when cameras are enabled");
+  return BB_OK;
+}
+
+// terrain regeneration + state reset + depth refresh for whatever is in the work lists
+static int launchResetAndRender(bb_engine* e, const bb_io* io, cudaStream_t s, bool do_reset) {
+  const int N = e->N;
+  if (do_reset) {
+    if (e->cfg.terrain_type == BB_TERRAIN_PERLIN) {
+      dim3 grid(blocksFor(HF_CELLS, 256), N < 128 ? N : 128);
+      k_terrain<<<grid, 256, 0, s>>>(e->p, e->d, e->d.reset_list, e->d.counters, 0, nullptr, nullptr);
+      e->launches++;
+    }
+    if (e->cfg.precision == 64) k_reset<double><<<blocksFor(N, 128), 128, 0, s>>>(e->p, e->d, *io);
+    else k_reset<float><<<blocksFor(N, 128), 128, 0, s>>>(e->p, e->d, *io);
+    e->launches++;
+  }
+  if (e->cfg.cameras) {
+    dim3 grid(N < 148 * 8 ? N : 148 * 8, 2);
+    if (e->cfg.precision == 64) k_depth<double><<<grid, 256, 0, s>>>(e->p, e->d, e->d.refresh_list, e->d.counters + 1, 0, (const double*)e->d.camq, io->rgbd_0, io->rgbd_1);
+    else k_depth<float><<<grid, 256, 0, s>>>(e->p, e->d, e->d.refresh_list, e->d.counters + 1, 0, (const float*)e->d.camq, io->rgbd_0, io->rgbd_1);
+    e->launches++;
+  }
+  return BB_OK;
+}
+
+extern "C" {
+
+void bb_default_config(bb_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->abi_version = BB_ABI_VERSION; c->num_envs = 1; c->env_offset = 0; c->device = 0; c->precision = 64;
+  c->terrain_type = BB_TERRAIN_PERLIN; c->terrain_seed = -1;
+  c->perlin_scale = 25.f; c->perlin_octaves = 4; c->perlin_persistence = 0.2f; c->perlin_lacunarity = 2.f; c->perlin_amplitude = 1.f;
+  c->hfield_zscale = 2.f; c->cameras = 1; c->im_h = 64; c->im_w = 64; c->camera_frame_rate = 90.f;
+  c->max_ep_steps = 4000; c->max_allowed_tilt = 20.f; c->max_wheel_velocity = 10.f;
+  c->reward_type = BB_REWARD_DIRECTIONAL; c->reward_scale = 0.01f; c->action_reg_coef = -0.0001f; c->survival_bonus = 0.02f;
+  c->target_direction[0] = 0.f; c->target_direction[1] = 1.f; c->goal_position[0] = 0.f; c->goal_position[1] = 0.f; c->distance_scale = 1.f;
+  c->seed = 0; c->auto_reset = 1;
+}
+
+const char* bb_last_error(const bb_engine* e) { return e ? e->err : g_create_error; }
+int bb_num_envs(const bb_engine* e) { return e ? e->N : 0; }
+int64_t bb_launch_count(const bb_engine* e) { return e ? e->launches : 0; }
+
+int bb_model_constants(double* dA4, double* meaninertia, double* masses3) {
+  ModelConst<double> m; buildModelConst(m);
+  if (dA4) for (int i = 0; i < 4; i++) dA4[i] = m.dA[i];
+  if (meaninertia) *meaninertia = m.meaninertia;
+  if (masses3) { masses3[0] = m.m0; masses3[1] = m.mw; masses3[2] = m.mL; }
+  return BB_OK;
+}
+
+int bb_create(const bb_config* cfg, bb_engine** out) {
+  if (!cfg || !out) { snprintf(g_create_error, sizeof(g_create_error), "bb_create: NULL argument"); return BB_ERR_INVALID; }
+  *out = nullptr;
+  if (cfg->abi_version != BB_ABI_VERSION || cfg->num_envs < 1 || (cfg->precision != 32 && cfg->precision != 64) || cfg->im_h < 1 || cfg->im_w < 1 ||
+      cfg->terrain_type < 0 || cfg->terrain_type > 2 || cfg->reward_type < 0 || cfg->reward_type > 2 || cfg->camera_frame_rate <= 0.f) {
+    snprintf(g_create_error, sizeof(g_create_error), "bb_create: invalid config (abi %d, num_envs %d, precision %d)", cfg->abi_version, cfg->num_envs, cfg->precision);
+    return BB_ERR_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device) {
+    snprintf(g_create_error, sizeof(g_create_error), "bb_create: CUDA device %d not available (%d devices); this engine has no CPU fallback", cfg->device, ndev);
+    return BB_ERR_NO_DEVICE;
+  }
+  bb_engine* e = new (std::nothrow) bb_engine();
+  if (!e) return BB_ERR_INVALID;
+  memset(e, 0, sizeof(*e));
+  e->cfg = *cfg; e->N = cfg->num_envs;
+  const int N = e->N;
+  auto bail = [&](int code) { snprintf(g_create_error, sizeof(g_create_error), "%s", e->err); bb_destroy(e); return code; };
+#define BB_CUDA_C(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { snprintf(e->err, sizeof(e->err), "%s failed: %s", #call, cudaGetErrorString(_e)); return bail(BB_ERR_CUDA); } } while (0)
+  BB_CUDA_C(cudaSetDevice(cfg->device));
+  {
+    ModelConst<double> m64; buildModelConst(m64);
+    ModelConst<float> m32; narrowModel(m64, m32);
+    BB_CUDA_C(cudaMemcpyToSymbol(c_mc64, &m64, sizeof(m64)));
+    BB_CUDA_C(cudaMemcpyToSymbol(c_mc32, &m32, sizeof(m32)));
+    BB_CUDA_C(cudaMemcpyToSymbol(c_perm, h_perm, sizeof(h_perm)));
+  }
+  EnvParams& p = e->p;
+  p.N = N; p.env_offset = cfg->env_offset; p.cameras = cfg->cameras; p.im_h = cfg->im_h; p.im_w = cfg->im_w;
+  {  // camera cadence: smallest k with k*dt >= 1/frame_rate, timestamps accumulated like mjData.time (ballbot_env.py:745-750)
+    double t = 0; int k = 0; const double want = 1.0 / (double)cfg->camera_frame_rate;
+    do { t += 0.002; k++; } while (t < want && k < 100000);
+    p.cam_period = k;
+  }
+  p.max_ep_steps = cfg->max_ep_steps; p.max_tilt = cfg->max_allowed_tilt; p.max_wheel_vel = cfg->max_wheel_velocity;
+  p.reward_type = cfg->reward_type; p.reward_scale = cfg->reward_scale; p.action_reg = cfg->action_reg_coef; p.survival = cfg->survival_bonus;
+  p.tdir[0] = cfg->target_direction[0]; p.tdir[1] = cfg->target_direction[1]; p.goal[0] = cfg->goal_position[0]; p.goal[1] = cfg->goal_position[1];
+  p.dist_scale = cfg->distance_scale; p.zscale = cfg->hfield_zscale; p.terrain_type = cfg->terrain_type; p.terrain_seed = cfg->terrain_seed;
+  p.seed = cfg->seed; p.auto_reset = cfg->auto_reset; p.hf_per_env = cfg->terrain_type != BB_TERRAIN_FLAT;
+  p.pscale = cfg->perlin_scale; p.ppers = cfg->perlin_persistence; p.plac = cfg->perlin_lacunarity; p.pamp = cfg->perlin_amplitude; p.poct = cfg->perlin_octaves;
+  e->tsize = cfg->precision == 64 ? 8 : 4;
+  DevState& d = e->d;
+  BB_CUDA_C(cudaMalloc(&d.st, e->tsize * NST * N));
+  BB_CUDA_C(cudaMalloc(&d.camq, e->tsize * NQ * N));
+  BB_CUDA_C(cudaMalloc(&d.step_count, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.cam_steps, sizeof(int) * N));
+  BB_CUDA_C(cudaMalloc(&d.episode, sizeof(unsigned) * N)); BB_CUDA_C(cudaMalloc(&d.tseed, sizeof(int) * N));
+  BB_CUDA_C(cudaMalloc(&d.ep_ret, sizeof(float) * N)); BB_CUDA_C(cudaMalloc(&d.ep_len, sizeof(int) * N));
+  BB_CUDA_C(cudaMalloc(&d.counters, sizeof(int) * 2));
+  BB_CUDA_C(cudaMalloc(&d.reset_list, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.refresh_list, sizeof(int) * N));
+  const size_t hfbytes = sizeof(float) * HF_CELLS * (p.hf_per_env ? (size_t)N : 1);
+  BB_CUDA_C(cudaMalloc(&d.hfield, hfbytes));
+  BB_CUDA_C(cudaMemset(d.hfield, 0, hfbytes));
+  BB_CUDA_C(cudaMemset(d.st, 0, e->tsize * NST * N)); BB_CUDA_C(cudaMemset(d.camq, 0, e->tsize * NQ * N));
+  BB_CUDA_C(cudaMemset(d.step_count, 0, sizeof(int) * N)); BB_CUDA_C(cudaMemset(d.cam_steps, 0, sizeof(int) * N));
+  BB_CUDA_C(cudaMemset(d.episode, 0, sizeof(unsigned) * N)); BB_CUDA_C(cudaMemset(d.tseed, 0, sizeof(int) * N));
+  BB_CUDA_C(cudaMemset(d.ep_ret, 0, sizeof(float) * N)); BB_CUDA_C(cudaMemset(d.ep_len, 0, sizeof(int) * N));
+  BB_CUDA_C(cudaMemset(d.counters, 0, sizeof(int) * 2));
+  BB_CUDA_C(cudaDeviceSynchronize());
+#undef BB_CUDA_C
+  *out = e;
+  return BB_OK;
+}
+
+int bb_destroy(bb_engine* e) {
+  if (!e) return BB_OK;
+  DevState& d = e->d;
+  cudaFree(d.st); cudaFree(d.camq); cudaFree(d.step_count); cudaFree(d.cam_steps); cudaFree(d.episode); cudaFree(d.tseed);
+  cudaFree(d.ep_ret); cudaFree(d.ep_len); cudaFree(d.counters); cudaFree(d.reset_list); cudaFree(d.refresh_list); cudaFree(d.hfield);
+  if (e->host_ready) {
+    cudaFreeHost(e->h_act); cudaFree(e->d_act); cudaFree(e->d_obs16); cudaFreeHost(e->h_obs16); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_pos2d);
+    cudaFreeHost(e->h_term_obs); cudaFreeHost(e->h_epret); cudaFreeHost(e->h_term); cudaFreeHost(e->h_fail); cudaFreeHost(e->h_eplen);
+    cudaFree(e->d_mask); cudaFreeHost(e->h_mask);
+    bb_io& o = e->dio;
+    cudaFree(o.orientation); cudaFree(o.angular_vel); cudaFree(o.vel); cudaFree(o.motor_state); cudaFree(o.actions); cudaFree(o.rel_image_ts);
+    cudaFree(o.rgbd_0); cudaFree(o.rgbd_1); cudaFree(o.reward); cudaFree(o.terminated); cudaFree(o.failure); cudaFree(o.pos2d);
+    cudaFree(o.terminal_obs); cudaFree(o.episode_return); cudaFree(o.episode_length); cudaFree(o.status);
+    cudaStreamDestroy(e->hstream);
+  }
+  delete e;
+  return BB_OK;
+}
+
+int bb_reset(bb_engine* e, const uint8_t* mask_dev, const bb_io* io, void* stream) {
+  if (!e) return BB_ERR_INVALID;
+  int rc = checkIo(e, io); if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int N = e->N;
+  k_clear_counters<<<1, 1, 0, s>>>(e->d);
+  k_mask_to_list<<<blocksFor(N, 256), 256, 0, s>>>(e->p, e->d, mask_dev);
+  e->launches += 2;
+  rc = launchResetAndRender(e, io, s, true); if (rc) return rc;
+  BB_CUDA(cudaGetLastError());
+  return BB_OK;
+}
+
+int bb_step(bb_engine* e, const float* actions_dev, const bb_io* io, void* stream) {
+  if (!e || !actions_dev) return e ? fail(e, BB_ERR_INVALID, "bb_step: actions is NULL") : BB_ERR_INVALID;
+  int rc = checkIo(e, io); if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int N = e->N;
+  const int bs = N >= 148 * 64 * 2 ? 64 : 32;
+  k_clear_counters<<<1, 1, 0, s>>>(e->d);
+  if (e->cfg.precision == 64) k_step<double><<<blocksFor(N, bs), bs, 0, s>>>(e->p, e->d, actions_dev, *io);
+  else k_step<float><<<blocksFor(N, bs), bs, 0, s>>>(e->p, e->d, actions_dev, *io);
+  e->launches += 2;
+  rc = launchResetAndRender(e, io, s, e->cfg.auto_reset != 0); if (rc) return rc;
+  BB_CUDA(cudaGetLastError());
+  return BB_OK;
+}
+
+int bb_add_reward(bb_engine* e, const float* term_dev, const bb_io* io, void* stream) {
+  if (!e || !term_dev) return BB_ERR_INVALID;
+  int rc = checkIo(e, io); if (rc) return rc;
+  k_add_reward<<<blocksFor(e->N, 256), 256, 0, (cudaStream_t)stream>>>(e->N, e->cfg.reward_scale, term_dev, *io, e->d.ep_ret);
+  e->launches++;
+  BB_CUDA(cudaGetLastError());
+  return BB_OK;
+}
+
+int bb_set_state(bb_engine* e, const double* qpos, const double* qvel, const double* warm, void* stream) {
+  if (!e) return BB_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream; const int N = e->N;
+  if (e->cfg.precision == 64) { k_set_state<double><<<blocksFor(N, 128), 128, 0, s>>>(N, (double*)e->d.st, qpos, qvel, warm); k_copy_camq<double><<<blocksFor(N, 128), 128, 0, s>>>(N, (const double*)e->d.st, (double*)e->d.camq); }
+  else { k_set_state<float><<<blocksFor(N, 128), 128, 0, s>>>(N, (float*)e->d.st, qpos, qvel, warm); k_copy_camq<float><<<blocksFor(N, 128), 128, 0, s>>>(N, (const float*)e->d.st, (float*)e->d.camq); }
+  e->launches += 2;
+  BB_CUDA(cudaGetLastError());
+  return BB_OK;
+}
+int bb_get_state(bb_engine* e, double* qpos, double* qvel, double* warm, void* stream) {
+  if (!e) return BB_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream; const int N = e->N;
+  if (e->cfg.precision == 64) k_get_state<double><<<blocksFor(N, 128), 128, 0, s>>>(N, (const double*)e->d.st, qpos, qvel, warm);
+  else k_get_state<float><<<blocksFor(N, 128), 128, 0, s>>>(N, (const float*)e->d.st, qpos, qvel, warm);
+  e->launches++;
+  BB_CUDA(cudaGetLastError());
+  return BB_OK;
+}
+int bb_set_hfield(bb_engine* e, const int32_t* ids, int32_t n, const float* hf, void* stream) {
+  if (!e || !ids || !hf || n < 0) return BB_ERR_INVALID;
+  if (!e->p.hf_per_env) return fail(e, BB_ERR_INVALID, "bb_set_hfield: engine was created with flat terrain (no per-env heightfields)");
+  if (n == 0) return BB_OK;
+  const size_t tot = (size_t)n * HF_CELLS;
+  k_scatter_hfield<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids, n, hf, e->d.hfield);
+  e->launches++;
+  BB_CUDA(cudaGetLastError());
+  return BB_OK;
+}
+int bb_get_hfield(bb_engine* e, int32_t env, float* out, void* stream) {
+  if (!e || !out || env < 0 || env >= e->N) return BB_ERR_INVALID;
+  const float* src = e->d.hfield + (e->p.hf_per_env ? (size_t)env * HF_CELLS : 0);
+  BB_CUDA(cudaMemcpyAsync(out, src, sizeof(float) * HF_CELLS, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return BB_OK;
+}
+int bb_get_terrain_seeds(bb_engine* e, int32_t* seeds, void* stream) {
+  if (!e || !seeds) return BB_ERR_INVALID;
+  BB_CUDA(cudaMemcpyAsync(seeds, e->d.tseed, sizeof(int) * e->N, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return BB_OK;
+}
+int bb_perlin_terrain(bb_engine* e, const int32_t* seeds, int32_t n, float* out, void* stream) {
+  if (!e || !seeds || !out || n < 1) return BB_ERR_INVALID;
+  dim3 grid(blocksFor(HF_CELLS, 256), n < 128 ? n : 128);
+  k_terrain<<<grid, 256, 0, (cudaStream_t)stream>>>(e->p, e->d, nullptr, nullptr, n, seeds, out);
+  e->launches++;
+  BB_CUDA(cudaGetLastError());
+  return BB_OK;
+}
+int bb_render_depth(bb_engine* e, float* img0, float* img1, void* stream) {
+  if (!e || !img0 || !img1) return BB_ERR_INVALID;
+  const int N = e->N; cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid(N < 148 * 8 ? N : 148 * 8, 2);
+  if (e->cfg.precision == 64) k_depth<double><<<grid, 256, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const double*)e->d.st, img0, img1);
+  else k_depth<float><<<grid, 256, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const float*)e->d.st, img0, img1);
+  e->launches++;
+  BB_CUDA(cudaGetLastError());
+  return BB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- host-buffer path
+static int hostInit(bb_engine* e) {
+  if (e->host_ready) return BB_OK;
+  const int N = e->N; const size_t npix = (size_t)e->cfg.im_h * e->cfg.im_w;
+  BB_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
+  BB_CUDA(cudaMallocHost(&e->h_act, sizeof(float) * 3 * N)); BB_CUDA(cudaMalloc(&e->d_act, sizeof(float) * 3 * N));
+  bb_io& o = e->dio; memset(&o, 0, sizeof(o));
+  BB_CUDA(cudaMalloc(&o.orientation, sizeof(float) * 3 * N)); BB_CUDA(cudaMalloc(&o.angular_vel, sizeof(float) * 3 * N));
+  BB_CUDA(cudaMalloc(&o.vel, sizeof(float) * 3 * N)); BB_CUDA(cudaMalloc(&o.motor_state, sizeof(float) * 3 * N));
+  BB_CUDA(cudaMalloc(&o.actions, sizeof(float) * 3 * N)); BB_CUDA(cudaMalloc(&o.rel_image_ts, sizeof(float) * N));
+  if (e->cfg.cameras) { BB_CUDA(cudaMalloc(&o.rgbd_0, sizeof(float) * npix * N)); BB_CUDA(cudaMalloc(&o.rgbd_1, sizeof(float) * npix * N)); }
+  BB_CUDA(cudaMalloc(&o.reward, sizeof(float) * N)); BB_CUDA(cudaMalloc(&o.terminated, N)); BB_CUDA(cudaMalloc(&o.failure, N));
+  BB_CUDA(cudaMalloc(&o.pos2d, sizeof(float) * 2 * N)); BB_CUDA(cudaMalloc(&o.terminal_obs, sizeof(float) * 16 * N));
+  BB_CUDA(cudaMalloc(&o.episode_return, sizeof(float) * N)); BB_CUDA(cudaMalloc(&o.episode_length, sizeof(int) * N));
+  BB_CUDA(cudaMalloc(&o.status, sizeof(int) * N));
+  BB_CUDA(cudaMemset(o.terminal_obs, 0, sizeof(float) * 16 * N)); BB_CUDA(cudaMemset(o.episode_return, 0, sizeof(float) * N));
+  BB_CUDA(cudaMemset(o.episode_length, 0, sizeof(int) * N));
+  BB_CUDA(cudaMalloc(&e->d_obs16, sizeof(float) * 16 * N)); BB_CUDA(cudaMallocHost(&e->h_obs16, sizeof(float) * 16 * N));
+  BB_CUDA(cudaMallocHost(&e->h_reward, sizeof(float) * N)); BB_CUDA(cudaMallocHost(&e->h_pos2d, sizeof(float) * 2 * N));
+  BB_CUDA(cudaMallocHost(&e->h_term_obs, sizeof(float) * 16 * N)); BB_CUDA(cudaMallocHost(&e->h_epret, sizeof(float) * N));
+  BB_CUDA(cudaMallocHost(&e->h_term, N)); BB_CUDA(cudaMallocHost(&e->h_fail, N)); BB_CUDA(cudaMallocHost(&e->h_eplen, sizeof(int) * N));
+  BB_CUDA(cudaMalloc(&e->d_mask, N)); BB_CUDA(cudaMallocHost(&e->h_mask, N));
+  e->host_ready = true;
+  return BB_OK;
+}
+static int hostReadback(bb_engine* e, const bb_host_io* out) {
+  const int N = e->N; cudaStream_t s = e->hstream; const bb_io& o = e->dio;
+  k_pack_obs16<<<blocksFor(N, 256), 256, 0, s>>>(N, o, e->d_obs16); e->launches++;
+  BB_CUDA(cudaMemcpyAsync(e->h_obs16, e->d_obs16, sizeof(float) * 16 * N, cudaMemcpyDeviceToHost, s));
+  BB_CUDA(cudaMemcpyAsync(e->h_reward, o.reward, sizeof(float) * N, cudaMemcpyDeviceToHost, s));
+  BB_CUDA(cudaMemcpyAsync(e->h_term, o.terminated, N, cudaMemcpyDeviceToHost, s));
+  BB_CUDA(cudaMemcpyAsync(e->h_fail, o.failure, N, cudaMemcpyDeviceToHost, s));
+  BB_CUDA(cudaMemcpyAsync(e->h_pos2d, o.pos2d, sizeof(float) * 2 * N, cudaMemcpyDeviceToHost, s));
+  if (out->terminal_obs) BB_CUDA(cudaMemcpyAsync(e->h_term_obs, o.terminal_obs, sizeof(float) * 16 * N, cudaMemcpyDeviceToHost, s));
+  if (out->episode_return) BB_CUDA(cudaMemcpyAsync(e->h_epret, o.episode_return, sizeof(float) * N, cudaMemcpyDeviceToHost, s));
+  if (out->episode_length) BB_CUDA(cudaMemcpyAsync(e->h_eplen, o.episode_length, sizeof(int) * N, cudaMemcpyDeviceToHost, s));
+  const size_t npix = (size_t)e->cfg.im_h * e->cfg.im_w;
+  if (e->cfg.cameras && out->img_0) BB_CUDA(cudaMemcpyAsync(out->img_0, o.rgbd_0, sizeof(float) * npix * N, cudaMemcpyDeviceToHost, s));
+  if (e->cfg.cameras && out->img_1) BB_CUDA(cudaMemcpyAsync(out->img_1, o.rgbd_1, sizeof(float) * npix * N, cudaMemcpyDeviceToHost, s));
+  BB_CUDA(cudaStreamSynchronize(s));
+  if (out->obs16) memcpy(out->obs16, e->h_obs16, sizeof(float) * 16 * N);
+  if (out->reward) memcpy(out->reward, e->h_reward, sizeof(float) * N);
+  if (out->terminated) memcpy(out->terminated, e->h_term, N);
+  if (out->failure) memcpy(out->failure, e->h_fail, N);
+  if (out->pos2d) memcpy(out->pos2d, e->h_pos2d, sizeof(float) * 2 * N);
+  if (out->terminal_obs) memcpy(out->terminal_obs, e->h_term_obs, sizeof(float) * 16 * N);
+  if (out->episode_return) memcpy(out->episode_return, e->h_epret, sizeof(float) * N);
+  if (out->episode_length) memcpy(out->episode_length, e->h_eplen, sizeof(int) * N);
+  return BB_OK;
+}
+int bb_step_host(bb_engine* e, const float* actions_host, const bb_host_io* out) {
+  if (!e || !actions_host || !out) return BB_ERR_INVALID;
+  int rc = hostInit(e); if (rc) return rc;
+  memcpy(e->h_act, actions_host, sizeof(float) * 3 * e->N);
+  BB_CUDA(cudaMemcpyAsync(e->d_act, e->h_act, sizeof(float) * 3 * e->N, cudaMemcpyHostToDevice, e->hstream));
+  rc = bb_step(e, e->d_act, &e->dio, e->hstream); if (rc) return rc;
+  return hostReadback(e, out);
+}
+int bb_reset_host(bb_engine* e, const uint8_t* mask_host, const bb_host_io* out) {
+  if (!e || !out) return BB_ERR_INVALID;
+  int rc = hostInit(e); if (rc) return rc;
+  const uint8_t* dm = nullptr;
+  if (mask_host) { memcpy(e->h_mask, mask_host, e->N); BB_CUDA(cudaMemcpyAsync(e->d_mask, e->h_mask, e->N, cudaMemcpyHostToDevice, e->hstream)); dm = e->d_mask; }
+  BB_CUDA(cudaMemsetAsync(e->dio.reward, 0, sizeof(float) * e->N, e->hstream));
+  BB_CUDA(cudaMemsetAsync(e->dio.terminated, 0, e->N, e->hstream)); BB_CUDA(cudaMemsetAsync(e->dio.failure, 0, e->N, e->hstream));
+  BB_CUDA(cudaMemsetAsync(e->dio.pos2d, 0, sizeof(float) * 2 * e->N, e->hstream));
+  rc = bb_reset(e, dm, &e->dio, e->hstream); if (rc) return rc;
+  return hostReadback(e, out);
+}
+
+}  // extern "C"

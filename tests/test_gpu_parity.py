@@ -1,0 +1,177 @@
+"""GPU parity tests proper: the CUDA engine, called through the C ABI (libballbot_b200.so), against the fp64 oracle.
+
+Tolerances are BASELINE.json's: single-step qpos/qvel within 1e-5 relative in fp64 mode, 1e-3 in fp32 mode; contact
+counts must match; 100-step trajectories within the drift bound stated in each test.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+QPOS0 = np.array([0, 0, 0.24, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.26, 1, 0, 0, 0], float)
+OBS_ORDER = ("orientation", "angular_vel", "vel", "motor_state", "actions", "relative_image_timestamp")
+
+
+def _engine(**kw):
+    from openballbot_rl_b200.engine import BallbotEngine
+    return BallbotEngine(**kw)
+
+
+def _obs16(eng):
+    return torch.cat([eng.obs[k] for k in OBS_ORDER], dim=1).cpu().numpy()
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(1.0, np.abs(b).max())
+
+
+def test_library_loaded_and_model_constants(oracle_mod):
+    from openballbot_rl_b200.engine import model_constants
+    mc = model_constants(); mo = oracle_mod.model_constants()
+    iw = mo["invweight0"][:, 0]
+    np.testing.assert_allclose(mc["dA"], [iw[7] + iw[4], iw[7] + iw[5], iw[7] + iw[6], iw[7]], rtol=1e-12)
+    assert abs(mc["meaninertia"] - mo["meaninertia"]) < 1e-12
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-5), (32, 1e-3)])
+def test_flat_trajectory_parity(oracle_mod, precision, tol):
+    """Flat terrain, proprio only: N envs with different action streams vs N oracle envs, 120 steps from reset."""
+    N, T = 8, 120
+    eng = _engine(num_envs=N, precision=precision, terrain="flat", cameras=False, auto_reset=False)
+    eng.reset()
+    envs = [oracle_mod.OracleEnv() for _ in range(N)]
+    for e in envs:
+        e.reset()
+    rng = np.random.default_rng(0)
+    worst_state = worst_obs = 0.0
+    for t in range(T):
+        a = np.clip(rng.normal(size=(N, 3)), -1, 1).astype(np.float32)
+        eng.step(torch.from_numpy(a).cuda())
+        qpos, qvel, warm = [x.cpu().numpy() for x in eng.get_state()]
+        obs = _obs16(eng); rew = eng.reward.cpu().numpy(); term = eng.terminated.cpu().numpy(); fail = eng.failure.cpu().numpy()
+        for i, e in enumerate(envs):
+            o, r, tm, fl, info = e.step(a[i])
+            qo, vo, wo, _ = e.get_state()
+            worst_state = max(worst_state, _rel(qpos[i], qo), _rel(qvel[i], vo))
+            worst_obs = max(worst_obs, np.abs(obs[i] - o).max(), abs(rew[i] - r))
+            if t == 0:   # single-step criterion
+                assert _rel(qpos[i], qo) < tol and _rel(qvel[i], vo) < tol
+            assert bool(term[i]) == tm and bool(fail[i]) == fl
+    # stated drift bound for the 120-step trajectory
+    bound = 1e-9 if precision == 64 else 5e-3
+    assert worst_state < bound, worst_state
+    assert worst_obs < (1e-6 if precision == 64 else 5e-3), worst_obs
+    eng.close()
+
+
+def test_random_state_single_step_parity(oracle_mod):
+    """Identical random states (contacts active), actions and warm starts: one mj_step, fp64, 1e-5 relative."""
+    N = 64
+    rng = np.random.default_rng(3)
+    eng = _engine(num_envs=N, precision=64, terrain="flat", cameras=False, auto_reset=False)
+    eng.reset()
+    qpos = np.tile(QPOS0, (N, 1)); qvel = rng.normal(size=(N, 15)) * 0.3; warm = rng.normal(size=(N, 15))
+    for i in range(N):
+        q = np.array([1, 0, 0, 0.]) + rng.normal(size=4) * 0.05; q /= np.linalg.norm(q)
+        qpos[i, 3:7] = q
+        qpos[i, 7:10] = rng.normal(size=3)
+        qpos[i, 2] = 0.24 - 0.031 + rng.uniform(-0.002, 0.002); qpos[i, 12] = 0.26 - 0.031 + rng.uniform(-0.003, 0.0)
+        qpos[i, 0:2] = rng.uniform(-0.3, 0.3, 2); qpos[i, 10:12] = qpos[i, 0:2] + rng.normal(size=2) * 0.002
+    eng.set_state(qpos, qvel, warm)
+    a = rng.uniform(-1, 1, (N, 3)).astype(np.float32)
+    eng.step(torch.from_numpy(a).cuda())
+    q1, v1, w1 = [x.cpu().numpy() for x in eng.get_state()]
+    ncon = (eng.status.cpu().numpy() >> 8)
+    e = oracle_mod.OracleEnv()
+    for i in range(N):
+        e.set_state(qpos[i], qvel[i], warm[i])
+        e.mj_step(-10.0 * a[i].astype(np.float64))
+        qo, vo, wo, _ = e.get_state()
+        assert _rel(q1[i], qo) < 1e-5 and _rel(v1[i], vo) < 1e-5 and _rel(w1[i], wo) < 1e-5, i
+    assert ncon.max() >= 4   # the batch exercised ball-terrain contacts
+    eng.close()
+
+
+def test_perlin_terrain_and_trajectory_parity(oracle_mod):
+    """On-device simplex-fBm terrain vs the oracle's restatement, then a trajectory on that terrain."""
+    N = 4
+    eng = _engine(num_envs=N, precision=64, terrain="perlin", cameras=False, auto_reset=False, seed=7)
+    eng.reset()
+    seeds = eng.terrain_seeds().cpu().numpy()
+    assert ((seeds >= 0) & (seeds < 10000)).all()
+    envs = []
+    for i in range(N):
+        hf_dev = eng.get_hfield(i).cpu().numpy()
+        hf_or = oracle_mod.perlin_terrain(seed=int(seeds[i]))
+        assert np.abs(hf_dev - hf_or).max() < 2e-5, np.abs(hf_dev - hf_or).max()
+        e = oracle_mod.OracleEnv(); e.reset(hf_dev)     # identical heightfield bits in both simulators
+        envs.append(e)
+    qpos = eng.get_state()[0].cpu().numpy()
+    for i, e in enumerate(envs):
+        np.testing.assert_allclose(qpos[i], e.get_state()[0], atol=1e-12)   # spawn height
+    rng = np.random.default_rng(1)
+    worst = 0.0
+    for t in range(150):
+        a = np.clip(rng.normal(size=(N, 3)), -1, 1).astype(np.float32)
+        eng.step(torch.from_numpy(a).cuda())
+        qpos, qvel, _ = [x.cpu().numpy() for x in eng.get_state()]
+        term = eng.terminated.cpu().numpy()
+        for i, e in enumerate(envs):
+            o, r, tm, fl, info = e.step(a[i])
+            qo, vo, _, _ = e.get_state()
+            worst = max(worst, _rel(qpos[i], qo), _rel(qvel[i], vo))
+            assert bool(term[i]) == tm
+    assert worst < 1e-8, worst
+    eng.close()
+
+
+def test_depth_raycast_parity(oracle_mod):
+    """Depth ray-cast kernel vs the oracle's CPU ray-cast on the same terrain and pose."""
+    eng = _engine(num_envs=2, precision=64, terrain="perlin", cameras=True, auto_reset=False, seed=3)
+    obs = eng.reset()
+    for i in range(2):
+        hf = eng.get_hfield(i).cpu().numpy()
+        e = oracle_mod.OracleEnv(cameras=True); e.reset(hf)
+        d0, d1 = e.depth()
+        g0 = obs["rgbd_0"][i, 0].cpu().numpy(); g1 = obs["rgbd_1"][i, 0].cpu().numpy()
+        for g, d in ((g0, d0), (g1, d1)):
+            assert g.min() > 0 and g.max() <= 1.0
+            frac_bad = (np.abs(g - d) > 1e-3).mean()    # silhouette pixels may flip surface in fp32
+            assert frac_bad < 0.01, frac_bad
+    eng.close()
+
+
+def test_auto_reset_and_episode_stats(oracle_mod):
+    """VecEnv semantics: done envs are reset in the same call, terminal obs / Monitor stats are reported."""
+    N = 256
+    eng = _engine(num_envs=N, precision=32, terrain="flat", cameras=False, auto_reset=True, max_ep_steps=50)
+    eng.reset()
+    a = torch.zeros(N, 3, device="cuda")
+    for t in range(50):
+        eng.step(a)
+    term = eng.terminated.cpu().numpy()
+    assert term.all()                                  # timeout reported as terminated (ballbot_env.py:982-985)
+    assert (eng.episode_length.cpu().numpy() == 50).all()
+    assert np.allclose(eng.episode_return.cpu().numpy(), 50 * 0.02, atol=2e-2)
+    q = eng.get_state()[0].cpu().numpy()
+    np.testing.assert_allclose(q[:, 2], 0.25, atol=1e-6)   # back at the spawn height (flat: offset 0.01)
+    assert np.abs(eng.obs["vel"].cpu().numpy()).max() == 0
+    eng.step(a)
+    assert not eng.terminated.cpu().numpy().any()
+    eng.close()
+
+
+def test_host_buffer_path_matches_device_path():
+    N = 32
+    e1 = _engine(num_envs=N, precision=32, terrain="flat", cameras=False)
+    e2 = _engine(num_envs=N, precision=32, terrain="flat", cameras=False)
+    e1.reset(); e2.reset_host()
+    rng = np.random.default_rng(0)
+    for t in range(10):
+        a = rng.uniform(-1, 1, (N, 3)).astype(np.float32)
+        e1.step(torch.from_numpy(a).cuda())
+        h = e2.step_host(a)
+    np.testing.assert_array_equal(_obs16(e1), h["obs16"])
+    np.testing.assert_array_equal(e1.reward.cpu().numpy(), h["reward"])
+    e1.close(); e2.close()
