@@ -122,6 +122,12 @@ int bb_perlin_terrain(bb_engine* e, const int32_t* seeds_dev, int32_t n_seeds, f
 /* depth ray-cast of both cameras for every env at its CURRENT state (sensors/rgbd.py:46-82), ignoring the cadence */
 int bb_render_depth(bb_engine* e, float* rgbd_0, float* rgbd_1, void* cuda_stream);
 
+/* parity probe == inspecting mjData.qacc / qacc_smooth / qfrc_smooth / ncon / solver_niter / contact[] after one
+ * mj_forward (reference call sites ballbot_env.py:525,620): out_dev double[64] = qacc[0:15], qacc_smooth[15:30],
+ * qfrc_smooth[30:45], ncon[45], niter[46], then model constants; contact dist[53], pos[53*3], frame[53*9]. */
+int bb_probe_forward(bb_engine* e, int32_t env, const double* ctrl3_dev, double* out_dev, double* cdist_dev, double* cpos_dev,
+                     double* cframe_dev, void* cuda_stream);
+
 /* Host-buffer convenience path == what SubprocVecEnv.step does for numpy callers: H2D copy of actions, bb_step,
  * D2H copy of the proprio observation block [N,16] (orientation, angular_vel, vel, motor_state, actions, rel ts),
  * reward, terminated, failure, pos2d (+ images when img_0/img_1 are non-NULL), then a stream synchronise. */

@@ -18,9 +18,11 @@
 #if defined(__CUDACC__)
 #define BB_HD __host__ __device__ __forceinline__
 #define BB_HDN __host__ __device__
+#define BB_NOINL __host__ __device__ __noinline__
 #else
 #define BB_HD inline
 #define BB_HDN
+#define BB_NOINL inline
 #endif
 
 namespace bb {
@@ -181,16 +183,18 @@ template <typename T> BB_HD V3<T> rodrigues(const V3<T>& a, const V3<T>& v, T s,
   return v * c + cross(a, v) * s + a * (dot(a, v) * ((T)1 - c));
 }
 
+template <typename T> BB_HD void normalizeQuat4(T* q) {
+  const T n = bsqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < (T)1e-15) { q[0] = (T)1; q[1] = (T)0; q[2] = (T)0; q[3] = (T)0; }
+  else { const T inv = (T)1 / n; q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv; }
+}
+template <typename T> BB_HD void normalizeQuats(T* qpos) { normalizeQuat4(qpos + 3); normalizeQuat4(qpos + 13); }
+
 // Fills s.M (packed), s.qfs (= passive - bias + actuator), geometry g, wheel capsule world frames, obs kinematics.
 template <typename T>
 BB_HD void smoothDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const T* ctrl, Scratch<T>& s, Geo<T>& g,
                           V3<T>* capC, V3<T>* capU, KinOut<T>* kin) {
-  // normalise free-joint quaternions in place (mj_kinematics does)
-  for (int o = 3; o <= 13; o += 10) {
-    T n = bsqrt(qpos[o] * qpos[o] + qpos[o + 1] * qpos[o + 1] + qpos[o + 2] * qpos[o + 2] + qpos[o + 3] * qpos[o + 3]);
-    if (n < (T)1e-15) { qpos[o] = 1; qpos[o + 1] = qpos[o + 2] = qpos[o + 3] = 0; }
-    else { T inv = (T)1 / n; qpos[o] *= inv; qpos[o + 1] *= inv; qpos[o + 2] *= inv; qpos[o + 3] *= inv; }
-  }
+  normalizeQuats(qpos);   // mj_kinematics normalises free-joint quaternions in place
   g.pB = ld3(qpos); g.pL = ld3(qpos + 10);
   g.RB = quat2rot(qpos[3], qpos[4], qpos[5], qpos[6]);
   g.RL = quat2rot(qpos[13], qpos[14], qpos[15], qpos[16]);
@@ -306,7 +310,9 @@ BB_HD void smoothDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const
 template <typename T> BB_HD void makeFrame(T* f, bool haveT1) {
   // f[0..2] normal (unit), f[3..5] optional tangent hint   (mju_makeFrame)
   V3<T> n = ld3(f), t = ld3(f + 3);
-  if (!haveT1 || dot(t, t) < (T)0.25) { t = (n.y < (T)0.5 && n.y > (T)-0.5) ? mk((T)0, (T)1, (T)0) : mk((T)0, (T)0, (T)1); }
+  const T ny = n.y;
+  const bool midY = (ny < (T)0.5) && (ny > (T)-0.5);
+  if (!haveT1 || dot(t, t) < (T)0.25) { t = midY ? mk((T)0, (T)1, (T)0) : mk((T)0, (T)0, (T)1); }
   t = t - n * dot(n, t);
   t = t * ((T)1 / bsqrt(dot(t, t)));
   st3(f + 3, t); st3(f + 6, cross(n, t));
@@ -683,7 +689,7 @@ template <typename T> struct Newton {
 
 // ---------------------------------------------------------------------------------------------- one mj_forward
 template <typename T>
-BB_HD void forwardDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const T* ctrl, const T* warm, const float* hf, T zscale,
+BB_NOINL void forwardDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const T* ctrl, const T* warm, const float* hf, T zscale,
                            Scratch<T>& s, T* qacc, KinOut<T>* kin) {
   Geo<T> g; V3<T> capC[3], capU[3];
   smoothDynamics(mc, qpos, qvel, ctrl, s, g, capC, capU, kin);
@@ -747,30 +753,30 @@ template <typename T>
 BB_HD void rk4Step(const ModelConst<T>& mc, T* qpos, T* qvel, T* warm, const T* ctrl, const float* hf, T zscale, Scratch<T>& s,
                    KinOut<T>* kin, T* qlast = nullptr) {
   const T h = mc.timestep;
-  T X[NQ + NV], dv[NV], da[NV], acc[NV], xq[NQ], xv[NV];
-  for (int i = 0; i < NQ; i++) xq[i] = qpos[i];
-  for (int i = 0; i < NV; i++) xv[i] = qvel[i];
+  // stage state (xq, xv), saved initial state (q0, v0), RK4-weighted sums of stage velocities / accelerations
+  T q0[NQ], v0[NV], xq[NQ], xv[NV], sumv[NV], suma[NV], acc[NV];
+  normalizeQuats(qpos);   // mj_kinematics normalises qpos in place during the first forward pass
+  for (int i = 0; i < NQ; i++) { q0[i] = qpos[i]; xq[i] = qpos[i]; }
+  for (int i = 0; i < NV; i++) { v0[i] = qvel[i]; xv[i] = qvel[i]; sumv[i] = (T)0; suma[i] = (T)0; acc[i] = (T)0; }
   int ncmax = 0, nit = 0;
+#pragma unroll 1
   for (int st = 0; st < 4; st++) {
     forwardDynamics(mc, xq, xv, ctrl, warm, hf, zscale, s, acc, kin);
     if (kin) { ncmax = kin->ncon > ncmax ? kin->ncon : ncmax; nit += kin->niter; }
-    if (st == 0) { for (int i = 0; i < NQ; i++) X[i] = xq[i]; for (int i = 0; i < NV; i++) X[NQ + i] = xv[i]; }
-    const T bw = (st == 0 || st == 3) ? (T)(1.0 / 6.0) : (T)(1.0 / 3.0);
-    for (int i = 0; i < NV; i++) {
-      if (st == 0) { dv[i] = bw * xv[i]; da[i] = bw * acc[i]; } else { dv[i] += bw * xv[i]; da[i] += bw * acc[i]; }
-    }
-    if (st == 3 && qlast) { for (int i = 0; i < NQ; i++) qlast[i] = xq[i]; }   // configuration the renderer sees (stale, App. C #2)
-    if (st < 3) {
-      const T a = st == 2 ? (T)1 : (T)0.5;
-      T sv[NV]; for (int i = 0; i < NV; i++) sv[i] = a * xv[i];
-      for (int i = 0; i < NQ; i++) xq[i] = X[i];
-      integratePos(xq, sv, h);
-      for (int i = 0; i < NV; i++) xv[i] = X[NQ + i] + h * a * acc[i];
+    const T bw = (st == 0 || st == 3) ? (T)(1.0 / 6.0) : (T)(1.0 / 3.0);       // RK4_B
+    for (int i = 0; i < NV; i++) { sumv[i] += bw * xv[i]; suma[i] += bw * acc[i]; }
+    if (st == 3) {
+      if (qlast) { for (int i = 0; i < NQ; i++) qlast[i] = xq[i]; }   // configuration the renderer sees (stale, App. C #2)
+    } else {
+      const T ha = (st == 2) ? h : (T)0.5 * h;                                   // RK4_A: 1/2, 1/2, 1
+      for (int i = 0; i < NQ; i++) xq[i] = q0[i];
+      integratePos(xq, xv, ha);
+      for (int i = 0; i < NV; i++) xv[i] = v0[i] + ha * acc[i];
     }
   }
-  for (int i = 0; i < NQ; i++) qpos[i] = X[i];
-  integratePos(qpos, dv, h);
-  for (int i = 0; i < NV; i++) { qvel[i] = X[NQ + i] + h * da[i]; warm[i] = acc[i]; }
+  for (int i = 0; i < NQ; i++) qpos[i] = q0[i];
+  integratePos(qpos, sumv, h);
+  for (int i = 0; i < NV; i++) { qvel[i] = v0[i] + h * suma[i]; warm[i] = acc[i]; }
   if (kin) { kin->ncon = ncmax; kin->niter = nit; }
 }
 

@@ -165,23 +165,29 @@ __global__ void k_clear_counters(DevState d) { d.counters[0] = 0; d.counters[1] 
 // --------------------------------------------------------------------------------------------- simplex fBm terrain
 __constant__ unsigned char c_perm[256];
 __device__ __forceinline__ int dperm(int i) { return c_perm[i & 255]; }
+// All arithmetic below uses unfused round-to-nearest single-precision ops (__fmul_rn/__fadd_rn/__fsub_rn are never
+// contracted into FMAs): the tiled-noise coordinates are ~1e4 where one float ulp is 1e-3, so the heights are only
+// reproducible if every rounding step matches the plain C evaluation order of noise._simplex.
+#define FM(a, b) __fmul_rn((a), (b))
+#define FA(a, b) __fadd_rn((a), (b))
+#define FS(a, b) __fsub_rn((a), (b))
 __device__ __forceinline__ float grad4(int gi, float x, float y, float z, float w) {
   // 32 gradient directions of 4-D simplex noise: one zero component (gi>>3 selects which), signs from the low bits
   const int zc = gi >> 3;
   const float s0 = (gi & 4) ? -1.f : 1.f, s1 = (gi & 2) ? -1.f : 1.f, s2 = (gi & 1) ? -1.f : 1.f;
   switch (zc) {
-    case 0: return s0 * y + s1 * z + s2 * w;
-    case 1: return s0 * x + s1 * z + s2 * w;
-    case 2: return s0 * x + s1 * y + s2 * w;
-    default: return s0 * x + s1 * y + s2 * z;
+    case 0: return FA(FA(FM(s0, y), FM(s1, z)), FM(s2, w));
+    case 1: return FA(FA(FM(s0, x), FM(s1, z)), FM(s2, w));
+    case 2: return FA(FA(FM(s0, x), FM(s1, y)), FM(s2, w));
+    default: return FA(FA(FM(s0, x), FM(s1, y)), FM(s2, z));
   }
 }
 __device__ float simplex4(float x, float y, float z, float w) {
   const float F4 = 0.309016994f, G4 = 0.138196601f;
-  const float sk = (x + y + z + w) * F4;
-  const float fi = floorf(x + sk), fj = floorf(y + sk), fk = floorf(z + sk), fl = floorf(w + sk);
-  const float t = (fi + fj + fk + fl) * G4;
-  const float x0 = x - (fi - t), y0 = y - (fj - t), z0 = z - (fk - t), w0 = w - (fl - t);
+  const float sk = FM(FA(FA(FA(x, y), z), w), F4);
+  const float fi = floorf(FA(x, sk)), fj = floorf(FA(y, sk)), fk = floorf(FA(z, sk)), fl = floorf(FA(w, sk));
+  const float t = FM(FA(FA(FA(fi, fj), fk), fl), G4);
+  const float x0 = FS(x, FS(fi, t)), y0 = FS(y, FS(fj, t)), z0 = FS(z, FS(fk, t)), w0 = FS(w, FS(fl, t));
   const int rx = (x0 > y0) + (x0 > z0) + (x0 > w0);
   const int ry = !(x0 > y0) + (y0 > z0) + (y0 > w0);
   const int rz = !(x0 > z0) + !(y0 > z0) + (z0 > w0);
@@ -192,15 +198,16 @@ __device__ float simplex4(float x, float y, float z, float w) {
   for (int c = 0; c < 5; c++) {
     const int thr = 4 - c;   // corner c steps along the c highest-ranked axes
     const int i1 = c == 0 ? 0 : (rx >= thr), j1 = c == 0 ? 0 : (ry >= thr), k1 = c == 0 ? 0 : (rz >= thr), l1 = c == 0 ? 0 : (rw >= thr);
-    const float xc = x0 - i1 + c * G4, yc = y0 - j1 + c * G4, zc = z0 - k1 + c * G4, wc = w0 - l1 + c * G4;
-    float tt = 0.6f - xc * xc - yc * yc - zc * zc - wc * wc;
+    const float off = FM((float)c, G4);
+    const float xc = FA(FS(x0, (float)i1), off), yc = FA(FS(y0, (float)j1), off), zc = FA(FS(z0, (float)k1), off), wc = FA(FS(w0, (float)l1), off);
+    float tt = FS(FS(FS(FS(0.6f, FM(xc, xc)), FM(yc, yc)), FM(zc, zc)), FM(wc, wc));
     if (tt >= 0.f) {
       const int gi = dperm(I + i1 + dperm(J + j1 + dperm(K + k1 + dperm(L + l1)))) & 31;
-      tt *= tt;
-      total += tt * tt * grad4(gi, xc, yc, zc, wc);
+      tt = FM(tt, tt);
+      total = FA(total, FM(FM(tt, tt), grad4(gi, xc, yc, zc, wc)));
     }
   }
-  return 27.f * total;
+  return FM(27.f, total);
 }
 // snoise2(x, y, octaves, persistence, lacunarity, repeatx=1024, repeaty=1024, base=seed): tiled branch = 4-D fBm on two circles
 __device__ float perlinHeight(int i, int j, int seed, float scale, int oct, float pers, float lac, float amp) {
@@ -208,13 +215,19 @@ __device__ float perlinHeight(int i, int j, int seed, float scale, int oct, floa
   float z = (float)seed, w = z;
   const float rr = (float)(1024.0 * 0.3183098861837907 * 0.5);
   const float yf = (float)((double)y * 2.0 / 1024.0), xf = (float)((double)x * 2.0 / 1024.0);
-  y = sinf(yf) * rr; w += cosf(yf) * rr;
-  x = sinf(xf) * rr; z += cosf(xf) * rr;
+  y = FM(sinf(yf), rr); w = FA(w, FM(cosf(yf), rr));
+  x = FM(sinf(xf), rr); z = FA(z, FM(cosf(xf), rr));
   float freq = 1.f, a = 1.f, mx = 1.f, total = simplex4(x, y, z, w);
-  for (int o = 1; o < oct; o++) { freq *= lac; a *= pers; mx += a; total += simplex4(x * freq, y * freq, z * freq, w * freq) * a; }
-  const double v = ((double)(total / mx) + 1.0) / 2.0 * (double)amp;
+  for (int o = 1; o < oct; o++) {
+    freq = FM(freq, lac); a = FM(a, pers); mx = FA(mx, a);
+    total = FA(total, FM(simplex4(FM(x, freq), FM(y, freq), FM(z, freq), FM(w, freq)), a));
+  }
+  const double v = ((double)__fdiv_rn(total, mx) + 1.0) / 2.0 * (double)amp;
   return (float)(v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v));
 }
+#undef FM
+#undef FA
+#undef FS
 // grid.x covers the cells of one heightfield, grid.y strides over the work list
 __global__ void __launch_bounds__(256) k_terrain(EnvParams p, DevState d, const int* __restrict__ list, const int* __restrict__ count,
                                                  int fixed_count, const int* __restrict__ seeds, float* __restrict__ out) {
@@ -428,6 +441,27 @@ __global__ void k_pack_obs16(int N, bb_io io, float* __restrict__ obs16) {
     obs16[16 * i + 9 + k] = io.motor_state[3 * i + k]; obs16[16 * i + 12 + k] = io.actions[3 * i + k];
   }
   obs16[16 * i + 15] = io.rel_image_ts[i];
+}
+
+// single forward-dynamics evaluation at the current state of one env: solver / contact probe for parity tests
+template <typename T> __global__ void k_probe(EnvParams p, DevState d, int env, const double* ctrl3, double* out, double* cdist, double* cpos, double* cframe) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const T* st = (const T*)d.st;
+  T qpos[NQ], qvel[NV], warm[NV], ctrl[3], qacc[NV];
+  for (int k = 0; k < NQ; k++) qpos[k] = st[(size_t)k * p.N + env];
+  for (int k = 0; k < NV; k++) { qvel[k] = st[(size_t)(NQ + k) * p.N + env]; warm[k] = st[(size_t)(NQ + NV + k) * p.N + env]; }
+  for (int k = 0; k < 3; k++) ctrl[k] = (T)ctrl3[k];
+  Scratch<T> s; KinOut<T> kin;
+  const float* hf = d.hfield + (p.hf_per_env ? (size_t)env * HF_CELLS : 0);
+  forwardDynamics(cmc<T>(), qpos, qvel, ctrl, warm, hf, (T)p.zscale, s, qacc, &kin);
+  for (int k = 0; k < NV; k++) { out[k] = (double)qacc[k]; out[15 + k] = (double)s.qas[k]; out[30 + k] = (double)s.qfs[k]; }
+  out[45] = kin.ncon; out[46] = kin.niter; out[47] = (double)cmc<T>().timestep; out[48] = cmc<T>().iterations; out[49] = cmc<T>().ls_iterations;
+  out[50] = (double)cmc<T>().meaninertia; out[51] = (double)cmc<T>().K; out[52] = (double)cmc<T>().B; out[53] = (double)cmc<T>().dA[3];
+  for (int c = 0; c < s.nc; c++) {
+    cdist[c] = (double)s.cDist[c];
+    for (int j = 0; j < 3; j++) cpos[3 * c + j] = (double)s.cP[c][j];
+    for (int j = 0; j < 9; j++) cframe[9 * c + j] = (double)s.cF[c][j];
+  }
 }
 
 const unsigned char h_perm[256] = {
@@ -706,6 +740,17 @@ int bb_render_depth(bb_engine* e, float* img0, float* img1, void* stream) {
   dim3 grid(N < 148 * 8 ? N : 148 * 8, 2);
   if (e->cfg.precision == 64) k_depth<double><<<grid, 256, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const double*)e->d.st, img0, img1);
   else k_depth<float><<<grid, 256, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const float*)e->d.st, img0, img1);
+  e->launches++;
+  BB_CUDA(cudaGetLastError());
+  return BB_OK;
+}
+
+// replaces reading mjData.contact / qacc / solver_niter after mj_forward in a debugger (parity tests): one forward-dynamics
+// evaluation for env `env` at its current state; out_dev double[64], contact arrays double[53 | 159 | 477] (device)
+int bb_probe_forward(bb_engine* e, int32_t env, const double* ctrl3_dev, double* out_dev, double* cdist_dev, double* cpos_dev, double* cframe_dev, void* stream) {
+  if (!e || env < 0 || env >= e->N || !ctrl3_dev || !out_dev || !cdist_dev || !cpos_dev || !cframe_dev) return BB_ERR_INVALID;
+  if (e->cfg.precision == 64) k_probe<double><<<1, 32, 0, (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev, cdist_dev, cpos_dev, cframe_dev);
+  else k_probe<float><<<1, 32, 0, (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev, cdist_dev, cpos_dev, cframe_dev);
   e->launches++;
   BB_CUDA(cudaGetLastError());
   return BB_OK;

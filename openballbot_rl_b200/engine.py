@@ -176,6 +176,17 @@ class BallbotEngine:
         self._check(self._L.bb_render_depth(self._h, _ptr(a), _ptr(b), self._stream()), "bb_render_depth")
         return a, b
 
+    def probe_forward(self, env, ctrl=(0.0, 0.0, 0.0)):
+        """One forward-dynamics evaluation of env ``env`` at its current state (solver / contact parity probe)."""
+        dev = self.device
+        c = torch.tensor(ctrl, dtype=torch.float64, device=dev)
+        out = torch.zeros(64, dtype=torch.float64, device=dev); cd = torch.zeros(53, dtype=torch.float64, device=dev)
+        cp = torch.zeros(53, 3, dtype=torch.float64, device=dev); cf = torch.zeros(53, 9, dtype=torch.float64, device=dev)
+        self._check(self._L.bb_probe_forward(self._h, int(env), _ptr(c), _ptr(out), _ptr(cd), _ptr(cp), _ptr(cf), self._stream()), "bb_probe_forward")
+        o = out.cpu().numpy(); n = int(o[45])
+        return dict(qacc=o[:15], qacc_smooth=o[15:30], qfrc_smooth=o[30:45], ncon=n, niter=int(o[46]), consts=o[47:54],
+                    dist=cd.cpu().numpy()[:n], pos=cp.cpu().numpy()[:n], frame=cf.cpu().numpy()[:n].reshape(n, 3, 3))
+
     @property
     def launch_count(self):
         return int(self._L.bb_launch_count(self._h))

@@ -21,6 +21,7 @@ static int fwd(const double* qpos, const double* qvel, const double* ctrl, const
   for (int i = 0; i < NV; i++) { v[i] = (T)qvel[i]; w[i] = (T)warm[i]; }
   for (int i = 0; i < 3; i++) c[i] = (T)ctrl[i];
   KinOut<T> k;
+  memset(&s, 0xFF, sizeof(s));   // poison: the GPU kernel's local scratch is uninitialised too
   forwardDynamics(model<T>(), q, v, c, w, hf, (T)zscale, s, a, &k);
   for (int i = 0; i < NV; i++) qacc[i] = a[i];
   if (M225) for (int i = 0; i < NV; i++) for (int j = 0; j < NV; j++) M225[i * NV + j] = s.M[tidx(i, j)];
@@ -43,6 +44,7 @@ static void step(double* qpos, double* qvel, double* warm, const double* ctrl, c
   for (int i = 0; i < NV; i++) { v[i] = (T)qvel[i]; w[i] = (T)warm[i]; }
   for (int i = 0; i < 3; i++) c[i] = (T)ctrl[i];
   KinOut<T> k;
+  memset(&s, 0xFF, sizeof(s));
   rk4Step(model<T>(), q, v, w, c, hf, (T)zscale, s, &k);
   for (int i = 0; i < NQ; i++) qpos[i] = q[i];
   for (int i = 0; i < NV; i++) { qvel[i] = v[i]; warm[i] = w[i]; }

@@ -104,7 +104,8 @@ def test_perlin_terrain_and_trajectory_parity(oracle_mod):
     for i in range(N):
         hf_dev = eng.get_hfield(i).cpu().numpy()
         hf_or = oracle_mod.perlin_terrain(seed=int(seeds[i]))
-        assert np.abs(hf_dev - hf_or).max() < 2e-5, np.abs(hf_dev - hf_or).max()
+        dmax = np.abs(hf_dev - hf_or).max()
+        assert dmax < 2e-6, dmax                        # float32 heights: identical up to sinf/cosf ulps
         e = oracle_mod.OracleEnv(); e.reset(hf_dev)     # identical heightfield bits in both simulators
         envs.append(e)
     qpos = eng.get_state()[0].cpu().numpy()
