@@ -60,6 +60,9 @@ typedef struct bb_config {
   float distance_scale;
   uint64_t seed;             /* base seed of the counter-based per-env terrain-seed generator */
   int32_t auto_reset;        /* 1: VecEnv semantics (done envs are reset inside bb_step) */
+  int32_t step_kernel;       /* 0: warp-per-env kernel (default); 1: thread-per-env reference mapping (cross-check) */
+  int32_t solver_mode;       /* 0: MuJoCo-faithful iteration path (every RK4 stage warm-starts from qacc_warmstart);
+                                1: fast -- stages 2..4 warm-start from the previous stage (same minimiser within tolerance) */
 } bb_config;
 
 /* Caller-owned device buffers written by bb_step / bb_reset.  Layouts follow the observation dict of
@@ -145,6 +148,11 @@ typedef struct bb_host_io {
 } bb_host_io;
 int bb_step_host(bb_engine* e, const float* actions_host, const bb_host_io* out);
 int bb_reset_host(bb_engine* e, const uint8_t* mask_host, const bb_host_io* out);
+
+/* per-kernel device timing (CUDA events on the caller's stream) of the next max_steps bb_step calls; bb_profile_end
+ * synchronises and returns the summed milliseconds of {step, terrain, reset, depth} kernels and the step count */
+int bb_profile_begin(bb_engine* e, int32_t max_steps);
+int bb_profile_end(bb_engine* e, double* ms4, int32_t* nsteps);
 
 /* number of kernel launches issued by this engine so far (bench.py's gpu_launches claim) */
 int64_t bb_launch_count(const bb_engine* e);

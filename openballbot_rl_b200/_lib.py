@@ -10,7 +10,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libballbot_b200.so")
-_SOURCES = ["bb_engine.cu", "bb_core.cuh", "bb_model.h"]
+_SOURCES = ["bb_engine.cu", "bb_core.cuh", "bb_warp.cuh", "bb_model.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 
@@ -33,7 +33,7 @@ class Config(C.Structure):
         ("max_ep_steps", C.c_int32), ("max_allowed_tilt", C.c_float), ("max_wheel_velocity", C.c_float),
         ("reward_type", C.c_int32), ("reward_scale", C.c_float), ("action_reg_coef", C.c_float),
         ("survival_bonus", C.c_float), ("target_direction", C.c_float * 2), ("goal_position", C.c_float * 2),
-        ("distance_scale", C.c_float), ("seed", C.c_uint64), ("auto_reset", C.c_int32),
+        ("distance_scale", C.c_float), ("seed", C.c_uint64), ("auto_reset", C.c_int32), ("step_kernel", C.c_int32), ("solver_mode", C.c_int32),
     ]
 
 
@@ -54,7 +54,7 @@ class HostIO(C.Structure):
 EXPORTED = ["bb_create", "bb_destroy", "bb_default_config", "bb_last_error", "bb_num_envs", "bb_reset", "bb_step",
             "bb_add_reward", "bb_set_state", "bb_get_state", "bb_set_hfield", "bb_get_hfield", "bb_get_terrain_seeds",
             "bb_perlin_terrain", "bb_render_depth", "bb_step_host", "bb_reset_host", "bb_launch_count",
-            "bb_model_constants", "bb_probe_forward"]
+            "bb_model_constants", "bb_probe_forward", "bb_profile_begin", "bb_profile_end"]
 
 
 def needs_build():
@@ -108,6 +108,8 @@ def lib():
     L.bb_reset_host.argtypes = [vp, vp, C.POINTER(HostIO)]
     L.bb_launch_count.argtypes = [vp]
     L.bb_launch_count.restype = C.c_int64
+    L.bb_profile_begin.argtypes = [vp, C.c_int32]
+    L.bb_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     L.bb_probe_forward.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp]
     L.bb_model_constants.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L

@@ -108,6 +108,7 @@ template <typename T> struct ModelConst {
   T K, B;          // solref -> stiffness / damping of aref
   T solimp[5];
   T mu[2], f1[2], f2[2], d1r[2], d2r[2];   // [0] wheel pairs, [1] hfield pair
+  T dmr[2];        // 1 / (mu^2 (1 + mu^2)): cone-zone stiffness ratio Dm / D0
   T meaninertia, timestep, grav;           // gravity = (0,0,-grav)
   T tolerance, ls_tolerance;
   // heightfield
@@ -191,10 +192,12 @@ template <typename T> BB_HD void normalizeQuat4(T* q) {
 template <typename T> BB_HD void normalizeQuats(T* qpos) { normalizeQuat4(qpos + 3); normalizeQuat4(qpos + 13); }
 
 // Fills s.M (packed), s.qfs (= passive - bias + actuator), geometry g, wheel capsule world frames, obs kinematics.
-template <typename T>
-BB_HD void smoothDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const T* ctrl, Scratch<T>& s, Geo<T>& g,
+// M (packed lower triangle, NTRI) and qfs (NV) are raw pointers so that the same code serves the thread-per-env scratch
+// and the warp-per-env shared-memory layout (ZERO_M=false: the caller has zeroed M and normalised the quaternions).
+template <typename T, bool ZERO_M = true>
+BB_HD void smoothDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const T* ctrl, T* M, T* qfs, Geo<T>& g,
                           V3<T>* capC, V3<T>* capU, KinOut<T>* kin) {
-  normalizeQuats(qpos);   // mj_kinematics normalises free-joint quaternions in place
+  if (ZERO_M) normalizeQuats(qpos);   // mj_kinematics normalises free-joint quaternions in place
   g.pB = ld3(qpos); g.pL = ld3(qpos + 10);
   g.RB = quat2rot(qpos[3], qpos[4], qpos[5], qpos[6]);
   g.RL = quat2rot(qpos[13], qpos[14], qpos[15], qpos[16]);
@@ -211,7 +214,7 @@ BB_HD void smoothDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const
   V3<T> F = (cross(w, cross(w, c0)) - gl) * mc.m0;
   V3<T> Fsum = F;
   V3<T> Tsum = cross(c0, F) + cross(w, smul(I0c, w));
-  for (int i = 0; i < NTRI; i++) s.M[i] = 0;
+  if (ZERO_M) { for (int i = 0; i < NTRI; i++) M[i] = 0; }
   T biasq[3];
   V3<T> pw[3], Lw[3];
   for (int i = 0; i < 3; i++) {
@@ -233,7 +236,7 @@ BB_HD void smoothDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const
     pw[i] = axs * mc.mw;
     const V3<T> Iwa = smul(Iw, a[i]);
     Lw[i] = Iwa + cross(ri[i], pw[i]);
-    s.M[tidx(6 + i, 6 + i)] = dot(a[i], Iwa) + mc.mw * dot(axs, axs) + mc.armature;
+    M[tidx(6 + i, 6 + i)] = dot(a[i], Iwa) + mc.mw * dot(axs, axs) + mc.armature;
     // bias (qdd = 0): classical accelerations in the rotating base frame
     const T qd = qvel[6 + i];
     const V3<T> wi = w + a[i] * qd;
@@ -246,21 +249,21 @@ BB_HD void smoothDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const
     biasq[i] = dot(a[i], cross(si[i], Fi) + Ni);
   }
   // ---- M_A
-  s.M[tidx(0, 0)] = mc.mA; s.M[tidx(1, 1)] = mc.mA; s.M[tidx(2, 2)] = mc.mA;
+  M[tidx(0, 0)] = mc.mA; M[tidx(1, 1)] = mc.mA; M[tidx(2, 2)] = mc.mA;
   {  // M[v, w_k] = d(momentum)/d(w_k) = R_B (e_k x mcA)
     const V3<T> k0 = rot(g.RB, cross(mk((T)1, (T)0, (T)0), mcA));
     const V3<T> k1 = rot(g.RB, cross(mk((T)0, (T)1, (T)0), mcA));
     const V3<T> k2 = rot(g.RB, cross(mk((T)0, (T)0, (T)1), mcA));
-    s.M[tidx(3, 0)] = k0.x; s.M[tidx(3, 1)] = k0.y; s.M[tidx(3, 2)] = k0.z;
-    s.M[tidx(4, 0)] = k1.x; s.M[tidx(4, 1)] = k1.y; s.M[tidx(4, 2)] = k1.z;
-    s.M[tidx(5, 0)] = k2.x; s.M[tidx(5, 1)] = k2.y; s.M[tidx(5, 2)] = k2.z;
+    M[tidx(3, 0)] = k0.x; M[tidx(3, 1)] = k0.y; M[tidx(3, 2)] = k0.z;
+    M[tidx(4, 0)] = k1.x; M[tidx(4, 1)] = k1.y; M[tidx(4, 2)] = k1.z;
+    M[tidx(5, 0)] = k2.x; M[tidx(5, 1)] = k2.y; M[tidx(5, 2)] = k2.z;
   }
-  s.M[tidx(3, 3)] = IA.xx; s.M[tidx(4, 4)] = IA.yy; s.M[tidx(5, 5)] = IA.zz;
-  s.M[tidx(4, 3)] = IA.xy; s.M[tidx(5, 3)] = IA.xz; s.M[tidx(5, 4)] = IA.yz;
+  M[tidx(3, 3)] = IA.xx; M[tidx(4, 4)] = IA.yy; M[tidx(5, 5)] = IA.zz;
+  M[tidx(4, 3)] = IA.xy; M[tidx(5, 3)] = IA.xz; M[tidx(5, 4)] = IA.yz;
   for (int i = 0; i < 3; i++) {
     const V3<T> pwW = rot(g.RB, pw[i]);
-    s.M[tidx(6 + i, 0)] = pwW.x; s.M[tidx(6 + i, 1)] = pwW.y; s.M[tidx(6 + i, 2)] = pwW.z;
-    s.M[tidx(6 + i, 3)] = Lw[i].x; s.M[tidx(6 + i, 4)] = Lw[i].y; s.M[tidx(6 + i, 5)] = Lw[i].z;
+    M[tidx(6 + i, 0)] = pwW.x; M[tidx(6 + i, 1)] = pwW.y; M[tidx(6 + i, 2)] = pwW.z;
+    M[tidx(6 + i, 3)] = Lw[i].x; M[tidx(6 + i, 4)] = Lw[i].y; M[tidx(6 + i, 5)] = Lw[i].z;
   }
   // ---- ball
   const V3<T> wl = ld3(qvel + 12);
@@ -269,27 +272,27 @@ BB_HD void smoothDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const
   const V3<T> FL = (cross(wl, cross(wl, d)) - glL) * mc.mL;
   const V3<T> FLw = rot(g.RL, FL);
   const V3<T> TL = cross(d, FL);
-  s.M[tidx(9, 9)] = mc.mL; s.M[tidx(10, 10)] = mc.mL; s.M[tidx(11, 11)] = mc.mL;
+  M[tidx(9, 9)] = mc.mL; M[tidx(10, 10)] = mc.mL; M[tidx(11, 11)] = mc.mL;
   {
     const V3<T> md = d * mc.mL;
     const V3<T> k0 = rot(g.RL, cross(mk((T)1, (T)0, (T)0), md));
     const V3<T> k1 = rot(g.RL, cross(mk((T)0, (T)1, (T)0), md));
     const V3<T> k2 = rot(g.RL, cross(mk((T)0, (T)0, (T)1), md));
-    s.M[tidx(12, 9)] = k0.x; s.M[tidx(12, 10)] = k0.y; s.M[tidx(12, 11)] = k0.z;
-    s.M[tidx(13, 9)] = k1.x; s.M[tidx(13, 10)] = k1.y; s.M[tidx(13, 11)] = k1.z;
-    s.M[tidx(14, 9)] = k2.x; s.M[tidx(14, 10)] = k2.y; s.M[tidx(14, 11)] = k2.z;
+    M[tidx(12, 9)] = k0.x; M[tidx(12, 10)] = k0.y; M[tidx(12, 11)] = k0.z;
+    M[tidx(13, 9)] = k1.x; M[tidx(13, 10)] = k1.y; M[tidx(13, 11)] = k1.z;
+    M[tidx(14, 9)] = k2.x; M[tidx(14, 10)] = k2.y; M[tidx(14, 11)] = k2.z;
   }
-  s.M[tidx(12, 12)] = mc.IL + mc.mL * mc.dz * mc.dz; s.M[tidx(13, 13)] = mc.IL + mc.mL * mc.dz * mc.dz; s.M[tidx(14, 14)] = mc.IL;
+  M[tidx(12, 12)] = mc.IL + mc.mL * mc.dz * mc.dz; M[tidx(13, 13)] = mc.IL + mc.mL * mc.dz * mc.dz; M[tidx(14, 14)] = mc.IL;
   // ---- qfrc_smooth = passive - bias + actuator
   const V3<T> FsW = rot(g.RB, Fsum);
-  s.qfs[0] = -FsW.x; s.qfs[1] = -FsW.y; s.qfs[2] = -FsW.z;
-  s.qfs[3] = -Tsum.x; s.qfs[4] = -Tsum.y; s.qfs[5] = -Tsum.z;
+  qfs[0] = -FsW.x; qfs[1] = -FsW.y; qfs[2] = -FsW.z;
+  qfs[3] = -Tsum.x; qfs[4] = -Tsum.y; qfs[5] = -Tsum.z;
   for (int i = 0; i < 3; i++) {
     T u = ctrl[i]; u = u > (T)10 ? (T)10 : (u < (T)-10 ? (T)-10 : u);   // ctrlrange, ballbot.xml:84-86
-    s.qfs[6 + i] = -mc.damping * qvel[6 + i] - biasq[i] + u;
+    qfs[6 + i] = -mc.damping * qvel[6 + i] - biasq[i] + u;
   }
-  s.qfs[9] = -FLw.x; s.qfs[10] = -FLw.y; s.qfs[11] = -FLw.z;
-  s.qfs[12] = -TL.x; s.qfs[13] = -TL.y; s.qfs[14] = -TL.z;
+  qfs[9] = -FLw.x; qfs[10] = -FLw.y; qfs[11] = -FLw.z;
+  qfs[12] = -TL.x; qfs[13] = -TL.y; qfs[14] = -TL.z;
   // ---- world geometry for contacts
   for (int i = 0; i < 3; i++) {
     g.aw[i] = rot(g.RB, a[i]);
@@ -692,7 +695,7 @@ template <typename T>
 BB_NOINL void forwardDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const T* ctrl, const T* warm, const float* hf, T zscale,
                            Scratch<T>& s, T* qacc, KinOut<T>* kin) {
   Geo<T> g; V3<T> capC[3], capU[3];
-  smoothDynamics(mc, qpos, qvel, ctrl, s, g, capC, capU, kin);
+  smoothDynamics(mc, qpos, qvel, ctrl, s.M, s.qfs, g, capC, capU, kin);
   // qacc_smooth = M^-1 qfrc_smooth
   for (int i = 0; i < NTRI; i++) s.H[i] = s.M[i];
   cholPacked(s.H);

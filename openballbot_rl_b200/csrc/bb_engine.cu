@@ -17,12 +17,18 @@
 
 #include "../../include/ballbot_b200.h"
 #include "bb_model.h"
+#include "bb_warp.cuh"
 
 using namespace bb;
 
 namespace {
 
+#ifndef BB_WARP_MINBLOCKS
+#define BB_WARP_MINBLOCKS 3
+#endif
 constexpr int NST = NQ + NV + NV;  // qpos, qvel, qacc_warmstart
+constexpr int SST = 48;            // per-env stride of the state array  T[N][SST] (one coalesced 384/192-byte record per env)
+constexpr int CST = 20;            // per-env stride of the camera configuration array T[N][CST]
 constexpr int HF_CELLS = HN * HN;
 
 __constant__ ModelConst<double> c_mc64;
@@ -37,12 +43,13 @@ struct EnvParams {
   int max_ep_steps; float max_tilt, max_wheel_vel;
   int reward_type; float reward_scale, action_reg, survival, tdir[2], goal[2], dist_scale;
   float zscale; int terrain_type, terrain_seed; unsigned long long seed;
-  int auto_reset, hf_per_env;
+  int auto_reset, hf_per_env, solver_mode;
   float pscale, ppers, plac, pamp; int poct;
 };
 struct DevState {
-  void* st;        // T[NST][N]
-  void* camq;      // T[NQ][N]  configuration the cameras see (last RK stage / reset state)
+  void* st;        // T[N][SST]
+  void* camq;      // T[N][CST]  configuration the cameras see (last RK stage / reset state)
+  void* gscr;      // T[N][bbw::GSCR] overflow scratch of the warp kernel (contact records beyond shared memory)
   int* step_count; int* cam_steps; unsigned* episode; int* tseed;
   float* hfield;   // [N][HF_CELLS] (hf_per_env) or [HF_CELLS]
   float* ep_ret; int* ep_len;
@@ -68,9 +75,9 @@ __global__ void __launch_bounds__(64) k_step(EnvParams p, DevState d, const floa
   T* st = (T*)d.st;
   T qpos[NQ], qvel[NV], warm[NV];
 #pragma unroll
-  for (int k = 0; k < NQ; k++) qpos[k] = st[(size_t)k * p.N + i];
+  for (int k = 0; k < NQ; k++) qpos[k] = st[(size_t)i * SST + k];
 #pragma unroll
-  for (int k = 0; k < NV; k++) { qvel[k] = st[(size_t)(NQ + k) * p.N + i]; warm[k] = st[(size_t)(NQ + NV + k) * p.N + i]; }
+  for (int k = 0; k < NV; k++) { qvel[k] = st[(size_t)i * SST + NQ + k]; warm[k] = st[(size_t)i * SST + NQ + NV + k]; }
   const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
   T ctrl[3];
   {  // ballbot_env.py:903-907
@@ -98,9 +105,9 @@ __global__ void __launch_bounds__(64) k_step(EnvParams p, DevState d, const floa
     for (int k = 0; k < NV; k++) qvel[k] = 0;
   }
 #pragma unroll
-  for (int k = 0; k < NQ; k++) st[(size_t)k * p.N + i] = qpos[k];
+  for (int k = 0; k < NQ; k++) st[(size_t)i * SST + k] = qpos[k];
 #pragma unroll
-  for (int k = 0; k < NV; k++) { st[(size_t)(NQ + k) * p.N + i] = qvel[k]; st[(size_t)(NQ + NV + k) * p.N + i] = warm[k]; }
+  for (int k = 0; k < NV; k++) { st[(size_t)i * SST + NQ + k] = qvel[k]; st[(size_t)i * SST + NQ + NV + k] = warm[k]; }
 
   // ---- observation (ballbot_env.py:772-827)
   float ob[16];
@@ -146,9 +153,120 @@ __global__ void __launch_bounds__(64) k_step(EnvParams p, DevState d, const floa
     d.reset_list[atomicAdd(&d.counters[0], 1)] = i;
   } else if (refresh) {
     T* cq = (T*)d.camq;
-    for (int k = 0; k < NQ; k++) cq[(size_t)k * p.N + i] = qlast[k];
+    for (int k = 0; k < NQ; k++) cq[(size_t)i * CST + k] = qlast[k];
     d.refresh_list[atomicAdd(&d.counters[1], 1)] = i;
   }
+}
+
+// --------------------------------------------------------------------------------------------- step, warp per env
+// 4 warps per CTA, one env per warp; solver state in dynamic shared memory (bbw::WS<T> per warp).
+template <typename T>
+__global__ void __launch_bounds__(128, BB_WARP_MINBLOCKS) k_step_warp(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (i >= p.N) return;
+  bbw::WS<T>& S = reinterpret_cast<bbw::WS<T>*>(smem_raw)[warp];
+  T* st = (T*)d.st + (size_t)i * SST;
+  // one coalesced record per env: qpos[17] qvel[15] warm[15]
+  T v0 = st[lane], v1 = lane < SST - 32 ? st[32 + lane] : (T)0;
+  bool bad = !(babs(v0) < (T)1e10) || (lane < NST - 32 && !(babs(v1) < (T)1e10));
+  bad = __any_sync(bbw::FULL, bad);
+  if (lane < NQ) S.xq[lane] = v0; else S.xv[lane - NQ] = v0;            // lanes 17..31 -> qvel[0..14]
+  if (lane < NV) S.warm[lane] = v1;                                       // record[32..46] -> warm[0..14]
+  const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
+  if (lane < 3) {  // ballbot_env.py:903-907
+    const float av = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
+    T u = (T)av * (T)p.max_wheel_vel; u = u > (T)p.max_wheel_vel ? (T)p.max_wheel_vel : (u < -(T)p.max_wheel_vel ? -(T)p.max_wheel_vel : u);
+    S.ctrl[lane] = -u;
+  }
+  __syncwarp();
+  KinOut<T> kin;
+  int cs = d.cam_steps[i] + 1;
+  bool refresh = false;
+  if (p.cameras && cs >= p.cam_period) { refresh = true; cs = 0; }
+  int status = 0;
+  if (!bad) {
+    const float* hf = d.hfield + (p.hf_per_env ? (size_t)i * HF_CELLS : 0);
+    T* gs = (T*)d.gscr + (size_t)i * bbw::GSCR;
+    T* cq = refresh ? (T*)d.camq + (size_t)i * CST : nullptr;
+    bbw::wRk4(cmc<T>(), S, hf, (T)p.zscale, gs, kin, cq, lane, p.solver_mode != 0);
+    bool b2 = (lane < NQ && !(babs(S.xq[lane]) < (T)1e10)) || (lane < NV && !(babs(S.xv[lane]) < (T)1e10));
+    bad = __any_sync(bbw::FULL, b2);
+    status = kin.ncon << 8;
+  }
+  if (bad) {
+    status |= 1;
+    kin.quatB[0] = 1; kin.quatB[1] = kin.quatB[2] = kin.quatB[3] = 0;
+    for (int k = 0; k < 3; k++) { kin.cvel_ang[k] = 0; kin.cvel_lin[k] = 0; kin.posB[k] = 0; }
+    if (lane < NV) S.xv[lane] = 0;
+    __syncwarp();
+  }
+  // write the state record back (coalesced)
+  st[lane] = lane < NQ ? S.xq[lane] : S.xv[lane - NQ];
+  if (lane < NV) st[32 + lane] = S.warm[lane];
+  // ---- observation / reward / termination: every lane evaluates the few scalars, lane 0 (or a few lanes) store
+  float ob[16];
+  proprioObs(kin, (const T*)S.xv, (T)p.max_wheel_vel, ob, ob + 3, ob + 6, ob + 9);
+  ob[12] = a0; ob[13] = a1; ob[14] = a2;
+  ob[15] = p.cameras ? (float)((double)cs * 0.002) : 0.f;
+  float r = 0.f;
+  if (p.reward_type == BB_REWARD_DIRECTIONAL) r = (ob[6] * p.tdir[0] + ob[7] * p.tdir[1]) * p.reward_scale;
+  else if (p.reward_type == BB_REWARD_DISTANCE) {
+    const float dx = p.goal[0] - (float)kin.posB[0], dy = p.goal[1] - (float)kin.posB[1];
+    r = (-p.dist_scale * sqrtf(dx * dx + dy * dy)) * p.reward_scale;
+  }
+  const float nrm = sqrtf(a0 * a0 + a1 * a1 + a2 * a2);
+  r += p.action_reg * (nrm * nrm);
+  const int sc = d.step_count[i] + 1;
+  bool term = sc >= p.max_ep_steps, fail = false;
+  const double tilt = tiltDegrees(ob);
+  if (tilt > (double)p.max_tilt || bad) { fail = true; term = true; } else r += p.survival;
+  const float eret = d.ep_ret[i] + r; const int elen = d.ep_len[i] + 1;
+  __syncwarp();
+  if (lane < 15) {   // obs block: orientation, angular_vel, vel, motor_state, actions (3 each)
+    float* dst = lane < 3 ? io.orientation : (lane < 6 ? io.angular_vel : (lane < 9 ? io.vel : (lane < 12 ? io.motor_state : io.actions)));
+    float v = ob[0];
+#pragma unroll
+    for (int k = 1; k < 15; k++) v = lane == k ? ob[k] : v;
+    dst[3 * i + lane % 3] = v;
+  }
+  if (term && io.terminal_obs && lane < 16) {
+    float v = ob[0];
+#pragma unroll
+    for (int k = 1; k < 16; k++) v = lane == k ? ob[k] : v;
+    io.terminal_obs[16 * i + lane] = v;
+  }
+  if (lane == 0) {
+    io.rel_image_ts[i] = ob[15];
+    io.reward[i] = r; io.terminated[i] = term; io.failure[i] = fail;
+    io.pos2d[2 * i] = (float)kin.posB[0]; io.pos2d[2 * i + 1] = (float)kin.posB[1];
+    if (io.status) io.status[i] = status;
+    if (term) { if (io.episode_return) io.episode_return[i] = eret; if (io.episode_length) io.episode_length[i] = elen; }
+    d.step_count[i] = sc; d.cam_steps[i] = cs; d.ep_ret[i] = eret; d.ep_len[i] = elen;
+    if (term && p.auto_reset) {
+      const unsigned ep = d.episode[i] + 1; d.episode[i] = ep;
+      d.tseed[i] = drawTerrainSeed(p, i, ep);
+      d.reset_list[atomicAdd(&d.counters[0], 1)] = i;
+    } else if (refresh) d.refresh_list[atomicAdd(&d.counters[1], 1)] = i;
+  }
+}
+// forward-dynamics probe through the warp path (same outputs as k_probe)
+template <typename T> __global__ void k_probe_warp(EnvParams p, DevState d, int env, const double* ctrl3, double* out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  bbw::WS<T>& S = reinterpret_cast<bbw::WS<T>*>(smem_raw)[0];
+  const T* st = (const T*)d.st + (size_t)env * SST;
+  if (lane < NQ) S.xq[lane] = st[lane];
+  if (lane < NV) { S.xv[lane] = st[NQ + lane]; S.warm[lane] = st[NQ + NV + lane]; }
+  if (lane < 3) S.ctrl[lane] = (T)ctrl3[lane];
+  __syncwarp();
+  KinOut<T> kin;
+  const float* hf = d.hfield + (p.hf_per_env ? (size_t)env * HF_CELLS : 0);
+  bbw::wForward(cmc<T>(), S, hf, (T)p.zscale, (T*)d.gscr + (size_t)env * bbw::GSCR, kin, lane);
+  __syncwarp();
+  if (lane < NV) { out[lane] = (double)S.qacc[lane]; out[15 + lane] = (double)S.qas[lane]; out[30 + lane] = (double)S.qfs[lane]; }
+  if (lane == 0) { out[45] = kin.ncon; out[46] = kin.niter; }
 }
 
 // explicit reset: mask -> reset list (+ new terrain seed)
@@ -256,8 +374,8 @@ __global__ void k_reset(EnvParams p, DevState d, bb_io io) {
   const double off = (double)mx * (double)p.zscale + 0.01;
   const double q0[NQ] = {0, 0, 0.24 + off, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.26 + off, 1, 0, 0, 0};
   T* st = (T*)d.st; T* cq = (T*)d.camq;
-  for (int j = 0; j < NQ; j++) { st[(size_t)j * p.N + i] = (T)q0[j]; cq[(size_t)j * p.N + i] = (T)q0[j]; }
-  for (int j = NQ; j < NST; j++) st[(size_t)j * p.N + i] = (T)0;
+  for (int j = 0; j < NQ; j++) { st[(size_t)i * SST + j] = (T)q0[j]; cq[(size_t)i * CST + j] = (T)q0[j]; }
+  for (int j = NQ; j < SST; j++) st[(size_t)i * SST + j] = (T)0;
   d.step_count[i] = 0; d.cam_steps[i] = 0; d.ep_ret[i] = 0.f; d.ep_len[i] = 0;
   // reset observation: mj_forward at rest => zero rotation vector and velocities (ballbot_env.py:634)
   for (int j = 0; j < 3; j++) {
@@ -351,8 +469,8 @@ __device__ float hitHfield(F3 o, F3 dir, const float* __restrict__ hf, float sx,
   return -1.f;
 }
 template <typename T>
-__device__ void buildScene(const ModelConst<float>& mc, const T* __restrict__ cq, int N, int i, Scene& sc) {
-  float q[NQ]; for (int k = 0; k < NQ; k++) q[k] = (float)cq[(size_t)k * N + i];
+__device__ void buildScene(const ModelConst<float>& mc, const T* __restrict__ cq, int stride, int i, Scene& sc) {
+  float q[NQ]; for (int k = 0; k < NQ; k++) q[k] = (float)cq[(size_t)i * stride + k];
   const Rot<float> RB = quat2rot(q[3], q[4], q[5], q[6]), RL = quat2rot(q[13], q[14], q[15], q[16]);
   const V3<float> pB = mk(q[0], q[1], q[2]), pL = mk(q[10], q[11], q[12]);
   auto toF = [](const V3<float>& v) { return f3(v.x, v.y, v.z); };
@@ -378,7 +496,7 @@ __device__ void buildScene(const ModelConst<float>& mc, const T* __restrict__ cq
 // block = (env from work list, camera); threads stride over the pixels
 template <typename T>
 __global__ void __launch_bounds__(256) k_depth(EnvParams p, DevState d, const int* __restrict__ list, const int* __restrict__ count,
-                                               int fixed_count, const T* __restrict__ cfgq, float* __restrict__ img0, float* __restrict__ img1) {
+                                               int fixed_count, const T* __restrict__ cfgq, int cfg_stride, float* __restrict__ img0, float* __restrict__ img1) {
   __shared__ Scene sc;
   const int n = count ? *count : fixed_count;
   const int cam = blockIdx.y;
@@ -386,7 +504,7 @@ __global__ void __launch_bounds__(256) k_depth(EnvParams p, DevState d, const in
   for (int k = blockIdx.x; k < n; k += gridDim.x) {
     const int env = list ? list[k] : k;
     __syncthreads();
-    if (threadIdx.x == 0) buildScene(c_mc32, cfgq, p.N, env, sc);
+    if (threadIdx.x == 0) buildScene(c_mc32, cfgq, cfg_stride, env, sc);
     __syncthreads();
     const float* hf = d.hfield + (p.hf_per_env ? (size_t)env * HF_CELLS : 0);
     float* out = (cam ? img1 : img0) + (size_t)env * npix;
@@ -408,19 +526,19 @@ __global__ void __launch_bounds__(256) k_depth(EnvParams p, DevState d, const in
 // --------------------------------------------------------------------------------------------- misc kernels
 template <typename T> __global__ void k_set_state(int N, T* st, const double* qpos, const double* qvel, const double* warm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= N) return;
-  if (qpos) for (int k = 0; k < NQ; k++) st[(size_t)k * N + i] = (T)qpos[(size_t)i * NQ + k];
-  if (qvel) for (int k = 0; k < NV; k++) st[(size_t)(NQ + k) * N + i] = (T)qvel[(size_t)i * NV + k];
-  if (warm) for (int k = 0; k < NV; k++) st[(size_t)(NQ + NV + k) * N + i] = (T)warm[(size_t)i * NV + k];
+  if (qpos) for (int k = 0; k < NQ; k++) st[(size_t)i * SST + k] = (T)qpos[(size_t)i * NQ + k];
+  if (qvel) for (int k = 0; k < NV; k++) st[(size_t)i * SST + NQ + k] = (T)qvel[(size_t)i * NV + k];
+  if (warm) for (int k = 0; k < NV; k++) st[(size_t)i * SST + NQ + NV + k] = (T)warm[(size_t)i * NV + k];
 }
 template <typename T> __global__ void k_get_state(int N, const T* st, double* qpos, double* qvel, double* warm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= N) return;
-  if (qpos) for (int k = 0; k < NQ; k++) qpos[(size_t)i * NQ + k] = (double)st[(size_t)k * N + i];
-  if (qvel) for (int k = 0; k < NV; k++) qvel[(size_t)i * NV + k] = (double)st[(size_t)(NQ + k) * N + i];
-  if (warm) for (int k = 0; k < NV; k++) warm[(size_t)i * NV + k] = (double)st[(size_t)(NQ + NV + k) * N + i];
+  if (qpos) for (int k = 0; k < NQ; k++) qpos[(size_t)i * NQ + k] = (double)st[(size_t)i * SST + k];
+  if (qvel) for (int k = 0; k < NV; k++) qvel[(size_t)i * NV + k] = (double)st[(size_t)i * SST + NQ + k];
+  if (warm) for (int k = 0; k < NV; k++) warm[(size_t)i * NV + k] = (double)st[(size_t)i * SST + NQ + NV + k];
 }
 template <typename T> __global__ void k_copy_camq(int N, const T* st, T* cq) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= N) return;
-  for (int k = 0; k < NQ; k++) cq[(size_t)k * N + i] = st[(size_t)k * N + i];
+  for (int k = 0; k < NQ; k++) cq[(size_t)i * CST + k] = st[(size_t)i * SST + k];
 }
 __global__ void k_scatter_hfield(const int* __restrict__ ids, int n, const float* __restrict__ src, float* __restrict__ dst) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -448,8 +566,8 @@ template <typename T> __global__ void k_probe(EnvParams p, DevState d, int env, 
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const T* st = (const T*)d.st;
   T qpos[NQ], qvel[NV], warm[NV], ctrl[3], qacc[NV];
-  for (int k = 0; k < NQ; k++) qpos[k] = st[(size_t)k * p.N + env];
-  for (int k = 0; k < NV; k++) { qvel[k] = st[(size_t)(NQ + k) * p.N + env]; warm[k] = st[(size_t)(NQ + NV + k) * p.N + env]; }
+  for (int k = 0; k < NQ; k++) qpos[k] = st[(size_t)env * SST + k];
+  for (int k = 0; k < NV; k++) { qvel[k] = st[(size_t)env * SST + NQ + k]; warm[k] = st[(size_t)env * SST + NQ + NV + k]; }
   for (int k = 0; k < 3; k++) ctrl[k] = (T)ctrl3[k];
   Scratch<T> s; KinOut<T> kin;
   const float* hf = d.hfield + (p.hf_per_env ? (size_t)env * HF_CELLS : 0);
@@ -489,6 +607,8 @@ struct bb_engine {
   size_t tsize;
   int64_t launches;
   char err[256];
+  // optional per-kernel CUDA-event timing (bb_profile_begin/end): 5 events per bb_step
+  cudaEvent_t* prof_ev; int prof_cap, prof_n;
   // host-path staging (allocated lazily)
   bool host_ready;
   cudaStream_t hstream;
@@ -520,7 +640,7 @@ static int checkIo(bb_engine* e, const bb_io* io) {
 }
 
 // terrain regeneration + state reset + depth refresh for whatever is in the work lists
-static int launchResetAndRender(bb_engine* e, const bb_io* io, cudaStream_t s, bool do_reset) {
+static int launchResetAndRender(bb_engine* e, const bb_io* io, cudaStream_t s, bool do_reset, cudaEvent_t* ev = nullptr) {
   const int N = e->N;
   if (do_reset) {
     if (e->cfg.terrain_type == BB_TERRAIN_PERLIN) {
@@ -528,16 +648,19 @@ static int launchResetAndRender(bb_engine* e, const bb_io* io, cudaStream_t s, b
       k_terrain<<<grid, 256, 0, s>>>(e->p, e->d, e->d.reset_list, e->d.counters, 0, nullptr, nullptr);
       e->launches++;
     }
+    if (ev) cudaEventRecord(ev[2], s);
     if (e->cfg.precision == 64) k_reset<double><<<blocksFor(N, 128), 128, 0, s>>>(e->p, e->d, *io);
     else k_reset<float><<<blocksFor(N, 128), 128, 0, s>>>(e->p, e->d, *io);
     e->launches++;
-  }
+  } else if (ev) cudaEventRecord(ev[2], s);
+  if (ev) cudaEventRecord(ev[3], s);
   if (e->cfg.cameras) {
     dim3 grid(N < 148 * 8 ? N : 148 * 8, 2);
-    if (e->cfg.precision == 64) k_depth<double><<<grid, 256, 0, s>>>(e->p, e->d, e->d.refresh_list, e->d.counters + 1, 0, (const double*)e->d.camq, io->rgbd_0, io->rgbd_1);
-    else k_depth<float><<<grid, 256, 0, s>>>(e->p, e->d, e->d.refresh_list, e->d.counters + 1, 0, (const float*)e->d.camq, io->rgbd_0, io->rgbd_1);
+    if (e->cfg.precision == 64) k_depth<double><<<grid, 256, 0, s>>>(e->p, e->d, e->d.refresh_list, e->d.counters + 1, 0, (const double*)e->d.camq, CST, io->rgbd_0, io->rgbd_1);
+    else k_depth<float><<<grid, 256, 0, s>>>(e->p, e->d, e->d.refresh_list, e->d.counters + 1, 0, (const float*)e->d.camq, CST, io->rgbd_0, io->rgbd_1);
     e->launches++;
   }
+  if (ev) cudaEventRecord(ev[4], s);
   return BB_OK;
 }
 
@@ -552,7 +675,7 @@ void bb_default_config(bb_config* c) {
   c->max_ep_steps = 4000; c->max_allowed_tilt = 20.f; c->max_wheel_velocity = 10.f;
   c->reward_type = BB_REWARD_DIRECTIONAL; c->reward_scale = 0.01f; c->action_reg_coef = -0.0001f; c->survival_bonus = 0.02f;
   c->target_direction[0] = 0.f; c->target_direction[1] = 1.f; c->goal_position[0] = 0.f; c->goal_position[1] = 0.f; c->distance_scale = 1.f;
-  c->seed = 0; c->auto_reset = 1;
+  c->seed = 0; c->auto_reset = 1; c->step_kernel = 0; c->solver_mode = 0;
 }
 
 const char* bb_last_error(const bb_engine* e) { return e ? e->err : g_create_error; }
@@ -594,6 +717,10 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
     BB_CUDA_C(cudaMemcpyToSymbol(c_mc64, &m64, sizeof(m64)));
     BB_CUDA_C(cudaMemcpyToSymbol(c_mc32, &m32, sizeof(m32)));
     BB_CUDA_C(cudaMemcpyToSymbol(c_perm, h_perm, sizeof(h_perm)));
+    unsigned char ti[NTRI], tj[NTRI];
+    for (int i = 0, e2 = 0; i < NV; i++) for (int j = 0; j <= i; j++, e2++) { ti[e2] = (unsigned char)i; tj[e2] = (unsigned char)j; }
+    BB_CUDA_C(cudaMemcpyToSymbol(bbw::c_tri_i, ti, sizeof(ti)));
+    BB_CUDA_C(cudaMemcpyToSymbol(bbw::c_tri_j, tj, sizeof(tj)));
   }
   EnvParams& p = e->p;
   p.N = N; p.env_offset = cfg->env_offset; p.cameras = cfg->cameras; p.im_h = cfg->im_h; p.im_w = cfg->im_w;
@@ -606,12 +733,13 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   p.reward_type = cfg->reward_type; p.reward_scale = cfg->reward_scale; p.action_reg = cfg->action_reg_coef; p.survival = cfg->survival_bonus;
   p.tdir[0] = cfg->target_direction[0]; p.tdir[1] = cfg->target_direction[1]; p.goal[0] = cfg->goal_position[0]; p.goal[1] = cfg->goal_position[1];
   p.dist_scale = cfg->distance_scale; p.zscale = cfg->hfield_zscale; p.terrain_type = cfg->terrain_type; p.terrain_seed = cfg->terrain_seed;
-  p.seed = cfg->seed; p.auto_reset = cfg->auto_reset; p.hf_per_env = cfg->terrain_type != BB_TERRAIN_FLAT;
+  p.seed = cfg->seed; p.auto_reset = cfg->auto_reset; p.solver_mode = cfg->solver_mode; p.hf_per_env = cfg->terrain_type != BB_TERRAIN_FLAT;
   p.pscale = cfg->perlin_scale; p.ppers = cfg->perlin_persistence; p.plac = cfg->perlin_lacunarity; p.pamp = cfg->perlin_amplitude; p.poct = cfg->perlin_octaves;
   e->tsize = cfg->precision == 64 ? 8 : 4;
   DevState& d = e->d;
-  BB_CUDA_C(cudaMalloc(&d.st, e->tsize * NST * N));
-  BB_CUDA_C(cudaMalloc(&d.camq, e->tsize * NQ * N));
+  BB_CUDA_C(cudaMalloc(&d.st, e->tsize * SST * N));
+  BB_CUDA_C(cudaMalloc(&d.camq, e->tsize * CST * N));
+  BB_CUDA_C(cudaMalloc(&d.gscr, e->tsize * (size_t)bbw::GSCR * N));
   BB_CUDA_C(cudaMalloc(&d.step_count, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.cam_steps, sizeof(int) * N));
   BB_CUDA_C(cudaMalloc(&d.episode, sizeof(unsigned) * N)); BB_CUDA_C(cudaMalloc(&d.tseed, sizeof(int) * N));
   BB_CUDA_C(cudaMalloc(&d.ep_ret, sizeof(float) * N)); BB_CUDA_C(cudaMalloc(&d.ep_len, sizeof(int) * N));
@@ -620,7 +748,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   const size_t hfbytes = sizeof(float) * HF_CELLS * (p.hf_per_env ? (size_t)N : 1);
   BB_CUDA_C(cudaMalloc(&d.hfield, hfbytes));
   BB_CUDA_C(cudaMemset(d.hfield, 0, hfbytes));
-  BB_CUDA_C(cudaMemset(d.st, 0, e->tsize * NST * N)); BB_CUDA_C(cudaMemset(d.camq, 0, e->tsize * NQ * N));
+  BB_CUDA_C(cudaMemset(d.st, 0, e->tsize * SST * N)); BB_CUDA_C(cudaMemset(d.camq, 0, e->tsize * CST * N));
   BB_CUDA_C(cudaMemset(d.step_count, 0, sizeof(int) * N)); BB_CUDA_C(cudaMemset(d.cam_steps, 0, sizeof(int) * N));
   BB_CUDA_C(cudaMemset(d.episode, 0, sizeof(unsigned) * N)); BB_CUDA_C(cudaMemset(d.tseed, 0, sizeof(int) * N));
   BB_CUDA_C(cudaMemset(d.ep_ret, 0, sizeof(float) * N)); BB_CUDA_C(cudaMemset(d.ep_len, 0, sizeof(int) * N));
@@ -634,8 +762,9 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
 int bb_destroy(bb_engine* e) {
   if (!e) return BB_OK;
   DevState& d = e->d;
-  cudaFree(d.st); cudaFree(d.camq); cudaFree(d.step_count); cudaFree(d.cam_steps); cudaFree(d.episode); cudaFree(d.tseed);
+  cudaFree(d.st); cudaFree(d.camq); cudaFree(d.gscr); cudaFree(d.step_count); cudaFree(d.cam_steps); cudaFree(d.episode); cudaFree(d.tseed);
   cudaFree(d.ep_ret); cudaFree(d.ep_len); cudaFree(d.counters); cudaFree(d.reset_list); cudaFree(d.refresh_list); cudaFree(d.hfield);
+  if (e->prof_ev) { for (int i = 0; i < 5 * e->prof_cap; i++) cudaEventDestroy(e->prof_ev[i]); free(e->prof_ev); }
   if (e->host_ready) {
     cudaFreeHost(e->h_act); cudaFree(e->d_act); cudaFree(e->d_obs16); cudaFreeHost(e->h_obs16); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_pos2d);
     cudaFreeHost(e->h_term_obs); cudaFreeHost(e->h_epret); cudaFreeHost(e->h_term); cudaFreeHost(e->h_fail); cudaFreeHost(e->h_eplen);
@@ -669,11 +798,21 @@ int bb_step(bb_engine* e, const float* actions_dev, const bb_io* io, void* strea
   cudaStream_t s = (cudaStream_t)stream;
   const int N = e->N;
   const int bs = N >= 148 * 64 * 2 ? 64 : 32;
+  cudaEvent_t* ev = nullptr;
+  if (e->prof_ev && e->prof_n < e->prof_cap) { ev = e->prof_ev + 5 * (size_t)e->prof_n; e->prof_n++; }
   k_clear_counters<<<1, 1, 0, s>>>(e->d);
-  if (e->cfg.precision == 64) k_step<double><<<blocksFor(N, bs), bs, 0, s>>>(e->p, e->d, actions_dev, *io);
-  else k_step<float><<<blocksFor(N, bs), bs, 0, s>>>(e->p, e->d, actions_dev, *io);
+  if (ev) cudaEventRecord(ev[0], s);
+  if (e->cfg.step_kernel == 1) {   // thread-per-env reference mapping
+    if (e->cfg.precision == 64) k_step<double><<<blocksFor(N, bs), bs, 0, s>>>(e->p, e->d, actions_dev, *io);
+    else k_step<float><<<blocksFor(N, bs), bs, 0, s>>>(e->p, e->d, actions_dev, *io);
+  } else {                         // warp-per-env (default)
+    const int wpb = 4;
+    if (e->cfg.precision == 64) k_step_warp<double><<<blocksFor(N, wpb), wpb * 32, wpb * sizeof(bbw::WS<double>), s>>>(e->p, e->d, actions_dev, *io);
+    else k_step_warp<float><<<blocksFor(N, wpb), wpb * 32, wpb * sizeof(bbw::WS<float>), s>>>(e->p, e->d, actions_dev, *io);
+  }
+  if (ev) cudaEventRecord(ev[1], s);
   e->launches += 2;
-  rc = launchResetAndRender(e, io, s, e->cfg.auto_reset != 0); if (rc) return rc;
+  rc = launchResetAndRender(e, io, s, e->cfg.auto_reset != 0, ev); if (rc) return rc;
   BB_CUDA(cudaGetLastError());
   return BB_OK;
 }
@@ -738,8 +877,8 @@ int bb_render_depth(bb_engine* e, float* img0, float* img1, void* stream) {
   if (!e || !img0 || !img1) return BB_ERR_INVALID;
   const int N = e->N; cudaStream_t s = (cudaStream_t)stream;
   dim3 grid(N < 148 * 8 ? N : 148 * 8, 2);
-  if (e->cfg.precision == 64) k_depth<double><<<grid, 256, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const double*)e->d.st, img0, img1);
-  else k_depth<float><<<grid, 256, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const float*)e->d.st, img0, img1);
+  if (e->cfg.precision == 64) k_depth<double><<<grid, 256, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const double*)e->d.st, SST, img0, img1);
+  else k_depth<float><<<grid, 256, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const float*)e->d.st, SST, img0, img1);
   e->launches++;
   BB_CUDA(cudaGetLastError());
   return BB_OK;
@@ -749,10 +888,39 @@ int bb_render_depth(bb_engine* e, float* img0, float* img1, void* stream) {
 // evaluation for env `env` at its current state; out_dev double[64], contact arrays double[53 | 159 | 477] (device)
 int bb_probe_forward(bb_engine* e, int32_t env, const double* ctrl3_dev, double* out_dev, double* cdist_dev, double* cpos_dev, double* cframe_dev, void* stream) {
   if (!e || env < 0 || env >= e->N || !ctrl3_dev || !out_dev || !cdist_dev || !cpos_dev || !cframe_dev) return BB_ERR_INVALID;
-  if (e->cfg.precision == 64) k_probe<double><<<1, 32, 0, (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev, cdist_dev, cpos_dev, cframe_dev);
-  else k_probe<float><<<1, 32, 0, (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev, cdist_dev, cpos_dev, cframe_dev);
+  if (e->cfg.step_kernel == 1) {
+    if (e->cfg.precision == 64) k_probe<double><<<1, 32, 0, (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev, cdist_dev, cpos_dev, cframe_dev);
+    else k_probe<float><<<1, 32, 0, (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev, cdist_dev, cpos_dev, cframe_dev);
+  } else {   // warp path: accelerations / counts only (contact arrays are left untouched)
+    if (e->cfg.precision == 64) k_probe_warp<double><<<1, 32, sizeof(bbw::WS<double>), (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev);
+    else k_probe_warp<float><<<1, 32, sizeof(bbw::WS<float>), (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev);
+  }
   e->launches++;
   BB_CUDA(cudaGetLastError());
+  return BB_OK;
+}
+
+// per-kernel device timing of the next `max_steps` bb_step calls (CUDA events on the caller's stream)
+int bb_profile_begin(bb_engine* e, int32_t max_steps) {
+  if (!e || max_steps < 1) return BB_ERR_INVALID;
+  if (e->prof_ev) { for (int i = 0; i < 5 * e->prof_cap; i++) cudaEventDestroy(e->prof_ev[i]); free(e->prof_ev); e->prof_ev = nullptr; }
+  e->prof_ev = (cudaEvent_t*)malloc(sizeof(cudaEvent_t) * 5 * (size_t)max_steps);
+  if (!e->prof_ev) return fail(e, BB_ERR_INVALID, "bb_profile_begin: out of host memory");
+  for (int i = 0; i < 5 * max_steps; i++) BB_CUDA(cudaEventCreate(&e->prof_ev[i]));
+  e->prof_cap = max_steps; e->prof_n = 0;
+  return BB_OK;
+}
+// ms4 = total milliseconds spent in {k_step, k_terrain, k_reset, k_depth} over the profiled steps; synchronises
+int bb_profile_end(bb_engine* e, double* ms4, int32_t* nsteps) {
+  if (!e || !e->prof_ev || !ms4) return BB_ERR_INVALID;
+  double acc[4] = {0, 0, 0, 0};
+  if (e->prof_n > 0) BB_CUDA(cudaEventSynchronize(e->prof_ev[5 * (size_t)(e->prof_n - 1) + 4]));
+  for (int k = 0; k < e->prof_n; k++)
+    for (int j = 0; j < 4; j++) { float ms = 0.f; BB_CUDA(cudaEventElapsedTime(&ms, e->prof_ev[5 * (size_t)k + j], e->prof_ev[5 * (size_t)k + j + 1])); acc[j] += ms; }
+  for (int j = 0; j < 4; j++) ms4[j] = acc[j];
+  if (nsteps) *nsteps = e->prof_n;
+  for (int i = 0; i < 5 * e->prof_cap; i++) cudaEventDestroy(e->prof_ev[i]);
+  free(e->prof_ev); e->prof_ev = nullptr; e->prof_cap = e->prof_n = 0;
   return BB_OK;
 }
 

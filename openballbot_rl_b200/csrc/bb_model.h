@@ -71,6 +71,7 @@ inline void buildModelConst(ModelConst<double>& mc) {
     mc.d1r[k] = impratio;                                                   // R_t1 = R_n / impratio
     mc.d2r[k] = mc.d1r[k] * (mc.f2[k] * mc.f2[k]) / (mc.f1[k] * mc.f1[k]);  // R_t2 = R_t1 mu1^2 / mu2^2
     mc.mu[k] = mc.f1[k] * std::sqrt(1.0 / impratio);                        // regularised cone
+    mc.dmr[k] = 1.0 / (mc.mu[k] * mc.mu[k] * (1.0 + mc.mu[k] * mc.mu[k]));
   }
   mc.hx = 5.0; mc.hbase = 0.1;
   // ---- base group: tower cylinder + ballast box + two camera sticks (cone meshes: file missing, density 1 -> dropped)
@@ -129,7 +130,7 @@ inline void buildModelConst(ModelConst<double>& mc) {
     static Scratch<double> s;   // large; setup only
     Geo<double> ge; V3<double> cC[3], cU[3];
     double qpos[NQ] = {0, 0, 0.24, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.26, 1, 0, 0, 0}, qvel[NV] = {0}, ctrl[3] = {0, 0, 0};
-    smoothDynamics(mc, qpos, qvel, ctrl, s, ge, cC, cU, (KinOut<double>*)nullptr);
+    smoothDynamics(mc, qpos, qvel, ctrl, s.M, s.qfs, ge, cC, cU, (KinOut<double>*)nullptr);
     double tr = 0; for (int i = 0; i < NV; i++) tr += s.M[tidx(i, i)];
     mc.meaninertia = tr / NV;
     for (int i = 0; i < NTRI; i++) s.H[i] = s.M[i];

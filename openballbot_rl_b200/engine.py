@@ -25,7 +25,7 @@ class BallbotEngine:
                  cameras=True, im_h=64, im_w=64, camera_frame_rate=90.0, max_ep_steps=4000, max_allowed_tilt=20.0,
                  max_wheel_velocity=10.0, reward="directional", reward_scale=0.01, action_reg_coef=-0.0001,
                  survival_bonus=0.02, target_direction=(0.0, 1.0), goal_position=(0.0, 0.0), distance_scale=1.0, seed=0,
-                 auto_reset=True, env_offset=0):
+                 auto_reset=True, env_offset=0, step_kernel="warp", solver="exact"):
         if not torch.cuda.is_available():
             raise EngineError("BallbotEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
         L = _lib.lib()
@@ -45,6 +45,8 @@ class BallbotEngine:
         cfg.target_direction[0], cfg.target_direction[1] = float(target_direction[0]), float(target_direction[1])
         cfg.goal_position[0], cfg.goal_position[1] = float(goal_position[0]), float(goal_position[1])
         cfg.distance_scale = float(distance_scale); cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF; cfg.auto_reset = int(bool(auto_reset))
+        cfg.step_kernel = {"warp": 0, "thread": 1}[step_kernel]
+        cfg.solver_mode = {"exact": 0, "fast": 1}[solver]
         self.cfg = cfg
         self._L = L
         self._h = C.c_void_p()
@@ -186,6 +188,14 @@ class BallbotEngine:
         o = out.cpu().numpy(); n = int(o[45])
         return dict(qacc=o[:15], qacc_smooth=o[15:30], qfrc_smooth=o[30:45], ncon=n, niter=int(o[46]), consts=o[47:54],
                     dist=cd.cpu().numpy()[:n], pos=cp.cpu().numpy()[:n], frame=cf.cpu().numpy()[:n].reshape(n, 3, 3))
+
+    def profile_begin(self, max_steps):
+        self._check(self._L.bb_profile_begin(self._h, int(max_steps)), "bb_profile_begin")
+
+    def profile_end(self):
+        ms = (C.c_double * 4)(); n = C.c_int32()
+        self._check(self._L.bb_profile_end(self._h, ms, C.byref(n)), "bb_profile_end")
+        return dict(step_ms=ms[0], terrain_ms=ms[1], reset_ms=ms[2], depth_ms=ms[3], steps=n.value)
 
     @property
     def launch_count(self):
