@@ -1,0 +1,10 @@
+"""Drop-in alias of the hot-path part of the reference's ``ballbot_rl`` package: ``ballbot_rl.training.utils``
+(make_ballbot_env, reference ballbot_rl/training/utils.py:11-85) backed by the B200 engine."""
+import importlib
+import sys
+
+for _alias, _real in {"ballbot_rl.training": "openballbot_rl_b200.training",
+                      "ballbot_rl.training.utils": "openballbot_rl_b200.training.utils"}.items():
+    _mod = importlib.import_module(_real)
+    sys.modules[_alias] = _mod
+training = sys.modules["ballbot_rl.training"]

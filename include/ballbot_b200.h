@@ -122,6 +122,10 @@ int bb_get_terrain_seeds(bb_engine* e, int32_t* seeds_dev, void* cuda_stream);
 
 /* on-device replacement of generate_perlin_terrain (terrain/perlin.py:8-74): out float[n_seeds,293*293] */
 int bb_perlin_terrain(bb_engine* e, const int32_t* seeds_dev, int32_t n_seeds, float* out_dev, void* cuda_stream);
+/* engine-independent, host-in/host-out variant for arbitrary n == the registry callable `perlin`
+ * (ComponentRegistry.get_terrain("perlin")(n, **cfg), terrain/__init__.py:19): out_host float[nseeds, n*n] */
+int bb_perlin_grid(int32_t device, int32_t n, float scale, int32_t octaves, float persistence, float lacunarity, float amplitude,
+                   const int32_t* seeds_host, int32_t nseeds, float* out_host);
 /* depth ray-cast of both cameras for every env at its CURRENT state (sensors/rgbd.py:46-82), ignoring the cadence */
 int bb_render_depth(bb_engine* e, float* rgbd_0, float* rgbd_1, void* cuda_stream);
 

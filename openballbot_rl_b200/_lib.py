@@ -54,7 +54,7 @@ class HostIO(C.Structure):
 EXPORTED = ["bb_create", "bb_destroy", "bb_default_config", "bb_last_error", "bb_num_envs", "bb_reset", "bb_step",
             "bb_add_reward", "bb_set_state", "bb_get_state", "bb_set_hfield", "bb_get_hfield", "bb_get_terrain_seeds",
             "bb_perlin_terrain", "bb_render_depth", "bb_step_host", "bb_reset_host", "bb_launch_count",
-            "bb_model_constants", "bb_probe_forward", "bb_profile_begin", "bb_profile_end"]
+            "bb_model_constants", "bb_probe_forward", "bb_profile_begin", "bb_profile_end", "bb_perlin_grid"]
 
 
 def needs_build():
@@ -108,6 +108,7 @@ def lib():
     L.bb_reset_host.argtypes = [vp, vp, C.POINTER(HostIO)]
     L.bb_launch_count.argtypes = [vp]
     L.bb_launch_count.restype = C.c_int64
+    L.bb_perlin_grid.argtypes = [C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float, vp, C.c_int32, vp]
     L.bb_profile_begin.argtypes = [vp, C.c_int32]
     L.bb_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     L.bb_probe_forward.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp]

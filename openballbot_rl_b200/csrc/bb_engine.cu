@@ -361,6 +361,15 @@ __global__ void __launch_bounds__(256) k_terrain(EnvParams p, DevState d, const 
   }
 }
 
+// general n x n grid (registry callable `perlin`, terrain/perlin.py:8-74 at arbitrary n)
+__global__ void __launch_bounds__(256) k_perlin_grid(int n, float scale, int oct, float pers, float lac, float amp, const int* __restrict__ seeds,
+                                                      int nseeds, float* __restrict__ out) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= n * n) return;
+  const int r = cell / n, c = cell - r * n;
+  for (int k = blockIdx.y; k < nseeds; k += gridDim.y) out[(size_t)k * n * n + cell] = perlinHeight(r, c, seeds[k], scale, oct, pers, lac, amp);
+}
+
 // --------------------------------------------------------------------------------------------- reset
 template <typename T>
 __global__ void k_reset(EnvParams p, DevState d, bb_io io) {
@@ -898,6 +907,28 @@ int bb_probe_forward(bb_engine* e, int32_t env, const double* ctrl3_dev, double*
   e->launches++;
   BB_CUDA(cudaGetLastError());
   return BB_OK;
+}
+
+// host-in / host-out Perlin heightfields for arbitrary n (plugin-API callable): replaces generate_perlin_terrain
+int bb_perlin_grid(int32_t device, int32_t n, float scale, int32_t octaves, float persistence, float lacunarity, float amplitude,
+                   const int32_t* seeds_host, int32_t nseeds, float* out_host) {
+  if (n < 1 || nseeds < 1 || !seeds_host || !out_host || octaves < 1) return BB_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) { snprintf(g_create_error, sizeof(g_create_error), "bb_perlin_grid: CUDA device %d not available; no CPU fallback", device); return BB_ERR_NO_DEVICE; }
+  if (cudaSetDevice(device) != cudaSuccess) return BB_ERR_CUDA;
+  if (cudaMemcpyToSymbol(c_perm, h_perm, sizeof(h_perm)) != cudaSuccess) return BB_ERR_CUDA;
+  int* dseeds = nullptr; float* dout = nullptr; const size_t cells = (size_t)n * n;
+  int rc = BB_OK;
+  if (cudaMalloc(&dseeds, sizeof(int) * nseeds) != cudaSuccess || cudaMalloc(&dout, sizeof(float) * cells * nseeds) != cudaSuccess) rc = BB_ERR_CUDA;
+  if (rc == BB_OK && cudaMemcpy(dseeds, seeds_host, sizeof(int) * nseeds, cudaMemcpyHostToDevice) != cudaSuccess) rc = BB_ERR_CUDA;
+  if (rc == BB_OK) {
+    dim3 grid((unsigned)((cells + 255) / 256), nseeds < 128 ? nseeds : 128);
+    k_perlin_grid<<<grid, 256>>>(n, scale, octaves, persistence, lacunarity, amplitude, dseeds, nseeds, dout);
+    if (cudaMemcpy(out_host, dout, sizeof(float) * cells * nseeds, cudaMemcpyDeviceToHost) != cudaSuccess) rc = BB_ERR_CUDA;
+  }
+  cudaFree(dseeds); cudaFree(dout);
+  if (rc != BB_OK) snprintf(g_create_error, sizeof(g_create_error), "bb_perlin_grid: CUDA error %s", cudaGetErrorString(cudaGetLastError()));
+  return rc;
 }
 
 // per-kernel device timing of the next `max_steps` bb_step calls (CUDA events on the caller's stream)

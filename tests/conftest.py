@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on a B200 with -m gpu)")
+    config.addinivalue_line("markers", "slow: takes more than a few seconds on the CPU")
 
 
 @pytest.fixture(scope="session")

@@ -1,0 +1,111 @@
+"""The engine's own physics core (openballbot_rl_b200/csrc/bb_core.cuh), compiled for the CPU by tests/hostcore, against
+the oracle: two independent formulations (base-local classical Newton-Euler + matrix-free contacts vs MuJoCo-shaped
+c-frame spatial algebra + dense efc_J) must agree to rounding.  This is the no-GPU half of the parity story; the GPU
+half (tests/test_gpu_parity.py) runs the same core inside the CUDA kernels."""
+import numpy as np
+import pytest
+
+from tests.hostcore import hostcore as H
+
+QPOS0 = np.array([0, 0, 0.24, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.26, 1, 0, 0, 0], float)
+
+
+def _rot(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def _contact_state(rng, pen):
+    qpos = QPOS0.copy()
+    q = np.array([1, 0, 0, 0.]) + rng.normal(size=4) * 0.05; q /= np.linalg.norm(q); qpos[3:7] = q
+    qpos[7:10] = rng.normal(size=3)
+    ql = rng.normal(size=4); ql /= np.linalg.norm(ql); qpos[13:17] = ql
+    xy = rng.uniform(-0.5, 0.5, 2)
+    bc = np.array([xy[0], xy[1], 0.09 - pen])
+    qpos[10:13] = bc - _rot(ql) @ np.array([0, 0, -0.14])
+    qpos[0:3] = bc - _rot(q) @ (np.array([0, 0, -0.12]) + rng.normal(size=3) * 0.002)
+    return qpos, rng.normal(size=15) * 0.3
+
+
+def test_model_constants_agree(oracle_mod):
+    mo, mh = oracle_mod.model_constants(), H.model()
+    iw = mo["invweight0"][:, 0]
+    np.testing.assert_allclose(mh["dA"], [iw[7] + iw[4], iw[7] + iw[5], iw[7] + iw[6], iw[7]], rtol=1e-12)
+    assert abs(mh["meaninertia"] - mo["meaninertia"]) < 1e-13
+    np.testing.assert_allclose(mh["masses"], [mo["mass"][1:4].sum(), mo["mass"][4], mo["mass"][7]], rtol=1e-13)
+
+
+def test_smooth_dynamics_agree_without_contacts(oracle_mod):
+    rng = np.random.default_rng(0)
+    e = oracle_mod.OracleEnv()
+    for _ in range(10):
+        qpos = QPOS0.copy(); qpos[2] += 1.0; qpos[12] += 2.0
+        q = rng.normal(size=4); qpos[3:7] = q / np.linalg.norm(q)
+        q = rng.normal(size=4); qpos[13:17] = q / np.linalg.norm(q)
+        qpos[7:10] = rng.normal(size=3) * 3
+        qvel = rng.normal(size=15); ctrl = rng.uniform(-12, 12, 3)          # beyond ctrlrange: both must clamp to +-10
+        e.set_state(qpos, qvel); fo = e.forward(ctrl)
+        fh = H.forward(qpos, qvel, ctrl, np.zeros(15))
+        assert fo["ncon"] == 0 and fh["ncon"] == 0
+        np.testing.assert_allclose(fh["qM"], fo["qM"], atol=1e-13)
+        np.testing.assert_allclose(fh["qfs"], fo["qM"] @ fo["qacc_smooth"], atol=1e-11)
+        np.testing.assert_allclose(fh["qacc"], fo["qacc"], rtol=1e-10, atol=1e-10)
+
+
+def test_contacts_and_newton_agree(oracle_mod):
+    rng = np.random.default_rng(1)
+    e = oracle_mod.OracleEnv()
+    seen = set()
+    for t in range(60):
+        qpos, qvel = _contact_state(rng, rng.uniform(0, 0.004))
+        ctrl = rng.uniform(-10, 10, 3); warm = rng.normal(size=15) * (t % 2)
+        e.set_state(qpos, qvel, warm); fo = e.forward(ctrl); co = e.contacts()
+        fh = H.forward(qpos, qvel, ctrl, warm)
+        pen = co["dist"] < 0
+        assert fh["ncon"] == pen.sum()                                       # contact sets match
+        np.testing.assert_allclose(fh["dist"], co["dist"][pen], atol=1e-14)
+        np.testing.assert_allclose(fh["pos"], co["pos"][pen], atol=1e-14)
+        np.testing.assert_allclose(fh["frame"], co["frame"][pen], atol=1e-12)
+        assert fh["niter"] == fo["niter"]
+        assert np.abs(fh["qacc"] - fo["qacc"]).max() / np.abs(fo["qacc"]).max() < 1e-10
+        seen.add(int(fh["ncon"]))
+    assert max(seen) >= 9                                                    # 3 wheel pairs + several terrain prisms
+
+
+@pytest.mark.parametrize("terrain", ["flat", "perlin"])
+def test_rk4_trajectory_agrees(oracle_mod, terrain):
+    """100-step drift bound: 1e-10 absolute in fp64; fp32 arithmetic stays within 2e-3 (BASELINE: 1e-3 single step)."""
+    rng = np.random.default_rng(2)
+    hf = None if terrain == "flat" else oracle_mod.perlin_terrain(seed=123)
+    e = oracle_mod.OracleEnv(); e.reset(hf)
+    s64 = e.get_state()[:3]; s32 = s64
+    first32 = None
+    for k in range(100):
+        ctrl = -10 * np.clip(rng.normal(size=3), -1, 1)
+        e.mj_step(ctrl)
+        s64 = H.step(*s64, ctrl, hf, prec=64)[:3]
+        s32 = H.step(*s32, ctrl, hf, prec=32)[:3]
+        qo, vo, wo, _ = e.get_state()
+        assert max(np.abs(qo - s64[0]).max(), np.abs(vo - s64[1]).max()) < 1e-10, k
+        if k == 0:
+            first32 = max(np.abs(qo - s32[0]).max() / max(1, np.abs(qo).max()), np.abs(vo - s32[1]).max() / max(1, np.abs(vo).max()))
+    assert first32 < 1e-3
+    assert max(np.abs(qo - s32[0]).max(), np.abs(vo - s32[1]).max()) < 2e-3 * max(1.0, np.abs(vo).max())
+
+
+def test_stale_observation_kinematics(oracle_mod):
+    """obs kinematics come from the LAST RK4 stage evaluation, not from the returned state."""
+    e = oracle_mod.OracleEnv(); e.reset()
+    rng = np.random.default_rng(3)
+    s = e.get_state()[:3]
+    for _ in range(30):
+        ctrl = rng.uniform(-10, 10, 3)
+        e.mj_step(ctrl)
+        q, v, w, kin, _, _ = H.step(*s, ctrl, None, prec=64); s = (q, v, w)
+    xpos, xquat, cvel = e.kin()
+    np.testing.assert_allclose(kin[0:4], xquat, atol=1e-12)
+    np.testing.assert_allclose(kin[4:7], cvel[0:3], atol=1e-11)             # "vel" <- cvel[0:3] (angular)
+    np.testing.assert_allclose(kin[7:10], cvel[3:6], atol=1e-11)            # "angular_vel" <- cvel[3:6] (linear, at subtree COM)
+    np.testing.assert_allclose(kin[10:13], xpos, atol=1e-12)
+    assert np.abs(xquat - q[3:7]).max() > 1e-9                               # and it really is stale w.r.t. the new qpos

@@ -1,0 +1,145 @@
+"""The CPU oracle itself: model constants against the reference's MJCF-derived figures, physical
+invariants, env semantics of ballbot_env.py, and the reference-recorded random-policy statistics (the statistical pin)."""
+import numpy as np
+import pytest
+
+QPOS0 = np.array([0, 0, 0.24, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0.26, 1, 0, 0, 0], float)
+
+
+def test_model_constants_match_mjcf(oracle_mod):
+    mc = oracle_mod.model_constants()
+    # masses derived from ballbot.xml densities: tower 0.2512 + ballast 3.2, stick 0.0670, wheel 0.0893, ball 0.1679
+    np.testing.assert_allclose(mc["mass"][1], 0.2512 + 3.2, atol=2e-4)
+    np.testing.assert_allclose(mc["mass"][2:4], 0.0670, atol=1e-4)
+    np.testing.assert_allclose(mc["mass"][4:7], 0.0893, atol=1e-4)
+    np.testing.assert_allclose(mc["mass"][7], 0.1679, atol=1e-4)
+    np.testing.assert_allclose(mc["inertia"][7], np.eye(3) * 5.44e-4, atol=1e-6)
+    assert mc["meaninertia"] > 0 and (mc["invweight0"][1:] > 0).all()
+
+
+def test_initial_wheel_penetration_and_contacts(oracle_mod):
+    """At qpos0 each wheel capsule penetrates the ball by ~1.05 cm and the ball floats 3 cm above ground."""
+    e = oracle_mod.OracleEnv()
+    e.set_state(QPOS0, np.zeros(15))
+    f = e.forward(np.zeros(3))
+    c = e.contacts()
+    assert f["ncon"] == 3 and set(c["pair"]) == {0, 1, 2}
+    np.testing.assert_allclose(c["dist"], -0.010494, atol=2e-5)
+    for fr in c["frame"]:
+        np.testing.assert_allclose(fr @ fr.T, np.eye(3), atol=1e-12)       # orthonormal contact frames
+    # patched frame (tools/mujoco_fix.patch): tangent-1 is the capsule axis made orthogonal to the normal
+    axis0 = np.array([0.1564, 0.6984, 0.6984])
+    t1 = c["frame"][0][1]
+    assert abs(abs(t1 @ (axis0 - (axis0 @ c["frame"][0][0]) * c["frame"][0][0]) / np.linalg.norm(axis0 - (axis0 @ c["frame"][0][0]) * c["frame"][0][0])) - 1) < 1e-3
+
+
+def test_free_fall_matches_gravity(oracle_mod):
+    """No contacts: both free bodies accelerate at -g exactly, RK4 integrates the parabola exactly."""
+    e = oracle_mod.OracleEnv()
+    q = QPOS0.copy(); q[2] += 2.0; q[12] += 1.0; q[10] = 1.0     # separate ball and base, far above the ground
+    e.set_state(q, np.zeros(15))
+    f = e.forward(np.zeros(3))
+    assert f["ncon"] == 0
+    np.testing.assert_allclose(f["qacc"][[2, 11]], -9.81, atol=1e-9)
+    for _ in range(50):
+        e.mj_step(np.zeros(3))
+    qp, qv, _, t = e.get_state()
+    np.testing.assert_allclose(qv[2], -9.81 * t, atol=1e-9)
+    np.testing.assert_allclose(qp[2], q[2] - 0.5 * 9.81 * t * t, atol=1e-9)
+
+
+def test_mass_matrix_is_spd_and_block_diagonal(oracle_mod):
+    e = oracle_mod.OracleEnv(); e.reset()
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        e.step(rng.uniform(-1, 1, 3).astype(np.float32))
+    M = e.forward()["qM"]
+    np.testing.assert_allclose(M, M.T, atol=1e-14)
+    assert np.linalg.eigvalsh(M).min() > 0
+    assert np.abs(M[:9, 9:]).max() == 0                                   # base+wheels tree and ball tree are decoupled
+    np.testing.assert_allclose(np.diag(M)[6:9], 0.005 + 2.5e-5, atol=5e-6)   # wheel armature + axial inertia
+
+
+def test_newton_solution_satisfies_kkt(oracle_mod):
+    """At the solver's answer the gradient M a - qfrc_smooth - J' f vanishes to the solver tolerance."""
+    e = oracle_mod.OracleEnv(); e.reset()
+    rng = np.random.default_rng(1)
+    for _ in range(120):
+        e.step(rng.uniform(-1, 1, 3).astype(np.float32))
+    f = e.forward(np.array([2.0, -3.0, 1.0]))
+    efc = e.efc()
+    assert efc["n"] >= 9
+    grad = f["qM"] @ (f["qacc"] - f["qacc_smooth"]) - efc["J"].T @ efc["force"]
+    assert np.abs(grad).max() < 1e-5 * max(1.0, np.abs(f["qM"] @ f["qacc"]).max())
+    assert (efc["force"][0::3] >= -1e-12).all()                           # normal forces push, never pull
+
+
+def test_env_semantics(oracle_mod):
+    e = oracle_mod.OracleEnv(max_ep_steps=30)
+    obs = e.reset()
+    assert not obs.any()                                                   # reset observation: everything at rest
+    qp = e.get_state()[0]
+    np.testing.assert_allclose(qp[[2, 12]], [0.25, 0.27], atol=1e-12)     # flat: spawn offset = 0 * zscale + 0.01
+    a = np.array([0.5, -1.5, 0.25], np.float32)                           # unclipped incoming action (penalty uses it)
+    o, r, term, fail, info = e.step(a)
+    np.testing.assert_allclose(o[12:15], a)
+    exp = np.float32(np.float32(o[6] * 0 + o[7] * 1) * np.float32(0.01)) + np.float32(-0.0001) * np.float32(np.linalg.norm(a) ** 2) + np.float32(0.02)
+    assert abs(r - exp) < 1e-7
+    for _ in range(29):
+        o, r, term, fail, info = e.step(np.zeros(3, np.float32))
+    assert term and not fail and info[2] == 30                            # timeout is reported as terminated (ballbot_env.py:982)
+
+
+def test_spawn_offset_window(oracle_mod):
+    hf = np.zeros((293, 293), np.float32)
+    hf[139, 146] = 0.9; hf[152, 146] = 0.9                                # just outside rows 140..151
+    assert abs(oracle_mod.spawn_offset(hf) - 0.01) < 1e-12
+    hf[151, 140] = 0.25
+    assert abs(oracle_mod.spawn_offset(hf) - (0.25 * 2.0 + 0.01)) < 1e-7
+
+
+def test_perlin_terrain_properties(oracle_mod):
+    a = oracle_mod.perlin_terrain(seed=42); b = oracle_mod.perlin_terrain(seed=42); c = oracle_mod.perlin_terrain(seed=43)
+    assert a.shape == (293 * 293,) and a.min() >= 0 and a.max() <= 1
+    np.testing.assert_array_equal(a, b)
+    assert np.abs(a - c).max() > 0.05                                     # seeds select different noise slices
+    g = a.reshape(293, 293)
+    assert np.abs(np.diff(g, axis=0)).max() < 0.05                        # smooth at the cell scale (feature size ~25 cells)
+
+
+def test_depth_render_geometry(oracle_mod):
+    """Flat ground, robot at rest: both cameras look down-inwards; ground depth matches the camera height geometry."""
+    e = oracle_mod.OracleEnv(cameras=True); e.reset()
+    d0, d1 = e.depth()
+    assert d0.shape == (64, 64) and 0 < d0.min() and d0.max() <= 1.0
+    assert (np.abs(d0 - d1[:, ::-1]) < 2e-3).mean() > 0.9                 # mirror-image cameras (the 3 wheels break exact symmetry)
+    # camera height above the ground: 0.25 - 0.06 = 0.19 m; the ground is visible within the 1 m clip
+    assert 0.15 < np.median(d0) < 0.45
+    obs, *_ = e.step(np.zeros(3, np.float32))
+    assert abs(obs[15] - 0.002) < 1e-7                                    # relative_image_timestamp after one step
+
+
+@pytest.mark.slow
+def test_random_policy_statistics_match_reference_records(oracle_mod):
+    """Statistical pin: the reference's first PPO rollout (N(0,1)-clipped actions, 10 envs, 20,480 steps) recorded
+    ep_len_mean 446.1 / ep_rew_mean 8.887 on flat terrain and 157.8 / 3.186 on perlin (progress.csv:2 of the four
+    archived 2025-12-0x runs).  The oracle must reproduce them within sampling error."""
+    e = oracle_mod.OracleEnv()
+    rng = np.random.default_rng(10)
+    out = {}
+    for terrain, n_ep in (("flat", 30), ("perlin", 40)):
+        lens, rets = [], []
+        for ep in range(n_ep):
+            e.reset(None if terrain == "flat" else oracle_mod.perlin_terrain(seed=int(rng.integers(0, 10000))))
+            G, n = 0.0, 0
+            while True:
+                _, r, term, _, _ = e.step(np.clip(rng.normal(size=3), -1, 1).astype(np.float32))
+                G += r; n += 1
+                if term:
+                    break
+            lens.append(n); rets.append(G)
+        out[terrain] = (np.mean(lens), np.std(lens) / np.sqrt(n_ep), np.mean(rets))
+    assert abs(out["flat"][0] - 446.1) < 4 * out["flat"][1] + 10, out
+    assert abs(out["flat"][2] - 8.887) < 1.0, out
+    assert abs(out["perlin"][0] - 157.8) < 4 * out["perlin"][1] + 8, out
+    assert abs(out["perlin"][2] - 3.186) < 0.6, out
