@@ -24,7 +24,7 @@ def test_vec_env_torch_protocol_and_auto_reset():
     ts_seen = set()
     for t in range(25):
         obs, rew, dones, info = venv.step(torch.zeros(N, 3, device="cuda"))
-        ts_seen.update(np.round(obs["relative_image_timestamp"].cpu().numpy().ravel(), 4).tolist())
+        ts_seen.update(np.round(obs["relative_image_timestamp"].cpu().numpy().ravel().astype(np.float64), 4).tolist())
     assert ts_seen <= {0.0, 0.002, 0.004, 0.006, 0.008, 0.01} and len(ts_seen) == 6     # 6-step camera cadence
     assert bool(dones.all()) and (info["episode_l"] <= 25).all()
     assert float(obs["relative_image_timestamp"].abs().max()) == 0.0                  # done envs were reset in the same call
