@@ -122,6 +122,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default 65536 perlin / 4096 flat)")
     ap.add_argument("--precision", type=int, default=64, choices=[32, 64])
     ap.add_argument("--preroll", type=int, default=-1, help="untimed steps that desynchronise the episodes (default 300 perlin / 0 flat)")
+    ap.add_argument("--solver", default="exact", choices=["exact", "fast"], help="exact: MuJoCo-faithful iteration path; fast: chained warm start + inexact line search")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -134,7 +135,7 @@ def main():
     workload_name = ("perlin uneven terrain + ball-hfield contacts + depth raycast 2x64x64 every 6th step, terrain regen on reset"
                      if args.workload == "perlin" else "flat terrain, proprioceptive obs only")
     config = {"workload": f"{workload_name}; {envs} envs/GPU (BASELINE.json configs[{2 if args.workload == 'perlin' else 1}])",
-              "envs_per_gpu": envs, "physics": f"fp{args.precision}", "integrator": "RK4 dt=0.002", "actions": "U(-1,1)^3 device RNG seed 0",
+              "envs_per_gpu": envs, "physics": f"fp{args.precision}", "solver": args.solver, "integrator": "RK4 dt=0.002", "actions": "U(-1,1)^3 device RNG seed 0",
               "parallelism": f"env-sharded x{world}, no collective on the step path"}
     cores = os.cpu_count() or 1
 
@@ -178,7 +179,7 @@ def main():
 
     perlin = args.workload == "perlin"
     eng = BallbotEngine(num_envs=envs, device=local_rank, precision=args.precision, terrain="perlin" if perlin else "flat",
-                        cameras=perlin, auto_reset=True, seed=0, env_offset=rank * envs)
+                        cameras=perlin, auto_reset=True, seed=0, env_offset=rank * envs, solver=args.solver)
     gen = torch.Generator(device=dev); gen.manual_seed(rank)
     n_act = 64
     act = (torch.rand(n_act, envs, 3, device=dev, generator=gen) * 2 - 1).contiguous()   # U(-1,1)^3, pre-generated on device

@@ -23,8 +23,11 @@ using namespace bb;
 
 namespace {
 
+#ifndef BB_WPB
+#define BB_WPB 1          // warps (= envs) per CTA of the step kernel; 1 avoids waiting for the slowest env of a CTA
+#endif
 #ifndef BB_WARP_MINBLOCKS
-#define BB_WARP_MINBLOCKS 3
+#define BB_WARP_MINBLOCKS (12 / BB_WPB)
 #endif
 constexpr int NST = NQ + NV + NV;  // qpos, qvel, qacc_warmstart
 constexpr int SST = 48;            // per-env stride of the state array  T[N][SST] (one coalesced 384/192-byte record per env)
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(64) k_step(EnvParams p, DevState d, const floa
 // --------------------------------------------------------------------------------------------- step, warp per env
 // 4 warps per CTA, one env per warp; solver state in dynamic shared memory (bbw::WS<T> per warp).
 template <typename T>
-__global__ void __launch_bounds__(128, BB_WARP_MINBLOCKS) k_step_warp(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io) {
+__global__ void __launch_bounds__(32 * BB_WPB, BB_WARP_MINBLOCKS) k_step_warp(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -263,7 +266,7 @@ template <typename T> __global__ void k_probe_warp(EnvParams p, DevState d, int 
   __syncwarp();
   KinOut<T> kin;
   const float* hf = d.hfield + (p.hf_per_env ? (size_t)env * HF_CELLS : 0);
-  bbw::wForward(cmc<T>(), S, hf, (T)p.zscale, (T*)d.gscr + (size_t)env * bbw::GSCR, kin, lane);
+  bbw::wForward(cmc<T>(), S, hf, (T)p.zscale, (T*)d.gscr + (size_t)env * bbw::GSCR, kin, lane, p.solver_mode != 0);
   __syncwarp();
   if (lane < NV) { out[lane] = (double)S.qacc[lane]; out[15 + lane] = (double)S.qas[lane]; out[30 + lane] = (double)S.qfs[lane]; }
   if (lane == 0) { out[45] = kin.ncon; out[46] = kin.niter; }
@@ -403,7 +406,7 @@ __device__ __forceinline__ F3 operator*(F3 a, float s) { return f3(a.x * s, a.y 
 __device__ __forceinline__ float fdot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ F3 fcross(F3 a, F3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 struct Prim { F3 c, u; float r, hl; int type; };  // type 0 sphere, 1 capsule, 2 cylinder
-struct Scene { F3 cam_o[2]; F3 cam_x[2], cam_y[2], cam_z[2]; Prim prim[7]; };
+struct Scene { F3 cam_o[2]; F3 cam_x[2], cam_y[2], cam_z[2]; Prim prim[7]; float brad2[7]; };
 
 __device__ __forceinline__ float hitSphere(F3 o, F3 dir, F3 c, float rad) {
   const F3 oc = o - c; const float a = fdot(dir, dir), b = fdot(oc, dir), cc = fdot(oc, oc) - rad * rad;
@@ -467,12 +470,16 @@ __device__ float hitHfield(F3 o, F3 dir, const float* __restrict__ hf, float sx,
   float tcur = t0;
   for (int it = 0; it < 4 * n; it++) {
     if (cx < 0 || cx > n - 2 || cy < 0 || cy > n - 2 || tcur > t1) return -1.f;
-    const float x0 = -sx + cx * dx, y0 = -sx + cy * dx;
-    const F3 v00 = f3(x0, y0, hf[cy * n + cx] * sz), v10 = f3(x0 + dx, y0, hf[cy * n + cx + 1] * sz);
-    const F3 v01 = f3(x0, y0 + dx, hf[(cy + 1) * n + cx] * sz), v11 = f3(x0 + dx, y0 + dx, hf[(cy + 1) * n + cx + 1] * sz);
-    const float ta = hitTri(o, dir, v01, v00, v11), tb = hitTri(o, dir, v00, v11, v10);
-    float best = -1.f; if (ta > 0.f) best = ta; if (tb > 0.f && (best < 0.f || tb < best)) best = tb;
-    if (best > 0.f && best <= tmax) return best;
+    const float h00 = hf[cy * n + cx] * sz, h10 = hf[cy * n + cx + 1] * sz, h01 = hf[(cy + 1) * n + cx] * sz, h11 = hf[(cy + 1) * n + cx + 1] * sz;
+    const float texit = fminf(fminf(tmx, tmy), t1);
+    const float zlow = fminf(o.z + tcur * dir.z, o.z + texit * dir.z);       // lowest point of the ray inside this cell
+    if (zlow <= fmaxf(fmaxf(h00, h10), fmaxf(h01, h11))) {                    // otherwise the ray passes above both triangles
+      const float x0 = -sx + cx * dx, y0 = -sx + cy * dx;
+      const F3 v00 = f3(x0, y0, h00), v10 = f3(x0 + dx, y0, h10), v01 = f3(x0, y0 + dx, h01), v11 = f3(x0 + dx, y0 + dx, h11);
+      const float ta = hitTri(o, dir, v01, v00, v11), tb = hitTri(o, dir, v00, v11, v10);
+      float best = -1.f; if (ta > 0.f) best = ta; if (tb > 0.f && (best < 0.f || tb < best)) best = tb;
+      if (best > 0.f && best <= tmax) return best;
+    }
     if (tmx < tmy) { cx += stx; tcur = tmx; tmx += tdx; } else { cy += sty; tcur = tmy; tmy += tdy; }
   }
   return -1.f;
@@ -501,6 +508,11 @@ __device__ void buildScene(const ModelConst<float>& mc, const T* __restrict__ cq
     Prim& pr = sc.prim[5 + k]; pr.type = 1; pr.r = mc.stick_r; pr.hl = mc.stick_hl;
     pr.c = toF(pB + rot(RB, ld3(mc.stick_c[k]))); pr.u = toF(rot(RB, ld3(mc.stick_u[k])));
   }
+  for (int g = 0; g < 7; g++) {   // squared bounding-sphere radii (sphere r, capsule hl + r, cylinder sqrt(r^2 + hl^2)), 1 mm slack
+    const Prim& pr = sc.prim[g];
+    const float br = pr.type == 0 ? pr.r : (pr.type == 1 ? pr.hl + pr.r : sqrtf(pr.r * pr.r + pr.hl * pr.hl));
+    sc.brad2[g] = (br + 1e-3f) * (br + 1e-3f);
+  }
 }
 // block = (env from work list, camera); threads stride over the pixels
 template <typename T>
@@ -522,9 +534,16 @@ __global__ void __launch_bounds__(256) k_depth(EnvParams p, DevState d, const in
       const int r = px / p.im_w, c = px - r * p.im_w;
       const float xn = (2.f * (c + 0.5f) / p.im_w - 1.f) * ((float)p.im_w / p.im_h), yn = 1.f - 2.f * (r + 0.5f) / p.im_h;  // fovy 90
       const F3 dir = sc.cam_x[cam] * xn + sc.cam_y[cam] * yn - sc.cam_z[cam];
+      const float inv_dd = 1.f / fdot(dir, dir);
       float best = 1.0f;   // depth >= 1 is clipped to 1 (sensors/rgbd.py:74)
 #pragma unroll 1
-      for (int g = 0; g < 7; g++) { const float t = hitPrim(o, dir, sc.prim[g]); if (t > 1e-4f && t < best) best = t; }
+      for (int g = 0; g < 7; g++) {
+        const Prim& pr = sc.prim[g];
+        const F3 oc = pr.c - o; const float along = fdot(oc, dir) * inv_dd;   // bounding-sphere reject before the exact test
+        const F3 perp = oc - dir * along;
+        if (fdot(perp, perp) > sc.brad2[g]) continue;
+        const float t = hitPrim(o, dir, pr); if (t > 1e-4f && t < best) best = t;
+      }
       const float t = hitHfield(o, dir, hf, c_mc32.hx, p.zscale, best);
       if (t > 1e-4f && t < best) best = t;
       out[px] = best;
@@ -815,7 +834,7 @@ int bb_step(bb_engine* e, const float* actions_dev, const bb_io* io, void* strea
     if (e->cfg.precision == 64) k_step<double><<<blocksFor(N, bs), bs, 0, s>>>(e->p, e->d, actions_dev, *io);
     else k_step<float><<<blocksFor(N, bs), bs, 0, s>>>(e->p, e->d, actions_dev, *io);
   } else {                         // warp-per-env (default)
-    const int wpb = 4;
+    const int wpb = BB_WPB;
     if (e->cfg.precision == 64) k_step_warp<double><<<blocksFor(N, wpb), wpb * 32, wpb * sizeof(bbw::WS<double>), s>>>(e->p, e->d, actions_dev, *io);
     else k_step_warp<float><<<blocksFor(N, wpb), wpb * 32, wpb * sizeof(bbw::WS<float>), s>>>(e->p, e->d, actions_dev, *io);
   }

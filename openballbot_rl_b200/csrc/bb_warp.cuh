@@ -60,6 +60,7 @@ template <typename T> __device__ __noinline__ void wCholSolve(T* A, T* col, cons
     const int e = lane + 32 * m, ee = e < NTRI ? e : 0;
     ei[m] = c_tri_i[ee]; ej[m] = e < NTRI ? c_tri_j[ee] : 99; a[m] = A[ee];
   }
+  // entries of surplus slots (e >= NTRI) get ej = 99 / ei = 0: they never publish and their updates are discarded
 #pragma unroll 1
   for (int j = 0; j < NV; j++) {
 #pragma unroll
@@ -68,10 +69,14 @@ template <typename T> __device__ __noinline__ void wCholSolve(T* A, T* col, cons
     T piv = col[j];
     piv = piv < (T)1e-15 ? (T)1e-15 : piv;
     const T inv = brsqrt(piv);
+    const T inv2 = inv * inv;
 #pragma unroll
-    for (int m = 0; m < 4; m++) {
-      if (ej[m] == j) a[m] = (ei[m] == j) ? piv * inv : a[m] * inv;          // final L(i,j)
-      else if (ej[m] > j && ej[m] < NV) a[m] -= (col[ei[m]] * inv) * (col[ej[m]] * inv);   // trailing update
+    for (int m = 0; m < 4; m++) {   // branch-free: selects instead of divergent blocks
+      const int cj = ej[m] < NV ? ej[m] : 0;
+      const T ci = col[ei[m]], cjv = col[cj];
+      const T upd = a[m] - ci * cjv * inv2;                                  // trailing update  A(i,k) -= L(i,j) L(k,j)
+      const T fin = (ei[m] == j) ? piv * inv : a[m] * inv;                   // final L(i,j)
+      a[m] = ej[m] == j ? fin : (ej[m] > j ? upd : a[m]);
     }
     __syncwarp();
   }
@@ -285,7 +290,8 @@ __device__ __noinline__ LsPt<T> lsEval(const ModelConst<T>& mc, WS<T>& S, T* gs,
 template <typename T> struct WNewton {
   const ModelConst<T>& mc; WS<T>& S; T* gs; int lane, ncon;
   LsCtx<T> q; T cost, gauss;
-  __device__ WNewton(const ModelConst<T>& m, WS<T>& s, T* g, int l, int n) : mc(m), S(s), gs(g), lane(l), ncon(n) {}
+  bool fast;   // fast solver mode: inexact line search (stop when |phi'| <= 1e-3 |phi'(0)|), same minimiser of the outer problem
+  __device__ WNewton(const ModelConst<T>& m, WS<T>& s, T* g, int l, int n, bool f) : mc(m), S(s), gs(g), lane(l), ncon(n), fast(f) {}
 
   // forces/zones/cost at the current jar, Hessian, factorisation, gradient, Newton direction (S.Mgrad)
   __device__ __forceinline__ void update() {
@@ -313,10 +319,12 @@ template <typename T> struct WNewton {
     }
     const int col = lane < NV ? lane : 0;
     T gacc = lane < NV ? S.Ma[lane] - S.qfs[lane] : (T)0;
+    const int nres = ncon < NCS ? ncon : NCS;
+#pragma unroll 1
     for (int c = 0; c < ncon; c++) {
       const int st = S.cst[c];
       if ((st & 3) == 0) continue;
-      const T* rec = crec(S, gs, c);
+      const T* rec = c < nres ? (const T*)(S.rec + c * CR) : (const T*)(gs + (c - NCS) * CR);
       const T* r0 = rec; const T* r1 = rec + JST; const T* r2 = rec + 2 * JST;
       gacc -= r0[col] * rec[O_FRC] + r1[col] * rec[O_FRC + 1] + r2[col] * rec[O_FRC + 2];
       const int jmin = (st & 4) ? 9 : 0;   // heightfield contacts only touch the ball dofs
@@ -346,7 +354,7 @@ template <typename T> struct WNewton {
     const T sv = lane < NV ? S.search[lane] : (T)0;
     const T sn = qsqrt(wsum(sv * sv));
     if (sn < (T)1e-15) return 0;
-    const T gtol = mc.tolerance * mc.ls_tolerance * sn / scale;
+    T gtol = mc.tolerance * mc.ls_tolerance * sn / scale;
     const T mv = wSymvRow(S.M, S.search, lane);
     if (lane < NV) S.Mv[lane] = mv;
     for (int c = lane; c < ncon; c += 32) { T* rec = crec(S, gs, c); rowsDot(rec, S.search, rec + O_JV); }
@@ -357,6 +365,7 @@ template <typename T> struct WNewton {
     __syncwarp();
     int it = 0;
     const LsPt<T> p0 = lsEval(mc, S, gs, lane, ncon, q, (T)0);
+    if (fast) gtol = bmax(gtol, (T)1e-3 * babs(p0.d1));
     LsPt<T> p1 = lsEval(mc, S, gs, lane, ncon, q, p0.alpha - qdiv(p0.d1, p0.d2)), p2 = p0, pmid = p0, p1n = p0, p2n = p0;
     if (p0.cost < p1.cost) p1 = p0;
     if (babs(p1.d1) < gtol) return p1.alpha;
@@ -440,7 +449,8 @@ template <typename T> struct WNewton {
 // ---------------------------------------------------------------------------------------------- one mj_forward (warp)
 // in: S.xq, S.xv, S.ctrl, S.warm    out: S.qacc (and S.xq normalised).  kin: observation kinematics of this stage.
 template <typename T>
-__device__ __noinline__ void wForward(const ModelConst<T>& mc, WS<T>& S, const float* __restrict__ hf, T zscale, T* gs, KinOut<T>& kin, int lane) {
+__device__ __noinline__ void wForward(const ModelConst<T>& mc, WS<T>& S, const float* __restrict__ hf, T zscale, T* gs, KinOut<T>& kin, int lane,
+                                      bool fast) {
   if (lane == 0) normalizeQuats(S.xq);
   for (int e = lane; e < NTRI; e += 32) S.M[e] = 0;
   __syncwarp();
@@ -525,7 +535,7 @@ __device__ __noinline__ void wForward(const ModelConst<T>& mc, WS<T>& S, const f
     }
     __syncwarp();
   }
-  WNewton<T> nw(mc, S, gs, lane, ncon);
+  WNewton<T> nw(mc, S, gs, lane, ncon, fast);
   const int niter = nw.run();
   kin.ncon = ncon; kin.niter = niter;
 }
@@ -552,7 +562,7 @@ __device__ void wRk4(const ModelConst<T>& mc, WS<T>& S, const float* __restrict_
 #pragma unroll 1
   for (int st = 0; st < 5; st++) {
     if (st < 4) {
-      wForward(mc, S, hf, zscale, gs, kin, lane);
+      wForward(mc, S, hf, zscale, gs, kin, lane, chain_warm);
       ncmax = kin.ncon > ncmax ? kin.ncon : ncmax; nit += kin.niter;
       const T bw = (st == 0 || st == 3) ? (T)(1.0 / 6.0) : (T)(1.0 / 3.0);
       if (lane < NV) { S.sumv[lane] += bw * S.xv[lane]; S.suma[lane] += bw * S.qacc[lane]; }
