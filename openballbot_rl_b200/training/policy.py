@@ -1,0 +1,82 @@
+"""Pure-PyTorch replica of the reference's policy forward for device-resident rollouts.
+
+Reference: ``PPO("MultiInputPolicy", ..., policy_kwargs=dict(activation_fn=LeakyReLU, net_arch=dict(pi=[128]*4, vf=[128]*4),
+features_extractor_class=Extractor))`` (ballbot_rl/training/train.py:38-56, 126-141) with
+``Extractor`` = per-key modules concatenated in the observation space's (alphabetical) key order
+(ballbot_rl/policies/mlp_policy.py:7-157) and the depth encoder of ballbot_rl/encoders/models.py:10-26.
+This is the only tensor-core work on the path and it stays in PyTorch (cuDNN / cuBLAS); it consumes the GPU VecEnv's
+observation dict without any host round trip.  ``load_sb3_state`` accepts the arrays of an SB3 ``policy.pth``.
+"""
+from typing import Dict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+# gymnasium.spaces.Dict sorts the keys: this is the concatenation order of the 56 features
+FEATURE_ORDER = ("actions", "angular_vel", "motor_state", "orientation", "relative_image_timestamp", "rgbd_0", "rgbd_1", "vel")
+
+
+def make_depth_encoder(h: int = 64, w: int = 64, in_c: int = 1, out_sz: int = 20) -> nn.Sequential:
+    return nn.Sequential(
+        nn.Conv2d(in_c, 32, kernel_size=3, stride=2, padding=1), nn.BatchNorm2d(32), nn.LeakyReLU(),
+        nn.Conv2d(32, 32, kernel_size=3, stride=2, padding=1), nn.BatchNorm2d(32), nn.LeakyReLU(),
+        nn.Flatten(), nn.Linear(32 * h // 4 * w // 4, out_sz), nn.BatchNorm1d(out_sz), nn.Tanh())
+
+
+class BallbotPolicy(nn.Module):
+    def __init__(self, im_h: int = 64, im_w: int = 64, hidden: int = 128, cameras: bool = True):
+        super().__init__()
+        self.cameras = cameras
+        self.encoders = nn.ModuleDict({k: make_depth_encoder(im_h, im_w) for k in ("rgbd_0", "rgbd_1")}) if cameras else nn.ModuleDict()
+        feat = 3 * 5 + 1 + (40 if cameras else 0)
+
+        def mlp(out):
+            layers, d = [], feat
+            for _ in range(4):
+                layers += [nn.Linear(d, hidden), nn.LeakyReLU()]
+                d = hidden
+            return nn.Sequential(*layers), nn.Linear(hidden, out)
+        self.policy_net, self.action_net = mlp(3)
+        self.value_net_body, self.value_net = mlp(1)
+        self.log_std = nn.Parameter(torch.zeros(3))
+
+    def features(self, obs: Dict[str, torch.Tensor]) -> torch.Tensor:
+        parts = []
+        for k in FEATURE_ORDER:
+            if k.startswith("rgbd_"):
+                if self.cameras:
+                    parts.append(self.encoders[k](obs[k]))
+            else:
+                parts.append(obs[k].flatten(1))
+        return torch.cat(parts, dim=1)
+
+    def forward(self, obs: Dict[str, torch.Tensor], deterministic: bool = True) -> torch.Tensor:
+        """Actions clipped to [-1, 1] exactly like ``PPO.predict`` / ``collect_rollouts`` do before ``env.step``."""
+        mean = self.action_net(self.policy_net(self.features(obs)))
+        if not deterministic:
+            mean = mean + torch.randn_like(mean) * self.log_std.exp()
+        return mean.clamp(-1.0, 1.0)
+
+    def value(self, obs: Dict[str, torch.Tensor]) -> torch.Tensor:
+        return self.value_net(self.value_net_body(self.features(obs))).squeeze(-1)
+
+    def load_sb3_state(self, arrays: Dict[str, np.ndarray]) -> "BallbotPolicy":
+        """arrays: SB3 ``policy.pth`` entries (``features_extractor.extractors.rgbd_k.*``, ``mlp_extractor.policy_net.*``,
+        ``action_net.*``, optionally the value nets, ``log_std``)."""
+        sd = {}
+        for k, v in arrays.items():
+            t = torch.as_tensor(np.asarray(v))
+            if k.startswith("features_extractor.extractors."):
+                sd["encoders." + k[len("features_extractor.extractors."):]] = t
+            elif k.startswith("mlp_extractor.policy_net."):
+                sd["policy_net." + k[len("mlp_extractor.policy_net."):]] = t
+            elif k.startswith("mlp_extractor.value_net."):
+                sd["value_net_body." + k[len("mlp_extractor.value_net."):]] = t
+            elif k.startswith(("action_net.", "value_net.")) or k == "log_std":
+                sd[k] = t
+        missing, unexpected = self.load_state_dict(sd, strict=False)
+        bad = [m for m in missing if not (m.startswith(("value_net", "value_net_body")) or m.endswith("num_batches_tracked"))]
+        if bad or unexpected:
+            raise ValueError(f"state dict mismatch: missing {bad}, unexpected {unexpected}")
+        return self

@@ -163,3 +163,31 @@ def test_fast_solver_mode_within_baseline_tolerance(oracle_mod):
             worst1 = max(worst1, np.abs(q1[i] - qo).max() / max(1, np.abs(qo).max()), np.abs(v1[i] - vo).max() / max(1, np.abs(vo).max()))
     assert worst1 < 1e-5, worst1
     eng.close()
+
+
+def test_fixed_policy_episode_on_engine_matches_reference_eval(oracle_mod):
+    """The archived reference policy closed over the CUDA engine (device-resident obs -> torch policy -> bb_step):
+    reference recorded return 9.198632 / length 378 (deterministic eval, flat terrain)."""
+    import os
+    from openballbot_rl_b200.envs import BallbotVecEnv
+    from openballbot_rl_b200.training.policy import BallbotPolicy
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policy_flat_10M.npz"))
+    pol = BallbotPolicy().load_sb3_state({k: z[k] for k in z.files if not k.startswith("eval_")}).eval().cuda()
+    ref_ret, ref_len = float(z["eval_return"][0]), int(z["eval_length"][0])
+    N = 4
+    venv = BallbotVecEnv(N, terrain_config={"type": "flat", "config": {}}, reward_config=REWARD, env_config=ENV_CFG, precision=64)
+    venv.engine.cfg  # noqa: B018
+    obs = venv.reset()
+    ret = torch.zeros(N, device="cuda"); length = torch.zeros(N, dtype=torch.int32, device="cuda"); alive = torch.ones(N, dtype=torch.bool, device="cuda")
+    with torch.no_grad():
+        for t in range(600):
+            obs, rew, dones, info = venv.step(pol(obs))
+            ret += rew * alive; length += alive.int()
+            alive &= ~dones
+            if not bool(alive.any()):
+                break
+    L, G = length.cpu().numpy(), ret.cpu().numpy()
+    assert (L == L[0]).all()                                        # identical envs, deterministic policy
+    assert abs(int(L[0]) - ref_len) <= 0.08 * ref_len, (L, ref_len)
+    assert abs(float(G[0]) - ref_ret) <= 0.06 * ref_ret, (G, ref_ret)
+    venv.close()

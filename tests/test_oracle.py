@@ -143,3 +143,37 @@ def test_random_policy_statistics_match_reference_records(oracle_mod):
     assert abs(out["flat"][2] - 8.887) < 1.0, out
     assert abs(out["perlin"][0] - 157.8) < 4 * out["perlin"][1] + 8, out
     assert abs(out["perlin"][2] - 3.186) < 0.6, out
+
+
+def _policy():
+    import os
+    import torch
+    from openballbot_rl_b200.training.policy import BallbotPolicy
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policy_flat_10M.npz"))
+    pol = BallbotPolicy().load_sb3_state({k: z[k] for k in z.files if not k.startswith("eval_")}).eval()
+    return pol, float(z["eval_return"][0]), int(z["eval_length"][0])
+
+
+def test_fixed_policy_episode_matches_reference_eval(oracle_mod):
+    """End-to-end pin: the reference's archived PPO policy (flat terrain, 10 M steps; tests/golden/make_policy_fixture.py)
+    was evaluated deterministically by the reference itself: return 9.198632, length 378, 8/8 episodes identical
+    (results/evaluations.npz).  Closing the loop through THIS oracle (physics + obs quirks + reward + tilt termination +
+    depth ray-cast -> frozen encoder -> policy MLP) must land on the same episode within a few percent."""
+    import torch
+    pol, ref_ret, ref_len = _policy()
+    assert (ref_len, round(ref_ret, 6)) == (378, 9.198632)
+    e = oracle_mod.OracleEnv(cameras=True)
+    o = e.reset(); d0, d1 = e.depth()
+    G, n = 0.0, 0
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))[None]
+    with torch.no_grad():
+        while True:
+            obs = {"orientation": t(o[0:3]), "angular_vel": t(o[3:6]), "vel": t(o[6:9]), "motor_state": t(o[9:12]), "actions": t(o[12:15]),
+                   "relative_image_timestamp": t(o[15:16]), "rgbd_0": t(d0)[None], "rgbd_1": t(d1)[None]}
+            o, r, term, fail, _ = e.step(pol(obs)[0].numpy())
+            d0, d1 = e.depth(); G += r; n += 1
+            if term:
+                break
+    assert fail                                    # the recorded episode also ends by tilt, not by timeout
+    assert abs(n - ref_len) <= 0.08 * ref_len, (n, ref_len)        # measured here: 387 vs 378
+    assert abs(G - ref_ret) <= 0.06 * ref_ret, (G, ref_ret)        # measured here: 9.318 vs 9.1986
