@@ -10,7 +10,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libballbot_b200.so")
-_SOURCES = ["bb_engine.cu", "bb_core.cuh", "bb_warp.cuh", "bb_model.h"]
+_SOURCES = ["bb_engine.cu", "bb_core.cuh", "bb_group.cuh", "bb_model.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 

@@ -25,6 +25,10 @@
 #define BB_NOINL inline
 #endif
 
+#if defined(BB_STATS) && !defined(__CUDA_ARCH__)
+static long bb_stats_ls_evals = 0;   // host-only instrumentation for scripts/exp (never defined in the product build)
+#endif
+
 namespace bb {
 
 constexpr int NQ = 17, NV = 15, HN = 293;
@@ -194,7 +198,13 @@ template <typename T> BB_HD void normalizeQuats(T* qpos) { normalizeQuat4(qpos +
 // Fills s.M (packed), s.qfs (= passive - bias + actuator), geometry g, wheel capsule world frames, obs kinematics.
 // M (packed lower triangle, NTRI) and qfs (NV) are raw pointers so that the same code serves the thread-per-env scratch
 // and the warp-per-env shared-memory layout (ZERO_M=false: the caller has zeroed M and normalised the quaternions).
-template <typename T, bool ZERO_M = true>
+// ML selects the layout of M: 0 = packed lower triangle (tidx), 1 = full symmetric 15 x 16 row-major (both triangles
+// written; the warp kernel zeroes the never-written entries once per launch).
+template <int ML, typename T> BB_HD void setM(T* M, int i, int j, T v) {
+  if (ML == 0) M[tidx(i, j)] = v;
+  else { M[i * 16 + j] = v; M[j * 16 + i] = v; }
+}
+template <typename T, bool ZERO_M = true, int ML = 0>
 BB_HD void smoothDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const T* ctrl, T* M, T* qfs, Geo<T>& g,
                           V3<T>* capC, V3<T>* capU, KinOut<T>* kin) {
   if (ZERO_M) normalizeQuats(qpos);   // mj_kinematics normalises free-joint quaternions in place
@@ -236,7 +246,7 @@ BB_HD void smoothDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const
     pw[i] = axs * mc.mw;
     const V3<T> Iwa = smul(Iw, a[i]);
     Lw[i] = Iwa + cross(ri[i], pw[i]);
-    M[tidx(6 + i, 6 + i)] = dot(a[i], Iwa) + mc.mw * dot(axs, axs) + mc.armature;
+    setM<ML>(M, 6 + i, 6 + i, dot(a[i], Iwa) + mc.mw * dot(axs, axs) + mc.armature);
     // bias (qdd = 0): classical accelerations in the rotating base frame
     const T qd = qvel[6 + i];
     const V3<T> wi = w + a[i] * qd;
@@ -249,21 +259,21 @@ BB_HD void smoothDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const
     biasq[i] = dot(a[i], cross(si[i], Fi) + Ni);
   }
   // ---- M_A
-  M[tidx(0, 0)] = mc.mA; M[tidx(1, 1)] = mc.mA; M[tidx(2, 2)] = mc.mA;
+  setM<ML>(M, 0, 0, mc.mA); setM<ML>(M, 1, 1, mc.mA); setM<ML>(M, 2, 2, mc.mA);
   {  // M[v, w_k] = d(momentum)/d(w_k) = R_B (e_k x mcA)
     const V3<T> k0 = rot(g.RB, cross(mk((T)1, (T)0, (T)0), mcA));
     const V3<T> k1 = rot(g.RB, cross(mk((T)0, (T)1, (T)0), mcA));
     const V3<T> k2 = rot(g.RB, cross(mk((T)0, (T)0, (T)1), mcA));
-    M[tidx(3, 0)] = k0.x; M[tidx(3, 1)] = k0.y; M[tidx(3, 2)] = k0.z;
-    M[tidx(4, 0)] = k1.x; M[tidx(4, 1)] = k1.y; M[tidx(4, 2)] = k1.z;
-    M[tidx(5, 0)] = k2.x; M[tidx(5, 1)] = k2.y; M[tidx(5, 2)] = k2.z;
+    setM<ML>(M, 3, 0, k0.x); setM<ML>(M, 3, 1, k0.y); setM<ML>(M, 3, 2, k0.z);
+    setM<ML>(M, 4, 0, k1.x); setM<ML>(M, 4, 1, k1.y); setM<ML>(M, 4, 2, k1.z);
+    setM<ML>(M, 5, 0, k2.x); setM<ML>(M, 5, 1, k2.y); setM<ML>(M, 5, 2, k2.z);
   }
-  M[tidx(3, 3)] = IA.xx; M[tidx(4, 4)] = IA.yy; M[tidx(5, 5)] = IA.zz;
-  M[tidx(4, 3)] = IA.xy; M[tidx(5, 3)] = IA.xz; M[tidx(5, 4)] = IA.yz;
+  setM<ML>(M, 3, 3, IA.xx); setM<ML>(M, 4, 4, IA.yy); setM<ML>(M, 5, 5, IA.zz);
+  setM<ML>(M, 4, 3, IA.xy); setM<ML>(M, 5, 3, IA.xz); setM<ML>(M, 5, 4, IA.yz);
   for (int i = 0; i < 3; i++) {
     const V3<T> pwW = rot(g.RB, pw[i]);
-    M[tidx(6 + i, 0)] = pwW.x; M[tidx(6 + i, 1)] = pwW.y; M[tidx(6 + i, 2)] = pwW.z;
-    M[tidx(6 + i, 3)] = Lw[i].x; M[tidx(6 + i, 4)] = Lw[i].y; M[tidx(6 + i, 5)] = Lw[i].z;
+    setM<ML>(M, 6 + i, 0, pwW.x); setM<ML>(M, 6 + i, 1, pwW.y); setM<ML>(M, 6 + i, 2, pwW.z);
+    setM<ML>(M, 6 + i, 3, Lw[i].x); setM<ML>(M, 6 + i, 4, Lw[i].y); setM<ML>(M, 6 + i, 5, Lw[i].z);
   }
   // ---- ball
   const V3<T> wl = ld3(qvel + 12);
@@ -272,17 +282,17 @@ BB_HD void smoothDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const
   const V3<T> FL = (cross(wl, cross(wl, d)) - glL) * mc.mL;
   const V3<T> FLw = rot(g.RL, FL);
   const V3<T> TL = cross(d, FL);
-  M[tidx(9, 9)] = mc.mL; M[tidx(10, 10)] = mc.mL; M[tidx(11, 11)] = mc.mL;
+  setM<ML>(M, 9, 9, mc.mL); setM<ML>(M, 10, 10, mc.mL); setM<ML>(M, 11, 11, mc.mL);
   {
     const V3<T> md = d * mc.mL;
     const V3<T> k0 = rot(g.RL, cross(mk((T)1, (T)0, (T)0), md));
     const V3<T> k1 = rot(g.RL, cross(mk((T)0, (T)1, (T)0), md));
     const V3<T> k2 = rot(g.RL, cross(mk((T)0, (T)0, (T)1), md));
-    M[tidx(12, 9)] = k0.x; M[tidx(12, 10)] = k0.y; M[tidx(12, 11)] = k0.z;
-    M[tidx(13, 9)] = k1.x; M[tidx(13, 10)] = k1.y; M[tidx(13, 11)] = k1.z;
-    M[tidx(14, 9)] = k2.x; M[tidx(14, 10)] = k2.y; M[tidx(14, 11)] = k2.z;
+    setM<ML>(M, 12, 9, k0.x); setM<ML>(M, 12, 10, k0.y); setM<ML>(M, 12, 11, k0.z);
+    setM<ML>(M, 13, 9, k1.x); setM<ML>(M, 13, 10, k1.y); setM<ML>(M, 13, 11, k1.z);
+    setM<ML>(M, 14, 9, k2.x); setM<ML>(M, 14, 10, k2.y); setM<ML>(M, 14, 11, k2.z);
   }
-  M[tidx(12, 12)] = mc.IL + mc.mL * mc.dz * mc.dz; M[tidx(13, 13)] = mc.IL + mc.mL * mc.dz * mc.dz; M[tidx(14, 14)] = mc.IL;
+  setM<ML>(M, 12, 12, mc.IL + mc.mL * mc.dz * mc.dz); setM<ML>(M, 13, 13, mc.IL + mc.mL * mc.dz * mc.dz); setM<ML>(M, 14, 14, mc.IL);
   // ---- qfrc_smooth = passive - bias + actuator
   const V3<T> FsW = rot(g.RB, Fsum);
   qfs[0] = -FsW.x; qfs[1] = -FsW.y; qfs[2] = -FsW.z;
@@ -579,6 +589,9 @@ template <typename T> struct Newton {
     cholSolvePacked(s.H, s.grad, s.Mgrad);
   }
   BB_HD LsPt<T> eval(T alpha) {
+#if defined(BB_STATS) && !defined(__CUDA_ARCH__)
+    bb_stats_ls_evals++;
+#endif
     LsPt<T> p; p.alpha = alpha;
     p.cost = qG0 + alpha * (qG1 + alpha * qG2); p.d1 = qG1 + (T)2 * alpha * qG2; p.d2 = (T)2 * qG2;
     for (int c = 0; c < s.nc; c++) {

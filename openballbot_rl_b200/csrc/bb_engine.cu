@@ -17,14 +17,14 @@
 
 #include "../../include/ballbot_b200.h"
 #include "bb_model.h"
-#include "bb_warp.cuh"
+#include "bb_group.cuh"
 
 using namespace bb;
 
 namespace {
 
 #ifndef BB_WPB
-#define BB_WPB 1          // warps (= envs) per CTA of the step kernel; 1 avoids waiting for the slowest env of a CTA
+#define BB_WPB 1          // warps per CTA of the step kernel (2 envs per warp); 1 avoids waiting for the slowest warp of a CTA
 #endif
 #ifndef BB_WARP_MINBLOCKS
 #define BB_WARP_MINBLOCKS (12 / BB_WPB)
@@ -52,7 +52,7 @@ struct EnvParams {
 struct DevState {
   void* st;        // T[N][SST]
   void* camq;      // T[N][CST]  configuration the cameras see (last RK stage / reset state)
-  void* gscr;      // T[N][bbw::GSCR] overflow scratch of the warp kernel (contact records beyond shared memory)
+  void* gscr;      // T[N][bbg::GSCR] overflow scratch of the group kernel (contact records beyond shared memory)
   int* step_count; int* cam_steps; unsigned* episode; int* tseed;
   float* hfield;   // [N][HF_CELLS] (hf_per_env) or [HF_CELLS]
   float* ep_ret; int* ep_len;
@@ -161,29 +161,35 @@ __global__ void __launch_bounds__(64) k_step(EnvParams p, DevState d, const floa
   }
 }
 
-// --------------------------------------------------------------------------------------------- step, warp per env
-// 4 warps per CTA, one env per warp; solver state in dynamic shared memory (bbw::WS<T> per warp).
+// --------------------------------------------------------------------------------------------- step, lane group per env
+// One 16-lane group per env (two envs per warp, bb_group.cuh); solver state in dynamic shared memory (bbg::GS<T> per env).
 template <typename T>
 __global__ void __launch_bounds__(32 * BB_WPB, BB_WARP_MINBLOCKS) k_step_warp(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
+  const bbg::Ln L = bbg::makeLn();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / bbg::G;
+  const int i = (blockIdx.x * (blockDim.x >> 5) + warp) * bbg::EPW + grp;
   if (i >= p.N) return;
-  bbw::WS<T>& S = reinterpret_cast<bbw::WS<T>*>(smem_raw)[warp];
+  bbg::GS<T>& S = reinterpret_cast<bbg::GS<T>*>(smem_raw)[warp * bbg::EPW + grp];
   T* st = (T*)d.st + (size_t)i * SST;
   // one coalesced record per env: qpos[17] qvel[15] warm[15]
-  T v0 = st[lane], v1 = lane < SST - 32 ? st[32 + lane] : (T)0;
-  bool bad = !(babs(v0) < (T)1e10) || (lane < NST - 32 && !(babs(v1) < (T)1e10));
-  bad = __any_sync(bbw::FULL, bad);
-  if (lane < NQ) S.xq[lane] = v0; else S.xv[lane - NQ] = v0;            // lanes 17..31 -> qvel[0..14]
-  if (lane < NV) S.warm[lane] = v1;                                       // record[32..46] -> warm[0..14]
-  const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
-  if (lane < 3) {  // ballbot_env.py:903-907
-    const float av = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
-    T u = (T)av * (T)p.max_wheel_vel; u = u > (T)p.max_wheel_vel ? (T)p.max_wheel_vel : (u < -(T)p.max_wheel_vel ? -(T)p.max_wheel_vel : u);
-    S.ctrl[lane] = -u;
+  bool bad = false;
+  for (int k = L.gl; k < NQ + NV; k += bbg::G) {
+    const T v = st[k];
+    bad |= !(babs(v) < (T)1e10);
+    if (k < NQ) S.xq[k] = v; else S.xv[k - NQ] = v;
   }
-  __syncwarp();
+  T warm = st[NQ + NV + L.gi];
+  if (L.gl == NV) S.xv[NV] = 0;
+  for (int k = L.gl; k < NV * bbg::MS; k += bbg::G) S.M[k] = 0;   // structural zeros of the mass matrix (never written again)
+  bad = __any_sync(L.mask, bad);
+  const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
+  if (L.gl < 3) {  // ballbot_env.py:903-907
+    const float av = L.gl == 0 ? a0 : (L.gl == 1 ? a1 : a2);
+    T u = (T)av * (T)p.max_wheel_vel; u = u > (T)p.max_wheel_vel ? (T)p.max_wheel_vel : (u < -(T)p.max_wheel_vel ? -(T)p.max_wheel_vel : u);
+    S.ctrl[L.gl] = -u;
+  }
+  __syncwarp(L.mask);
   KinOut<T> kin;
   int cs = d.cam_steps[i] + 1;
   bool refresh = false;
@@ -191,23 +197,29 @@ __global__ void __launch_bounds__(32 * BB_WPB, BB_WARP_MINBLOCKS) k_step_warp(En
   int status = 0;
   if (!bad) {
     const float* hf = d.hfield + (p.hf_per_env ? (size_t)i * HF_CELLS : 0);
-    T* gs = (T*)d.gscr + (size_t)i * bbw::GSCR;
+    T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
     T* cq = refresh ? (T*)d.camq + (size_t)i * CST : nullptr;
-    bbw::wRk4(cmc<T>(), S, hf, (T)p.zscale, gs, kin, cq, lane, p.solver_mode != 0);
-    bool b2 = (lane < NQ && !(babs(S.xq[lane]) < (T)1e10)) || (lane < NV && !(babs(S.xv[lane]) < (T)1e10));
-    bad = __any_sync(bbw::FULL, b2);
-    status = kin.ncon << 8;
+    int ncmax, nit;
+    bbg::gRk4(cmc<T>(), S, hf, (T)p.zscale, gs, cq, L, warm, p.solver_mode != 0, ncmax, nit);
+    bool b2 = (L.gl < NV && !(babs(S.xv[L.gl]) < (T)1e10));
+    for (int k = L.gl; k < NQ; k += bbg::G) b2 |= !(babs(S.xq[k]) < (T)1e10);
+    bad = __any_sync(L.mask, b2);
+    status = ncmax << 8;
+#pragma unroll
+    for (int k = 0; k < 4; k++) kin.quatB[k] = S.kin[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { kin.cvel_ang[k] = S.kin[4 + k]; kin.cvel_lin[k] = S.kin[7 + k]; kin.posB[k] = S.kin[10 + k]; }
   }
   if (bad) {
     status |= 1;
     kin.quatB[0] = 1; kin.quatB[1] = kin.quatB[2] = kin.quatB[3] = 0;
     for (int k = 0; k < 3; k++) { kin.cvel_ang[k] = 0; kin.cvel_lin[k] = 0; kin.posB[k] = 0; }
-    if (lane < NV) S.xv[lane] = 0;
-    __syncwarp();
+    if (L.gl < NV) S.xv[L.gl] = 0;
+    __syncwarp(L.mask);
   }
   // write the state record back (coalesced)
-  st[lane] = lane < NQ ? S.xq[lane] : S.xv[lane - NQ];
-  if (lane < NV) st[32 + lane] = S.warm[lane];
+  for (int k = L.gl; k < NQ + NV; k += bbg::G) st[k] = k < NQ ? S.xq[k] : S.xv[k - NQ];
+  if (L.gl < NV) st[NQ + NV + L.gl] = warm;
   // ---- observation / reward / termination: every lane evaluates the few scalars, lane 0 (or a few lanes) store
   float ob[16];
   proprioObs(kin, (const T*)S.xv, (T)p.max_wheel_vel, ob, ob + 3, ob + 6, ob + 9);
@@ -226,21 +238,21 @@ __global__ void __launch_bounds__(32 * BB_WPB, BB_WARP_MINBLOCKS) k_step_warp(En
   const double tilt = tiltDegrees(ob);
   if (tilt > (double)p.max_tilt || bad) { fail = true; term = true; } else r += p.survival;
   const float eret = d.ep_ret[i] + r; const int elen = d.ep_len[i] + 1;
-  __syncwarp();
-  if (lane < 15) {   // obs block: orientation, angular_vel, vel, motor_state, actions (3 each)
-    float* dst = lane < 3 ? io.orientation : (lane < 6 ? io.angular_vel : (lane < 9 ? io.vel : (lane < 12 ? io.motor_state : io.actions)));
+  __syncwarp(L.mask);
+  if (L.gl < 15) {   // obs block: orientation, angular_vel, vel, motor_state, actions (3 each)
+    float* dst = L.gl < 3 ? io.orientation : (L.gl < 6 ? io.angular_vel : (L.gl < 9 ? io.vel : (L.gl < 12 ? io.motor_state : io.actions)));
     float v = ob[0];
 #pragma unroll
-    for (int k = 1; k < 15; k++) v = lane == k ? ob[k] : v;
-    dst[3 * i + lane % 3] = v;
+    for (int k = 1; k < 15; k++) v = L.gl == k ? ob[k] : v;
+    dst[3 * i + L.gl % 3] = v;
   }
-  if (term && io.terminal_obs && lane < 16) {
+  if (term && io.terminal_obs && L.gl < 16) {
     float v = ob[0];
 #pragma unroll
-    for (int k = 1; k < 16; k++) v = lane == k ? ob[k] : v;
-    io.terminal_obs[16 * i + lane] = v;
+    for (int k = 1; k < 16; k++) v = L.gl == k ? ob[k] : v;
+    io.terminal_obs[16 * i + L.gl] = v;
   }
-  if (lane == 0) {
+  if (L.gl == 0) {
     io.rel_image_ts[i] = ob[15];
     io.reward[i] = r; io.terminated[i] = term; io.failure[i] = fail;
     io.pos2d[2 * i] = (float)kin.posB[0]; io.pos2d[2 * i + 1] = (float)kin.posB[1];
@@ -254,22 +266,24 @@ __global__ void __launch_bounds__(32 * BB_WPB, BB_WARP_MINBLOCKS) k_step_warp(En
     } else if (refresh) d.refresh_list[atomicAdd(&d.counters[1], 1)] = i;
   }
 }
-// forward-dynamics probe through the warp path (same outputs as k_probe)
+// forward-dynamics probe through the group path (same outputs as k_probe)
 template <typename T> __global__ void k_probe_warp(EnvParams p, DevState d, int env, const double* ctrl3, double* out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  bbw::WS<T>& S = reinterpret_cast<bbw::WS<T>*>(smem_raw)[0];
+  if ((threadIdx.x & 31) >= bbg::G) return;
+  const bbg::Ln L = bbg::makeLn();
+  bbg::GS<T>& S = reinterpret_cast<bbg::GS<T>*>(smem_raw)[0];
   const T* st = (const T*)d.st + (size_t)env * SST;
-  if (lane < NQ) S.xq[lane] = st[lane];
-  if (lane < NV) { S.xv[lane] = st[NQ + lane]; S.warm[lane] = st[NQ + NV + lane]; }
-  if (lane < 3) S.ctrl[lane] = (T)ctrl3[lane];
-  __syncwarp();
-  KinOut<T> kin;
+  for (int k = L.gl; k < NQ + NV; k += bbg::G) { if (k < NQ) S.xq[k] = st[k]; else S.xv[k - NQ] = st[k]; }
+  const T warm = st[NQ + NV + L.gi];
+  if (L.gl == NV) S.xv[NV] = 0;
+  for (int k = L.gl; k < NV * bbg::MS; k += bbg::G) S.M[k] = 0;
+  if (L.gl < 3) S.ctrl[L.gl] = (T)ctrl3[L.gl];
+  __syncwarp(L.mask);
   const float* hf = d.hfield + (p.hf_per_env ? (size_t)env * HF_CELLS : 0);
-  bbw::wForward(cmc<T>(), S, hf, (T)p.zscale, (T*)d.gscr + (size_t)env * bbw::GSCR, kin, lane, p.solver_mode != 0);
-  __syncwarp();
-  if (lane < NV) { out[lane] = (double)S.qacc[lane]; out[15 + lane] = (double)S.qas[lane]; out[30 + lane] = (double)S.qfs[lane]; }
-  if (lane == 0) { out[45] = kin.ncon; out[46] = kin.niter; }
+  int ncon, niter; T qas, qfs;
+  const T qacc = bbg::gForward(cmc<T>(), S, hf, (T)p.zscale, (T*)d.gscr + (size_t)env * bbg::GSCR, L, warm, p.solver_mode != 0, true, ncon, niter, &qas, &qfs);
+  if (L.gl < NV) { out[L.gl] = (double)qacc; out[15 + L.gl] = (double)qas; out[30 + L.gl] = (double)qfs; }
+  if (L.gl == 0) { out[45] = ncon; out[46] = niter; }
 }
 
 // explicit reset: mask -> reset list (+ new terrain seed)
@@ -745,10 +759,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
     BB_CUDA_C(cudaMemcpyToSymbol(c_mc64, &m64, sizeof(m64)));
     BB_CUDA_C(cudaMemcpyToSymbol(c_mc32, &m32, sizeof(m32)));
     BB_CUDA_C(cudaMemcpyToSymbol(c_perm, h_perm, sizeof(h_perm)));
-    unsigned char ti[NTRI], tj[NTRI];
-    for (int i = 0, e2 = 0; i < NV; i++) for (int j = 0; j <= i; j++, e2++) { ti[e2] = (unsigned char)i; tj[e2] = (unsigned char)j; }
-    BB_CUDA_C(cudaMemcpyToSymbol(bbw::c_tri_i, ti, sizeof(ti)));
-    BB_CUDA_C(cudaMemcpyToSymbol(bbw::c_tri_j, tj, sizeof(tj)));
+
   }
   EnvParams& p = e->p;
   p.N = N; p.env_offset = cfg->env_offset; p.cameras = cfg->cameras; p.im_h = cfg->im_h; p.im_w = cfg->im_w;
@@ -767,7 +778,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   DevState& d = e->d;
   BB_CUDA_C(cudaMalloc(&d.st, e->tsize * SST * N));
   BB_CUDA_C(cudaMalloc(&d.camq, e->tsize * CST * N));
-  BB_CUDA_C(cudaMalloc(&d.gscr, e->tsize * (size_t)bbw::GSCR * N));
+  BB_CUDA_C(cudaMalloc(&d.gscr, e->tsize * (size_t)bbg::GSCR * N));
   BB_CUDA_C(cudaMalloc(&d.step_count, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.cam_steps, sizeof(int) * N));
   BB_CUDA_C(cudaMalloc(&d.episode, sizeof(unsigned) * N)); BB_CUDA_C(cudaMalloc(&d.tseed, sizeof(int) * N));
   BB_CUDA_C(cudaMalloc(&d.ep_ret, sizeof(float) * N)); BB_CUDA_C(cudaMalloc(&d.ep_len, sizeof(int) * N));
@@ -835,8 +846,9 @@ int bb_step(bb_engine* e, const float* actions_dev, const bb_io* io, void* strea
     else k_step<float><<<blocksFor(N, bs), bs, 0, s>>>(e->p, e->d, actions_dev, *io);
   } else {                         // warp-per-env (default)
     const int wpb = BB_WPB;
-    if (e->cfg.precision == 64) k_step_warp<double><<<blocksFor(N, wpb), wpb * 32, wpb * sizeof(bbw::WS<double>), s>>>(e->p, e->d, actions_dev, *io);
-    else k_step_warp<float><<<blocksFor(N, wpb), wpb * 32, wpb * sizeof(bbw::WS<float>), s>>>(e->p, e->d, actions_dev, *io);
+    const int epb = wpb * bbg::EPW;   // envs per CTA
+    if (e->cfg.precision == 64) k_step_warp<double><<<blocksFor(N, epb), wpb * 32, epb * sizeof(bbg::GS<double>), s>>>(e->p, e->d, actions_dev, *io);
+    else k_step_warp<float><<<blocksFor(N, epb), wpb * 32, epb * sizeof(bbg::GS<float>), s>>>(e->p, e->d, actions_dev, *io);
   }
   if (ev) cudaEventRecord(ev[1], s);
   e->launches += 2;
@@ -920,8 +932,8 @@ int bb_probe_forward(bb_engine* e, int32_t env, const double* ctrl3_dev, double*
     if (e->cfg.precision == 64) k_probe<double><<<1, 32, 0, (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev, cdist_dev, cpos_dev, cframe_dev);
     else k_probe<float><<<1, 32, 0, (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev, cdist_dev, cpos_dev, cframe_dev);
   } else {   // warp path: accelerations / counts only (contact arrays are left untouched)
-    if (e->cfg.precision == 64) k_probe_warp<double><<<1, 32, sizeof(bbw::WS<double>), (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev);
-    else k_probe_warp<float><<<1, 32, sizeof(bbw::WS<float>), (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev);
+    if (e->cfg.precision == 64) k_probe_warp<double><<<1, 32, sizeof(bbg::GS<double>), (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev);
+    else k_probe_warp<float><<<1, 32, sizeof(bbg::GS<float>), (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev);
   }
   e->launches++;
   BB_CUDA(cudaGetLastError());

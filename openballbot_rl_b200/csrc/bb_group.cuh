@@ -1,0 +1,748 @@
+// bb_group.cuh -- lane-group-per-env forward dynamics + RK4 for the B200 ballbot engine (device only).
+//
+// A group of G = 16 lanes integrates one environment, so one warp carries two environments through the same
+// instruction stream (the 15 dofs of the model fit one 16-lane group; with a full warp per env more than half of the
+// lanes idle in every solver phase).  All group collectives (__shfl_sync / __syncwarp / __ballot_sync) are issued with
+// the group's own member mask, so the two halves of a warp are logically independent and only pay for divergence
+// where their trip counts differ (Newton iterations, line-search evaluations, contact batches).
+//
+// Layout of the solver (mj_fwdConstraint / mj_solNewton semantics, reference call ballbot_env.py:912):
+//   * lane i < 15 of a group owns dof i: qfrc_smooth, qacc_smooth, qacc, M qacc, gradient, search direction and the
+//     RK4 accumulators are ONE register each per lane;
+//   * the mass matrix is a full symmetric 15 x 16 array in shared memory (lane i reads column i with unit stride);
+//   * the Hessian H = M + sum_c J_c' W_c J_c is assembled with column i in the registers of lane i and factorised in
+//     place (right-looking Cholesky: per column one shuffle for the pivot, one rsqrt, the scaled column is exchanged
+//     through a 16-word shared buffer); forward substitution is fused into the factorisation, the backward
+//     substitution needs one shuffle per dof;
+//   * contact c is owned by lane c % G for the per-contact scalar work (cone zones, line-search coefficients);
+//     its record (3 Jacobian rows + 24 scalars) lives in shared memory (3 wheel + 9 terrain records) and spills to a
+//     global scratch beyond that (deep impacts only);
+//   * the exact line search is a state machine around ONE evaluation call site, so two environments that are in
+//     different phases of their searches still share every evaluation instruction.
+// The arithmetic restates the same algorithm as bb_core.cuh (thread-per-env cross-check and CPU test harness); only
+// summation orders and the rsqrt-based square roots differ.
+#pragma once
+#include "bb_core.cuh"
+
+#ifndef BB_GROUP
+#define BB_GROUP 16
+#endif
+
+namespace bbg {
+using namespace bb;
+
+constexpr int G = BB_GROUP;                 // lanes per environment (16: two envs per warp, 32: one env per warp)
+constexpr int EPW = 32 / G;                 // environments per warp
+constexpr int MS = 16;                      // row stride of the full symmetric mass matrix
+// contact records (in T).  Wheel pair: rows of 16 (dofs 0..14 + zero pad); terrain pair: rows of 8 = dofs 8..15 (only the
+// ball dofs 9..14 are non-zero).  Scalar block at OS: W(6) frc(3) D0 jar(3) jv(3) LS(8).
+constexpr int CRW = 74, CRH = 50;           // strides == 10 (mod 16): one-record-per-lane access is bank-conflict-free
+constexpr int OSW = 48, OSH = 24;
+constexpr int O_W = 0, O_FRC = 6, O_D0 = 9, O_JAR = 10, O_JV = 13, O_LS = 16;
+constexpr int NHS = 9;                      // terrain records resident in shared memory
+constexpr int GSCR = (MAXH - NHS) * CRH;    // per-env global overflow scratch (in T)
+// geometry block published by the smooth-dynamics pass
+constexpr int GE_PB = 0, GE_PL = 3, GE_RB = 6, GE_RL = 15, GE_AW = 24, GE_HW = 33, GE_CC = 42, GE_CU = 51, GE_N = 60;
+
+template <typename T> struct GS {
+  T xq[20], xv[16], q0[20], ctrl[4];
+  T M[NV * MS];
+  T vb[2][16];          // vectors published by the dof lanes (broadcast reads)
+  T col[2][16];         // Cholesky column exchange (double buffered)
+  T geo[GE_N];
+  T kin[16];            // quatB(4) cvel_ang(3) cvel_lin(3) posB(3) of the last evaluated stage
+  T wrec[3 * CRW];
+  T hrec[NHS * CRH];
+  unsigned char cst[64];   // per contact: bits 0-1 zone (0 satisfied, 1 quadratic, 2 cone)
+};
+
+struct Ln { int gl; int gi; unsigned mask; };   // lane in group, clamped dof index, member mask of the group
+__device__ __forceinline__ Ln makeLn() {
+  Ln L; const int lane = threadIdx.x & 31;
+  L.gl = lane & (G - 1); L.gi = L.gl < NV ? L.gl : NV - 1;
+  L.mask = G == 32 ? 0xffffffffu : (0xffffu << (lane & 16));
+  return L;
+}
+template <typename T> __device__ __forceinline__ T gsum(T v, unsigned mask) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+template <typename T> __device__ __forceinline__ T gget(T v, int src, unsigned mask) { return __shfl_sync(mask, v, src, G); }
+
+template <typename T> struct V2T;
+template <> struct V2T<double> { typedef double2 t; };
+template <> struct V2T<float> { typedef float2 t; };
+template <typename T> __device__ __forceinline__ typename V2T<T>::t ld2(const T* p) { return *reinterpret_cast<const typename V2T<T>::t*>(p); }
+
+__device__ __forceinline__ float brsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double brsqrt(double x) { return rsqrt(x); }
+// s = sqrt(x), is = 1/sqrt(x) for x > 0 from one reciprocal square root (+ one correction step for s)
+__device__ __forceinline__ void sqrtInv(float x, float& s, float& is) { is = rsqrtf(x); s = x * is; }
+__device__ __forceinline__ void sqrtInv(double x, double& s, double& is) {
+  is = rsqrt(x);
+  const double s0 = x * is;
+  s = fma(fma(-s0, s0, x), 0.5 * is, s0);
+}
+
+template <typename T> __device__ __forceinline__ T* crec(GS<T>& S, T* gs, int c, int nw) {
+  return c < nw ? S.wrec + c * CRW : (c - nw < NHS ? S.hrec + (c - nw) * CRH : gs + (c - nw - NHS) * CRH);
+}
+
+// ---------------------------------------------------------------------------------------------- smooth dynamics
+// Every lane evaluates the (small, serial) smooth dynamics of its environment redundantly; the results go to shared
+// memory (mass matrix, qfrc_smooth -> vb[0], contact geometry, observation kinematics).
+template <typename T> __device__ __noinline__ void gSmooth(const ModelConst<T>& mc, GS<T>& S, bool wantKin) {
+  Geo<T> g; V3<T> capC[3], capU[3]; KinOut<T> kin;
+  smoothDynamics<T, false, 1>(mc, S.xq, S.xv, S.ctrl, S.M, S.vb[0], g, capC, capU, wantKin ? &kin : (KinOut<T>*)nullptr);
+  T* ge = S.geo;
+  st3(ge + GE_PB, g.pB); st3(ge + GE_PL, g.pL);
+  st3(ge + GE_RB, g.RB.c0); st3(ge + GE_RB + 3, g.RB.c1); st3(ge + GE_RB + 6, g.RB.c2);
+  st3(ge + GE_RL, g.RL.c0); st3(ge + GE_RL + 3, g.RL.c1); st3(ge + GE_RL + 6, g.RL.c2);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    st3(ge + GE_AW + 3 * i, g.aw[i]); st3(ge + GE_HW + 3 * i, g.hw[i]);
+    st3(ge + GE_CC + 3 * i, capC[i]); st3(ge + GE_CU + 3 * i, capU[i]);
+  }
+  if (wantKin) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) S.kin[k] = kin.quatB[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { S.kin[4 + k] = kin.cvel_ang[k]; S.kin[7 + k] = kin.cvel_lin[k]; S.kin[10 + k] = kin.posB[k]; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- Hessian + Cholesky + solve
+// Assembles column gi of H = M + sum_{c < ncon, zone != 0} J_c' W_c J_c in registers, factorises H = L L' across the
+// group and returns x[gi] of H x = b (b: one value per dof lane).  ncon = 0 gives M^-1 b (qacc_smooth).
+template <typename T>
+__device__ __noinline__ T gHessSolve(GS<T>& S, const T* gs, int ncon, int nw, T b, const Ln L) {
+  const int gi = L.gi;
+  T h[NV];
+#pragma unroll
+  for (int k = 0; k < NV; k++) h[k] = S.M[k * MS + gi];
+  // wheel pairs: dense 15-column rows
+#pragma unroll 1
+  for (int c = 0; c < nw; c++) {
+    if ((S.cst[c] & 3) == 0) continue;
+    const T* rec = S.wrec + c * CRW;
+    const T a0 = rec[gi], a1 = rec[16 + gi], a2 = rec[32 + gi];
+    const typename V2T<T>::t w01 = ld2(rec + OSW), w23 = ld2(rec + OSW + 2), w45 = ld2(rec + OSW + 4);
+    const T t0 = w01.x * a0 + w23.y * a1 + w45.x * a2;   // W = [w0 w3 w4; w3 w1 w5; w4 w5 w2]
+    const T t1 = w23.y * a0 + w01.y * a1 + w45.y * a2;
+    const T t2 = w45.x * a0 + w45.y * a1 + w23.x * a2;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+      const typename V2T<T>::t r0 = ld2(rec + k), r1 = ld2(rec + 16 + k), r2 = ld2(rec + 32 + k);
+      h[k] += r0.x * t0 + r1.x * t1 + r2.x * t2;
+      if (k + 1 < NV) h[k + 1] += r0.y * t0 + r1.y * t1 + r2.y * t2;
+    }
+  }
+  // terrain pair: only the ball dofs 9..14 (rows hold dofs 8..15)
+  const bool bl = gi >= 9;
+#pragma unroll 1
+  for (int c = nw; c < ncon; c++) {
+    if ((S.cst[c] & 3) == 0) continue;
+    const int hc = c - nw;
+    const T* rec = hc < NHS ? (const T*)(S.hrec + hc * CRH) : gs + (hc - NHS) * CRH;
+    const int o = bl ? gi - 8 : 0;
+    T a0 = rec[o], a1 = rec[8 + o], a2 = rec[16 + o];
+    if (!bl) { a0 = 0; a1 = 0; a2 = 0; }
+    const typename V2T<T>::t w01 = ld2(rec + OSH), w23 = ld2(rec + OSH + 2), w45 = ld2(rec + OSH + 4);
+    const T t0 = w01.x * a0 + w23.y * a1 + w45.x * a2;
+    const T t1 = w23.y * a0 + w01.y * a1 + w45.y * a2;
+    const T t2 = w45.x * a0 + w45.y * a1 + w23.x * a2;
+#pragma unroll
+    for (int k = 8; k < 16; k += 2) {
+      const typename V2T<T>::t r0 = ld2(rec + k - 8), r1 = ld2(rec + k), r2 = ld2(rec + 8 + k);
+      if (k >= 9) h[k] += r0.x * t0 + r1.x * t1 + r2.x * t2;
+      if (k + 1 < NV) h[k + 1] += r0.y * t0 + r1.y * t1 + r2.y * t2;
+    }
+  }
+  // ---- right-looking Cholesky, column per lane, forward substitution fused
+  T myinv = 0, y = b;
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    T piv = gget(h[j], j, L.mask);
+    piv = piv < (T)1e-15 ? (T)1e-15 : piv;
+    const T inv = brsqrt(piv);
+    const T l = h[j] * inv;                       // lanes i >= j: L(i,j)  (lane j: sqrt(pivot))
+    if (gi >= j) h[j] = l;
+    if (gi == j) myinv = inv;
+    const T yj = gget(y, j, L.mask) * inv;        // y_j = (b_j - sum_{k<j} L(j,k) y_k) / L(j,j)
+    if (gi == j) y = yj;
+    const T lz = gi > j ? l : (T)0;
+    y -= lz * yj;
+    if (j < NV - 1) {
+      T* col = S.col[j & 1];
+      if (G == 16 || L.gl < 16) col[L.gl] = l;
+      __syncwarp(L.mask);
+      // lanes i > j: A(k,i) -= L(i,j) L(k,j).  Lane j keeps the unscaled column (L(k,j) = h[k] * myinv).
+#pragma unroll
+      for (int k = (j + 1) & ~1; k < 16; k += 2) {
+        const typename V2T<T>::t cc = ld2(col + k);
+        if (k > j && k < NV) h[k] -= lz * cc.x;
+        if (k + 1 < NV) h[k + 1] -= lz * cc.y;
+      }
+    }
+  }
+  // ---- backward substitution L' x = y
+  T x = 0, s = 0;
+#pragma unroll
+  for (int k = NV - 1; k >= 0; k--) {
+    const T cand = (y - myinv * s) * myinv;       // valid on lane k
+    const T xk = gget(cand, k, L.mask);
+    if (gi == k) x = xk;
+    if (k > 0) s += h[k] * xk;                    // lanes j < k: h[k] = L(k,j) / myinv_j
+  }
+  return x;
+}
+
+// r[gi] = sum_k M(gi,k) v[k] for a published vector v (shared, 16 entries, v[15] finite)
+template <typename T> __device__ __forceinline__ T gSymv(const GS<T>& S, const T* v, int gi) {
+  T acc = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    const typename V2T<T>::t p = ld2(v + k);
+    acc += S.M[k * MS + gi] * p.x;
+    if (k + 1 < NV) acc += S.M[(k + 1) * MS + gi] * p.y;
+  }
+  return acc;
+}
+
+// out[k] = J_c[k] . v for the contact record `rec` (wheel: 15 dofs, terrain: dofs 8..15); v: published vector
+template <typename T> __device__ __forceinline__ void rowsDot(const T* rec, bool wheel, const T* v, T* out) {
+  const int n2 = wheel ? 8 : 4, rs = wheel ? 16 : 8;
+  const T* vv = wheel ? v : v + 8;
+  T a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 2
+  for (int p = 0; p < n2; p++) {
+    const typename V2T<T>::t x = ld2(vv + 2 * p), r0 = ld2(rec + 2 * p), r1 = ld2(rec + rs + 2 * p), r2 = ld2(rec + 2 * rs + 2 * p);
+    a0 += r0.x * x.x + r0.y * x.y; a1 += r1.x * x.x + r1.y * x.y; a2 += r2.x * x.x + r2.y * x.y;
+  }
+  out[0] = a0; out[1] = a1; out[2] = a2;
+}
+
+// ---------------------------------------------------------------------------------------------- per-contact cone math
+// zone logic of mj_constraintUpdate for one elliptic contact; returns cost; state: 0 satisfied, 1 quadratic, 2 cone
+template <typename T>
+__device__ __forceinline__ T coneLane(const ModelConst<T>& mc, int k, T D0, const T* jar, T* frc, T* h, int& state, bool wantH) {
+  const T mu = mc.mu[k], f1 = mc.f1[k], f2 = mc.f2[k];
+  const T U0 = jar[0] * mu, U1 = jar[1] * f1, U2 = jar[2] * f2;
+  const T N = U0, Tsq = U1 * U1 + U2 * U2;
+  T Tn = 0, iT = 0;
+  if (Tsq > 0) sqrtInv(Tsq, Tn, iT);
+  if (N >= mu * Tn || (Tn <= 0 && N >= 0)) { frc[0] = frc[1] = frc[2] = 0; state = 0; return 0; }
+  if (mu * N + Tn <= 0 || (Tn <= 0 && N < 0)) {
+    const T D1 = D0 * mc.d1r[k], D2 = D0 * mc.d2r[k];
+    frc[0] = -D0 * jar[0]; frc[1] = -D1 * jar[1]; frc[2] = -D2 * jar[2]; state = 1;
+    if (wantH) { h[0] = D0; h[1] = D1; h[2] = D2; h[3] = 0; h[4] = 0; h[5] = 0; }
+    return (T)0.5 * (D0 * jar[0] * jar[0] + D1 * jar[1] * jar[1] + D2 * jar[2] * jar[2]);
+  }
+  const T Dm = D0 * mc.dmr[k];
+  const T NT = N - mu * Tn;
+  frc[0] = -Dm * NT * mu;
+  const T sc = -frc[0] * iT;
+  frc[1] = sc * f1 * U1; frc[2] = sc * f2 * U2;
+  state = 2;
+  if (wantH) {
+    const T muN_T3 = mu * N * iT * iT * iT, dg = mu * mu - mu * N * iT;
+    h[0] = Dm * mu * mu;
+    h[1] = Dm * f1 * f1 * (muN_T3 * U1 * U1 + dg);
+    h[2] = Dm * f2 * f2 * (muN_T3 * U2 * U2 + dg);
+    h[3] = Dm * mu * f1 * (-mu * U1 * iT);
+    h[4] = Dm * mu * f2 * (-mu * U2 * iT);
+    h[5] = Dm * f1 * f2 * (muN_T3 * U1 * U2);
+  }
+  return (T)0.5 * Dm * NT * NT;
+}
+
+template <typename T> struct LsPt { T alpha, cost, d1, d2; };
+template <typename T> struct LsCtx { T qG0, qG1, qG2; };
+
+// cost and derivatives of the 1-D line-search objective at alpha (PrimalEval); uniform over the group
+template <typename T>
+__device__ __noinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, const T* gs, int ncon, int nw, const LsCtx<T> q, T alpha, const Ln L) {
+  T cost = 0, d1 = 0, d2 = 0;
+#pragma unroll 1
+  for (int c = L.gl; c < ncon; c += G) {
+    const bool wheel = c < nw;
+    const T* sc = crec(S, (T*)gs, c, nw) + (wheel ? OSW : OSH);
+    const int k = wheel ? 0 : 1;
+    const T mu = mc.mu[k];
+    const typename V2T<T>::t l01 = ld2(sc + O_LS), l23 = ld2(sc + O_LS + 2), l4q = ld2(sc + O_LS + 4), lq = ld2(sc + O_LS + 6);
+    const T U0 = l01.x, V0 = l01.y, UU = l23.x, UV = l23.y, VV = l4q.x;
+    const T N = U0 + alpha * V0, Tsq = UU + alpha * ((T)2 * UV + alpha * VV);
+    bool bottom = false;
+    if (Tsq <= 0) bottom = N < 0;
+    else {
+      T Tn, iT; sqrtInv(Tsq, Tn, iT);
+      if (N >= mu * Tn) {}
+      else if (mu * N + Tn <= 0) bottom = true;
+      else {
+        const T Dm = sc[O_D0] * mc.dmr[k];
+        const T b = UV + alpha * VV;
+        const T T1 = b * iT, T2 = VV * iT - b * T1 * iT * iT;
+        const T NT = N - mu * Tn, dNT = V0 - mu * T1;
+        cost += (T)0.5 * Dm * NT * NT; d1 += Dm * NT * dNT; d2 += Dm * (dNT * dNT - NT * mu * T2);
+      }
+    }
+    if (bottom) { cost += l4q.y + alpha * (lq.x + alpha * lq.y); d1 += lq.x + (T)2 * alpha * lq.y; d2 += (T)2 * lq.y; }
+  }
+  cost = gsum(cost, L.mask); d1 = gsum(d1, L.mask); d2 = gsum(d2, L.mask);
+  LsPt<T> p; p.alpha = alpha;
+  p.cost = q.qG0 + alpha * (q.qG1 + alpha * q.qG2) + cost; p.d1 = q.qG1 + (T)2 * alpha * q.qG2 + d1; p.d2 = (T)2 * q.qG2 + d2;
+  if (p.d2 < (T)1e-15) p.d2 = (T)1e-15;
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------- group Newton solver
+template <typename T> struct GNewton {
+  const ModelConst<T>& mc; GS<T>& S; T* gs; const Ln L; const int ncon, nw;
+  const bool fast;   // fast solver mode: inexact line search (stop when |phi'| <= 1e-3 |phi'(0)|), same minimiser of the outer problem
+  T qfs, qas;        // dof-lane registers
+  T qacc, Ma, grad, search, Mv;
+  T cost, gauss;
+  __device__ GNewton(const ModelConst<T>& m, GS<T>& s, T* g, const Ln l, int n, int w, bool f, T qf, T qa)
+      : mc(m), S(s), gs(g), L(l), ncon(n), nw(w), fast(f), qfs(qf), qas(qa) {}
+
+  // forces / zones / cone Hessian blocks at the current jar (contact lanes), cost, gradient (dof lanes)
+  __device__ __forceinline__ void costGrad() {
+    T cpart = 0;
+#pragma unroll 1
+    for (int c = L.gl; c < ncon; c += G) {
+      const bool wheel = c < nw;
+      T* sc = crec(S, gs, c, nw) + (wheel ? OSW : OSH);
+      T h[6], f[3]; int st;
+      const T jr[3] = {sc[O_JAR], sc[O_JAR + 1], sc[O_JAR + 2]};
+      cpart += coneLane(mc, wheel ? 0 : 1, sc[O_D0], jr, f, h, st, true);
+      S.cst[c] = (unsigned char)st;
+      sc[O_FRC] = f[0]; sc[O_FRC + 1] = f[1]; sc[O_FRC + 2] = f[2];
+      if (st) {
+#pragma unroll
+        for (int m = 0; m < 6; m++) sc[O_W + m] = h[m];
+      }
+    }
+    const bool dof = L.gl < NV;
+    gauss = gsum(dof ? (T)0.5 * (Ma - qfs) * (qacc - qas) : (T)0, L.mask);
+    cost = gauss + gsum(cpart, L.mask);
+    __syncwarp(L.mask);
+    T g = Ma - qfs;
+    const int gi = L.gi;
+#pragma unroll 1
+    for (int c = 0; c < nw; c++) {
+      if ((S.cst[c] & 3) == 0) continue;
+      const T* rec = S.wrec + c * CRW;
+      g -= rec[gi] * rec[OSW + O_FRC] + rec[16 + gi] * rec[OSW + O_FRC + 1] + rec[32 + gi] * rec[OSW + O_FRC + 2];
+    }
+    if (gi >= 9) {
+#pragma unroll 1
+      for (int c = nw; c < ncon; c++) {
+        if ((S.cst[c] & 3) == 0) continue;
+        const int hc = c - nw;
+        const T* rec = hc < NHS ? (const T*)(S.hrec + hc * CRH) : (const T*)(gs + (hc - NHS) * CRH);
+        g -= rec[gi - 8] * rec[OSH + O_FRC] + rec[gi] * rec[OSH + O_FRC + 1] + rec[8 + gi] * rec[OSH + O_FRC + 2];
+      }
+    }
+    grad = dof ? g : (T)0;
+  }
+
+  // exact line search of mj_solNewton (PrimalSearch) as a state machine around a single evaluation site
+  __device__ __forceinline__ T lineSearch(T scale) {
+    const bool dof = L.gl < NV;
+    const T sn2 = gsum(dof ? search * search : (T)0, L.mask);
+    if (sn2 < (T)1e-30) return 0;
+    T snorm, isn; sqrtInv(sn2, snorm, isn);
+    T gtol = mc.tolerance * mc.ls_tolerance * snorm / scale;
+    if (G == 16 || L.gl < 16) S.vb[0][L.gl] = dof ? search : (T)0;
+    __syncwarp(L.mask);
+    Mv = gSymv(S, S.vb[0], L.gi);
+    // jv = J search and the per-contact coefficients of the search (PrimalPrepare)
+#pragma unroll 1
+    for (int c = L.gl; c < ncon; c += G) {
+      const bool wheel = c < nw;
+      T* rec = crec(S, gs, c, nw);
+      T* sc = rec + (wheel ? OSW : OSH);
+      T w[3]; rowsDot(rec, wheel, S.vb[0], w);
+      sc[O_JV] = w[0]; sc[O_JV + 1] = w[1]; sc[O_JV + 2] = w[2];
+      const int k = wheel ? 0 : 1;
+      const T D0 = sc[O_D0], D1 = D0 * mc.d1r[k], D2 = D0 * mc.d2r[k];
+      const T mu = mc.mu[k], f1 = mc.f1[k], f2 = mc.f2[k];
+      const T j0 = sc[O_JAR], j1 = sc[O_JAR + 1], j2 = sc[O_JAR + 2];
+      const T u1 = j1 * f1, u2 = j2 * f2, v1 = w[1] * f1, v2 = w[2] * f2;
+      T* ls = sc + O_LS;
+      ls[0] = j0 * mu; ls[1] = w[0] * mu;
+      ls[2] = u1 * u1 + u2 * u2; ls[3] = u1 * v1 + u2 * v2; ls[4] = v1 * v1 + v2 * v2;
+      ls[5] = (T)0.5 * (D0 * j0 * j0 + D1 * j1 * j1 + D2 * j2 * j2);
+      ls[6] = D0 * j0 * w[0] + D1 * j1 * w[1] + D2 * j2 * w[2];
+      ls[7] = (T)0.5 * (D0 * w[0] * w[0] + D1 * w[1] * w[1] + D2 * w[2] * w[2]);
+    }
+    LsCtx<T> q;
+    q.qG0 = gauss;
+    q.qG1 = gsum(dof ? search * (Ma - qfs) : (T)0, L.mask);
+    q.qG2 = gsum(dof ? (T)0.5 * search * Mv : (T)0, L.mask);
+    __syncwarp(L.mask);
+    // states: 0 p0, 1 first Newton point, 2 one-sided Newton iteration, 3 p1next, 4 midpoint, 5 p1 re-bracket, 6 p2 re-bracket
+    LsPt<T> p1, p2, p1n, p2n, pmid;
+    T p0cost = 0, dir = 1, result = 0, a = 0;
+    int st = 0, it = 0, b1 = 0;
+    bool upd = false;
+    const int maxit = mc.ls_iterations;
+#pragma unroll 1
+    for (;;) {
+      const LsPt<T> p = lsEval(mc, S, gs, ncon, nw, q, a, L);
+      bool done = false;
+      if (st == 0) {
+        p0cost = p.cost; p1 = p; p2 = p; pmid = p; p1n = p; p2n = p;
+        if (fast) gtol = bmax(gtol, (T)1e-3 * babs(p.d1));
+        a = p.alpha - p.d1 / p.d2; st = 1;
+      } else if (st == 1) {
+        if (!(p0cost < p.cost)) p1 = p;        // p1 = better of p0, first Newton point
+        if (babs(p1.d1) < gtol) { result = p1.alpha; done = true; }
+        else {
+          dir = p1.d1 < 0 ? (T)1 : (T)-1;
+          if (p1.d1 * dir <= -gtol && it < maxit) { p2 = p1; upd = true; a = p1.alpha - p1.d1 / p1.d2; st = 2; }
+          else { result = p1.alpha; done = true; }   // !upd
+        }
+      } else if (st == 2) {
+        p1 = p; it++;
+        if (babs(p1.d1) < gtol) { result = p1.alpha; done = true; }
+        else if (p1.d1 * dir <= -gtol && it < maxit) { p2 = p1; a = p1.alpha - p1.d1 / p1.d2; }
+        else if (it >= maxit) { result = p1.alpha; done = true; }
+        else { p2n = p1; a = p1.alpha - p1.d1 / p1.d2; st = 3; }
+      } else if (st == 3) {
+        p1n = p;
+        a = (T)0.5 * (p1.alpha + p2.alpha); st = 4;
+      } else {
+        if (st == 4) { pmid = p; it++; b1 = -1; }
+        else if (st == 5) p1n = p;
+        else p2n = p;
+        // continue the body of the bracketing loop from where the pending evaluation was requested
+        if (st == 4) {
+          if (babs(p1n.d1) < gtol) { result = p1n.alpha; done = true; }
+          else if (babs(p2n.d1) < gtol) { result = p2n.alpha; done = true; }
+          else if (babs(pmid.d1) < gtol) { result = pmid.alpha; done = true; }
+        }
+        if (!done) {
+          bool need = false;
+          if (st == 4) {   // bracket(p1, cand, p1n)
+            int flag = 0;
+            const LsPt<T> cand[3] = {p1n, p2n, pmid};
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+              if (p1.d1 < 0 && cand[i].d1 < 0 && p1.d1 < cand[i].d1) { p1 = cand[i]; flag = 1; }
+              else if (p1.d1 > 0 && cand[i].d1 > 0 && p1.d1 > cand[i].d1) { p1 = cand[i]; flag = 2; }
+            }
+            b1 = flag;
+            if (flag) { a = p1.alpha - p1.d1 / p1.d2; st = 5; need = true; }
+          }
+          if (!need && st != 6) {   // bracket(p2, cand, p2n); cand uses the (possibly refreshed) p1n
+            int flag = 0;
+            const LsPt<T> cand[3] = {p1n, p2n, pmid};
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+              if (p2.d1 < 0 && cand[i].d1 < 0 && p2.d1 < cand[i].d1) { p2 = cand[i]; flag = 1; }
+              else if (p2.d1 > 0 && cand[i].d1 > 0 && p2.d1 > cand[i].d1) { p2 = cand[i]; flag = 2; }
+            }
+            if (flag) { a = p2.alpha - p2.d1 / p2.d2; st = 6; need = true; }
+            else if (!b1) { result = pmid.cost < p0cost ? pmid.alpha : (T)0; done = true; }
+          }
+          if (!need && !done) {   // next trip of the bracketing loop
+            if (it < maxit) { a = (T)0.5 * (p1.alpha + p2.alpha); st = 4; }
+            else {
+              if (p1.cost <= p2.cost && p1.cost < p0cost) result = p1.alpha;
+              else if (p2.cost <= p1.cost && p2.cost < p0cost) result = p2.alpha;
+              else result = 0;
+              done = true;
+            }
+          }
+        }
+      }
+      if (done) break;
+    }
+    return result;
+  }
+
+  // in: aref parked in the jv slot of every record, `warm` = qacc_warmstart of this dof lane.  Returns qacc; niter by reference.
+  __device__ __forceinline__ T run(T warm, int& niter) {
+    const bool dof = L.gl < NV;
+    // warm-start choice: total cost at qacc_warmstart (-> vb[0]) and at qacc_smooth (-> vb[1])
+    if (G == 16 || L.gl < 16) { S.vb[0][L.gl] = dof ? warm : (T)0; S.vb[1][L.gl] = dof ? qas : (T)0; }
+    __syncwarp(L.mask);
+    const T mw = gSymv(S, S.vb[0], L.gi);
+    T cw = dof ? (T)0.5 * (mw - qfs) * (warm - qas) : (T)0, cs = 0;
+#pragma unroll 1
+    for (int c = L.gl; c < ncon; c += G) {
+      const bool wheel = c < nw;
+      T* rec = crec(S, gs, c, nw);
+      T* sc = rec + (wheel ? OSW : OSH);
+      T jw[3], js[3], f[3], h[6]; int st;
+      rowsDot(rec, wheel, S.vb[0], jw); rowsDot(rec, wheel, S.vb[1], js);
+#pragma unroll
+      for (int m = 0; m < 3; m++) { const T ar = sc[O_JV + m]; jw[m] -= ar; js[m] -= ar; }
+      cw += coneLane(mc, wheel ? 0 : 1, sc[O_D0], jw, f, h, st, false);
+      cs += coneLane(mc, wheel ? 0 : 1, sc[O_D0], js, f, h, st, false);
+      // park both candidates: jar <- warm-start residual, LS[0..2] <- smooth residual
+      sc[O_JAR] = jw[0]; sc[O_JAR + 1] = jw[1]; sc[O_JAR + 2] = jw[2];
+      sc[O_LS] = js[0]; sc[O_LS + 1] = js[1]; sc[O_LS + 2] = js[2];
+    }
+    cw = gsum(cw, L.mask); cs = gsum(cs, L.mask);
+    const bool useSmooth = cw > cs;
+    if (useSmooth) {
+      qacc = qas; Ma = qfs;
+#pragma unroll 1
+      for (int c = L.gl; c < ncon; c += G) {
+        T* sc = crec(S, gs, c, nw) + (c < nw ? OSW : OSH);
+        sc[O_JAR] = sc[O_LS]; sc[O_JAR + 1] = sc[O_LS + 1]; sc[O_JAR + 2] = sc[O_LS + 2];
+      }
+    } else { qacc = warm; Ma = mw; }
+    __syncwarp(L.mask);
+    const T scale = (T)1 / (mc.meaninertia * (T)NV);
+    int iter = 0;
+    costGrad();
+#pragma unroll 1
+    while (iter < mc.iterations) {
+      search = -gHessSolve(S, gs, ncon, nw, grad, L);
+      const T alpha = lineSearch(scale);
+      if (alpha == 0) break;
+      qacc += alpha * search; Ma += alpha * Mv;
+#pragma unroll 1
+      for (int c = L.gl; c < ncon; c += G) {
+        T* sc = crec(S, gs, c, nw) + (c < nw ? OSW : OSH);
+        sc[O_JAR] += alpha * sc[O_JV]; sc[O_JAR + 1] += alpha * sc[O_JV + 1]; sc[O_JAR + 2] += alpha * sc[O_JV + 2];
+      }
+      const T old = cost;
+      costGrad();
+      iter++;
+      const T gn = gsum(grad * grad, L.mask);
+      if (scale * (old - cost) < mc.tolerance || scale * bsqrt(gn) < mc.tolerance) break;
+    }
+    niter = iter;
+    return qacc;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------- contact records
+// impedance / regulariser / reference acceleration (mj_makeImpedance, mj_referenceConstraint) -> scalar block
+template <typename T>
+__device__ __forceinline__ void finishRecord(const ModelConst<T>& mc, T* sc, int ty, T dist, const T* vel) {
+  const T x = babs(dist) / mc.solimp[2];
+  T imp;
+  if (x >= 1) imp = mc.solimp[1];
+  else if (x <= 0) imp = mc.solimp[0];
+  else {
+    const T mid = mc.solimp[3];
+    const T y = x <= mid ? x * x / mid : (T)1 - ((T)1 - x) * ((T)1 - x) / ((T)1 - mid);
+    imp = mc.solimp[0] + y * (mc.solimp[1] - mc.solimp[0]);
+  }
+  const T R0 = bmax((T)1e-15, ((T)1 - imp) * mc.dA[ty] / imp);
+  sc[O_D0] = (T)1 / R0;
+  // aref is parked in the jv slot until the solver has formed jar = J qacc - aref
+  sc[O_JV] = -mc.B * vel[0] - mc.K * imp * dist; sc[O_JV + 1] = -mc.B * vel[1]; sc[O_JV + 2] = -mc.B * vel[2];
+}
+
+// Contact generation (3 patched sphere-capsule pairs, tools/mujoco_fix.patch:9-18, + ball vs heightfield prisms in the
+// reference scan order) with the constraint rows built in place by the lane that found the contact.
+// Returns the contact count; nw = number of wheel contacts (they come first).
+template <typename T>
+__device__ __noinline__ int gCollide(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, const Ln L, int& nwOut) {
+  const int gl = L.gl;
+  const unsigned lt = (1u << gl) - 1u;
+  const int gsh = (threadIdx.x & 31) & ~(G - 1);     // bit position of the group's lane 0 in a ballot
+  const T* ge = S.geo;
+  const V3<T> pL = ld3(ge + GE_PL);
+  const Rot<T> RL = {ld3(ge + GE_RL), ld3(ge + GE_RL + 3), ld3(ge + GE_RL + 6)};
+  const V3<T> bc = pL + RL.c2 * mc.dz;
+  const T br = mc.ball_r;
+  // ---- wheel pairs on lanes 0..2
+  bool hit = false; T dist = 0; V3<T> n = mk((T)0, (T)0, (T)1), pos = n;
+  V3<T> cu = n;
+  if (gl < 3) {
+    const V3<T> cc = ld3(ge + GE_CC + 3 * gl); cu = ld3(ge + GE_CU + 3 * gl);
+    T x = dot(cu, bc - cc);
+    x = x > mc.wheel_hl ? mc.wheel_hl : (x < -mc.wheel_hl ? -mc.wheel_hl : x);
+    const V3<T> dif = cc + cu * x - bc;
+    const T cd = bsqrt(dot(dif, dif)), mind = br + mc.wheel_r;
+    if (cd < mind) { hit = true; n = dif * ((T)1 / cd); dist = cd - mind; pos = bc + n * (br + (T)0.5 * dist); }
+  }
+  unsigned m = (__ballot_sync(L.mask, hit) >> gsh) & ((G == 32) ? 0xffffffffu : 0xffffu);
+  const int nw = __popc(m);
+  if (hit) {
+    const int c = __popc(m & lt), ty = gl;
+    T* rec = S.wrec + c * CRW;
+    T F[9] = {n.x, n.y, n.z, cu.x, cu.y, cu.z, 0, 0, 0};
+    makeFrame(F, true);
+    const V3<T> pB = ld3(ge + GE_PB);
+    const Rot<T> RB = {ld3(ge + GE_RB), ld3(ge + GE_RB + 3), ld3(ge + GE_RB + 6)};
+    const V3<T> rB = pos - pB, rL = pos - pL;
+    const V3<T> cb0 = cross(RB.c0, rB), cb1 = cross(RB.c1, rB), cb2 = cross(RB.c2, rB);
+    const V3<T> cl0 = cross(rL, RL.c0), cl1 = cross(rL, RL.c1), cl2 = cross(rL, RL.c2);
+    const V3<T> ah = cross(ld3(ge + GE_AW + 3 * ty), pos - ld3(ge + GE_HW + 3 * ty));
+    T vel[3];
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+      T* jr = rec + k * 16;
+      const V3<T> fk = mk(F[3 * k], F[3 * k + 1], F[3 * k + 2]);
+      jr[0] = fk.x; jr[1] = fk.y; jr[2] = fk.z;
+      jr[3] = dot(fk, cb0); jr[4] = dot(fk, cb1); jr[5] = dot(fk, cb2);
+      const T hq = dot(fk, ah);
+      jr[6] = ty == 0 ? hq : (T)0; jr[7] = ty == 1 ? hq : (T)0; jr[8] = ty == 2 ? hq : (T)0;
+      jr[9] = -fk.x; jr[10] = -fk.y; jr[11] = -fk.z;
+      jr[12] = dot(fk, cl0); jr[13] = dot(fk, cl1); jr[14] = dot(fk, cl2); jr[15] = 0;
+      T v = 0;
+      for (int q = 0; q < NV; q++) v += jr[q] * S.xv[q];
+      vel[k] = v;
+    }
+    finishRecord(mc, rec + OSW, ty, dist, vel);
+    S.cst[c] = 0;
+  }
+  // ---- ball vs heightfield prisms
+  int cnt = 0;
+  const T sx = mc.hx;
+  const bool skip = (sx < bc.x - br) || (-sx > bc.x + br) || (sx < bc.y - br) || (-sx > bc.y + br) || (zscale < bc.z - br) || (-mc.hbase > bc.z + br);
+  if (!skip) {
+    const T gsc = (T)(HN - 1) / ((T)2 * sx);
+    int cmin = (int)bfloor((bc.x - br + sx) * gsc), cmax = (int)bceil((bc.x + br + sx) * gsc);
+    int rmin = (int)bfloor((bc.y - br + sx) * gsc), rmax = (int)bceil((bc.y + br + sx) * gsc);
+    cmin = cmin < 0 ? 0 : cmin; rmin = rmin < 0 ? 0 : rmin; cmax = cmax > HN - 1 ? HN - 1 : cmax; rmax = rmax > HN - 1 ? HN - 1 : rmax;
+    const int ncols = cmax - cmin, nrows = rmax - rmin, nprism = ncols > 0 && nrows > 0 ? 2 * ncols * nrows : 0;
+    const T dx = (T)2 * sx / (T)(HN - 1), zmin = bc.z - br;
+#pragma unroll 1
+    for (int base = 0; base < nprism && cnt < MAXH; base += G) {
+      const int p = base + gl;
+      hit = false;
+      if (p < nprism) {
+        const int cell = p >> 1, k = p & 1, r = rmin + cell / ncols, c = cmin + cell % ncols;
+        const T x0 = dx * (T)c - sx, x1 = dx * (T)(c + 1) - sx, y0 = dx * (T)r - sx, y1 = dx * (T)(r + 1) - sx;
+        const T ex = bc.x < x0 ? x0 - bc.x : (bc.x > x1 ? bc.x - x1 : (T)0), ey = bc.y < y0 ? y0 - bc.y : (bc.y > y1 ? bc.y - y1 : (T)0);
+        if (ex * ex + ey * ey < br * br) {
+          const T h00 = (T)hf[r * HN + c] * zscale, h10 = (T)hf[r * HN + c + 1] * zscale;
+          const T h01 = (T)hf[(r + 1) * HN + c] * zscale, h11 = (T)hf[(r + 1) * HN + c + 1] * zscale;
+          const V3<T> v01 = mk(x0, y1, h01), v00 = mk(x0, y0, h00), v11 = mk(x1, y1, h11), v10 = mk(x1, y0, h10);
+          const V3<T> ta = k ? v00 : v01, tb = k ? v11 : v00, tc = k ? v10 : v11;
+          if (!(ta.z < zmin && tb.z < zmin && tc.z < zmin)) {
+            const V3<T> q = closestOnTriangle(bc, ta, tb, tc);
+            const V3<T> dv = bc - q;
+            V3<T> nn = cross(tb - ta, tc - ta); if (nn.z < 0) nn = -nn;
+            if (dot(bc - ta, nn) < 0) {   // centre under the top plane: contact only inside this prism's column
+              const V3<T> e1 = tb - ta, e2 = tc - ta, ap = bc - ta;
+              const T u = e1.x * e2.y - e1.y * e2.x;
+              const T sa = (ap.x * e2.y - ap.y * e2.x) / u, tt = (e1.x * ap.y - e1.y * ap.x) / u;
+              if (!(sa < 0 || tt < 0 || sa + tt > 1)) {
+                hit = true; n = nn * ((T)1 / bsqrt(dot(nn, nn))); dist = dot(ap, n) - br; pos = bc - n * (br + (T)0.5 * dist);
+              }
+            } else {
+              const T dl = bsqrt(dot(dv, dv));
+              if (dl < br && dl >= (T)1e-15) { hit = true; dist = dl - br; n = dv * ((T)1 / dl); pos = q + n * ((T)0.5 * dist); }
+            }
+          }
+        }
+      }
+      m = (__ballot_sync(L.mask, hit) >> gsh) & ((G == 32) ? 0xffffffffu : 0xffffu);
+      if (m == 0) continue;
+      const int rank = cnt + __popc(m & lt);
+      if (hit && rank < MAXH) {
+        const int c = nw + rank;
+        T* rec = rank < NHS ? S.hrec + rank * CRH : gs + (rank - NHS) * CRH;
+        T F[9] = {n.x, n.y, n.z, 0, 0, 0, 0, 0, 0};
+        makeFrame(F, false);
+        const V3<T> rL = pos - pL;
+        // relative velocity = ball - world: linear +f, angular f . (c_m x ... ) with the sign of body 2
+        const V3<T> cl0 = cross(RL.c0, rL), cl1 = cross(RL.c1, rL), cl2 = cross(RL.c2, rL);
+        T vel[3];
+#pragma unroll 1
+        for (int k = 0; k < 3; k++) {
+          T* jr = rec + k * 8;
+          const V3<T> fk = mk(F[3 * k], F[3 * k + 1], F[3 * k + 2]);
+          jr[0] = 0; jr[1] = fk.x; jr[2] = fk.y; jr[3] = fk.z;
+          jr[4] = dot(fk, cl0); jr[5] = dot(fk, cl1); jr[6] = dot(fk, cl2); jr[7] = 0;
+          T v = 0;
+          for (int q = 1; q < 7; q++) v += jr[q] * S.xv[8 + q];
+          vel[k] = v;
+        }
+        finishRecord(mc, rec + OSH, 3, dist, vel);
+        S.cst[c] = 0;
+      }
+      cnt += __popc(m);
+    }
+    cnt = cnt < MAXH ? cnt : MAXH;
+  }
+  __syncwarp(L.mask);
+  nwOut = nw;
+  return nw + cnt;
+}
+
+// ---------------------------------------------------------------------------------------------- one mj_forward (group)
+// in: S.xq, S.xv, S.ctrl, warm (dof-lane register)   out: returns qacc of this dof lane (and S.xq normalised).
+template <typename T>
+__device__ __noinline__ T gForward(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, const Ln L, T warm, bool fast,
+                                   bool wantKin, int& nconOut, int& niterOut, T* qasOut = nullptr, T* qfsOut = nullptr) {
+  if (L.gl == 0) normalizeQuats(S.xq);
+  __syncwarp(L.mask);
+  gSmooth(mc, S, wantKin);
+  __syncwarp(L.mask);
+  const T qfs = L.gl < NV ? S.vb[0][L.gi] : (T)0;
+  __syncwarp(L.mask);
+  const T qas = gHessSolve(S, gs, 0, 0, qfs, L);   // qacc_smooth = M^-1 qfrc_smooth
+  if (qasOut) { *qasOut = qas; *qfsOut = qfs; }
+  int nw;
+  const int ncon = gCollide(mc, S, hf, zscale, gs, L, nw);
+  nconOut = ncon; niterOut = 0;
+  if (ncon == 0) return qas;
+  GNewton<T> nwt(mc, S, gs, L, ncon, nw, fast, qfs, qas);
+  int niter;
+  const T qacc = nwt.run(warm, niter);
+  niterOut = niter;
+  return qacc;
+}
+
+// quaternion/position integration is done by lane 0 through one shared (non-inlined) copy of the code
+template <typename T> __device__ __noinline__ void gIntegrate(T* dst, const T* src, const T* vel, T h) {
+  for (int i = 0; i < NQ; i++) dst[i] = src[i];
+  integratePos(dst, vel, h);
+}
+
+// ---------------------------------------------------------------------------------------------- RK4 (group)
+// in: S.xq/S.xv = state, S.ctrl, warm ; out: S.xq/S.xv = new state, warm = last-stage qacc, S.kin = last-stage kinematics.
+// qlast (global, NQ) receives the last-stage configuration when non-null.
+template <typename T>
+__device__ void gRk4(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, T* qlast, const Ln L, T& warm, bool chain_warm,
+                     int& ncmax, int& nitsum) {
+  const T h = mc.timestep;
+  const bool dof = L.gl < NV;
+  if (L.gl == 0) normalizeQuats(S.xq);
+  __syncwarp(L.mask);
+  for (int k = L.gl; k < NQ; k += G) S.q0[k] = S.xq[k];
+  const T v0 = S.xv[L.gi];
+  T xv = v0, sumv = 0, suma = 0, qacc = 0;
+  __syncwarp(L.mask);
+  ncmax = 0; nitsum = 0;
+#pragma unroll 1
+  for (int st = 0; st < 5; st++) {
+    if (st < 4) {
+      int nc, ni;
+      qacc = gForward(mc, S, hf, zscale, gs, L, warm, chain_warm, st == 3, nc, ni);
+      ncmax = nc > ncmax ? nc : ncmax; nitsum += ni;
+      const T bw = (st == 0 || st == 3) ? (T)(1.0 / 6.0) : (T)(1.0 / 3.0);
+      sumv += bw * xv; suma += bw * qacc;
+      if (st == 3 && qlast) { for (int k = L.gl; k < NQ; k += G) qlast[k] = S.xq[k]; }
+      // fast mode: stages 2..4 start their Newton solve from the previous stage's solution instead of the previous
+      // step's qacc_warmstart (same unique minimiser within the solver tolerance, fewer iterations)
+      if (chain_warm && st < 3) warm = qacc;
+      __syncwarp(L.mask);
+    }
+    // stage advance (st < 3: X0 + a_st h (v_st, acc_st)) or final update (st == 4: X0 + h sum_j B_j (v_j, acc_j))
+    if (st != 3) {
+      const T ha = st == 4 ? h : ((st == 2) ? h : (T)0.5 * h);
+      if (st == 4) { if (G == 16 || L.gl < 16) S.vb[0][L.gl] = dof ? sumv : (T)0; __syncwarp(L.mask); }
+      if (L.gl == 0) gIntegrate(S.xq, S.q0, st == 4 ? (const T*)S.vb[0] : (const T*)S.xv, ha);
+      __syncwarp(L.mask);
+      xv = v0 + ha * (st == 4 ? suma : qacc);
+      if (st == 4) warm = qacc;
+      if (dof) S.xv[L.gl] = xv;
+      __syncwarp(L.mask);
+    }
+  }
+}
+
+}  // namespace bbg

@@ -5,8 +5,11 @@ from openballbot_rl_b200.engine import BallbotEngine
 ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=4096); ap.add_argument("--steps", type=int, default=70)
 ap.add_argument("--precision", type=int, default=64); ap.add_argument("--terrain", default="flat")
-ap.add_argument("--kernel", default="warp"); ap.add_argument("--solver", default="exact")
+ap.add_argument("--kernel", default="warp"); ap.add_argument("--solver", default="exact"); ap.add_argument("--lib", default=None)
 a = ap.parse_args()
+if a.lib:
+    from openballbot_rl_b200 import _lib
+    _lib.LIB_PATH = a.lib   # A/B experiments only: an alternative build of the same CUDA library
 eng = BallbotEngine(num_envs=a.envs, precision=a.precision, terrain=a.terrain, cameras=(a.terrain == "perlin"), step_kernel=a.kernel, solver=a.solver, seed=0)
 eng.reset()
 g = torch.Generator(device="cuda"); g.manual_seed(0)

@@ -68,3 +68,6 @@ void hc_model(double* dA4, double* meaninertia, double* masses3 /*m0,mw,mL*/, do
   for (int i = 0; i < 3; i++) c0[i] = m.c0[i];
 }
 }
+#ifdef BB_STATS
+extern "C" long hc_ls_evals() { return bb_stats_ls_evals; }
+#endif
