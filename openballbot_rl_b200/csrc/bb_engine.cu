@@ -58,7 +58,12 @@ struct DevState {
   float* ep_ret; int* ep_len;
   int* counters;   // [0] reset-list length, [1] refresh-list length
   int* reset_list; int* refresh_list;
+  // work-sorted scheduling of the group step kernel: key = Newton iterations of the env's previous step (capped)
+  int* work;       // [N] key of the previous step
+  int* order;      // [N] env indices sorted by descending key (heavy envs first, similar envs share a warp)
+  int* bins;       // [WORK_BINS] histogram of work[] (accumulated by the step kernel) + [WORK_BINS] scatter cursors
 };
+constexpr int WORK_BINS = 64;
 
 __device__ __forceinline__ unsigned long long splitmix(unsigned long long x) {
   x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31);
@@ -168,8 +173,9 @@ __global__ void __launch_bounds__(32 * BB_WPB, BB_WARP_MINBLOCKS) k_step_warp(En
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const bbg::Ln L = bbg::makeLn();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / bbg::G;
-  const int i = (blockIdx.x * (blockDim.x >> 5) + warp) * bbg::EPW + grp;
-  if (i >= p.N) return;
+  const int slot = (blockIdx.x * (blockDim.x >> 5) + warp) * bbg::EPW + grp;
+  if (slot >= p.N) return;
+  const int i = d.order[slot];
   bbg::GS<T>& S = reinterpret_cast<bbg::GS<T>*>(smem_raw)[warp * bbg::EPW + grp];
   T* st = (T*)d.st + (size_t)i * SST;
   // one coalesced record per env: qpos[17] qvel[15] warm[15]
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(32 * BB_WPB, BB_WARP_MINBLOCKS) k_step_warp(En
   int cs = d.cam_steps[i] + 1;
   bool refresh = false;
   if (p.cameras && cs >= p.cam_period) { refresh = true; cs = 0; }
-  int status = 0;
+  int status = 0, key = 0;
   if (!bad) {
     const float* hf = d.hfield + (p.hf_per_env ? (size_t)i * HF_CELLS : 0);
     T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
@@ -205,6 +211,7 @@ __global__ void __launch_bounds__(32 * BB_WPB, BB_WARP_MINBLOCKS) k_step_warp(En
     for (int k = L.gl; k < NQ; k += bbg::G) b2 |= !(babs(S.xq[k]) < (T)1e10);
     bad = __any_sync(L.mask, b2);
     status = ncmax << 8;
+    key = nit < WORK_BINS ? nit : WORK_BINS - 1;
 #pragma unroll
     for (int k = 0; k < 4; k++) kin.quatB[k] = S.kin[k];
 #pragma unroll
@@ -253,6 +260,7 @@ __global__ void __launch_bounds__(32 * BB_WPB, BB_WARP_MINBLOCKS) k_step_warp(En
     io.terminal_obs[16 * i + L.gl] = v;
   }
   if (L.gl == 0) {
+    d.work[i] = key; atomicAdd(&d.bins[key], 1);
     io.rel_image_ts[i] = ob[15];
     io.reward[i] = r; io.terminated[i] = term; io.failure[i] = fail;
     io.pos2d[2 * i] = (float)kin.posB[0]; io.pos2d[2 * i + 1] = (float)kin.posB[1];
@@ -295,7 +303,37 @@ __global__ void k_mask_to_list(EnvParams p, DevState d, const uint8_t* __restric
   d.tseed[i] = drawTerrainSeed(p, i, ep);
   d.reset_list[atomicAdd(&d.counters[0], 1)] = i;
 }
+// k_begin_step, one block of WORK_BINS threads: clears the work-list counters and turns the key histogram of the previous step into
+// the scatter cursors of k_order (descending keys: the longest solves are scheduled first).
 __global__ void k_clear_counters(DevState d) { d.counters[0] = 0; d.counters[1] = 0; }
+__global__ void k_begin_step(DevState d) {
+  __shared__ int h[WORK_BINS];
+  const int t = threadIdx.x;
+  if (t == 0) { d.counters[0] = 0; d.counters[1] = 0; }
+  h[t] = d.bins[t];
+  __syncthreads();
+  int start = 0;
+  for (int k = WORK_BINS - 1; k > t; k--) start += h[k];
+  d.bins[WORK_BINS + t] = start;
+  d.bins[t] = 0;
+}
+// counting-sort scatter: order[] = env indices grouped by key (the order inside a bin is irrelevant: envs are independent)
+__global__ void k_order(int N, DevState d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int key = d.work[i];
+  const unsigned peers = __match_any_sync(__activemask(), key);
+  const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(&d.bins[WORK_BINS + key], __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  d.order[base + __popc(peers & ((1u << lane) - 1u))] = i;
+}
+__global__ void k_init_order(int N, DevState d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) { d.work[i] = 0; d.order[i] = i; }
+  if (i < 2 * WORK_BINS) d.bins[i] = i == 0 ? N : 0;
+}
 
 // --------------------------------------------------------------------------------------------- simplex fBm terrain
 __constant__ unsigned char c_perm[256];
@@ -783,6 +821,8 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   BB_CUDA_C(cudaMalloc(&d.episode, sizeof(unsigned) * N)); BB_CUDA_C(cudaMalloc(&d.tseed, sizeof(int) * N));
   BB_CUDA_C(cudaMalloc(&d.ep_ret, sizeof(float) * N)); BB_CUDA_C(cudaMalloc(&d.ep_len, sizeof(int) * N));
   BB_CUDA_C(cudaMalloc(&d.counters, sizeof(int) * 2));
+  BB_CUDA_C(cudaMalloc(&d.work, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.order, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.bins, sizeof(int) * 2 * WORK_BINS));
+  k_init_order<<<blocksFor(N > 2 * WORK_BINS ? N : 2 * WORK_BINS, 256), 256>>>(N, d);
   BB_CUDA_C(cudaMalloc(&d.reset_list, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.refresh_list, sizeof(int) * N));
   const size_t hfbytes = sizeof(float) * HF_CELLS * (p.hf_per_env ? (size_t)N : 1);
   BB_CUDA_C(cudaMalloc(&d.hfield, hfbytes));
@@ -802,6 +842,7 @@ int bb_destroy(bb_engine* e) {
   if (!e) return BB_OK;
   DevState& d = e->d;
   cudaFree(d.st); cudaFree(d.camq); cudaFree(d.gscr); cudaFree(d.step_count); cudaFree(d.cam_steps); cudaFree(d.episode); cudaFree(d.tseed);
+  cudaFree(d.work); cudaFree(d.order); cudaFree(d.bins);
   cudaFree(d.ep_ret); cudaFree(d.ep_len); cudaFree(d.counters); cudaFree(d.reset_list); cudaFree(d.refresh_list); cudaFree(d.hfield);
   if (e->prof_ev) { for (int i = 0; i < 5 * e->prof_cap; i++) cudaEventDestroy(e->prof_ev[i]); free(e->prof_ev); }
   if (e->host_ready) {
@@ -839,7 +880,8 @@ int bb_step(bb_engine* e, const float* actions_dev, const bb_io* io, void* strea
   const int bs = N >= 148 * 64 * 2 ? 64 : 32;
   cudaEvent_t* ev = nullptr;
   if (e->prof_ev && e->prof_n < e->prof_cap) { ev = e->prof_ev + 5 * (size_t)e->prof_n; e->prof_n++; }
-  k_clear_counters<<<1, 1, 0, s>>>(e->d);
+  if (e->cfg.step_kernel == 1) k_clear_counters<<<1, 1, 0, s>>>(e->d);
+  else { k_begin_step<<<1, WORK_BINS, 0, s>>>(e->d); k_order<<<blocksFor(N, 256), 256, 0, s>>>(N, e->d); e->launches++; }
   if (ev) cudaEventRecord(ev[0], s);
   if (e->cfg.step_kernel == 1) {   // thread-per-env reference mapping
     if (e->cfg.precision == 64) k_step<double><<<blocksFor(N, bs), bs, 0, s>>>(e->p, e->d, actions_dev, *io);
