@@ -198,11 +198,13 @@ template <typename T> BB_HD void normalizeQuats(T* qpos) { normalizeQuat4(qpos +
 // Fills s.M (packed), s.qfs (= passive - bias + actuator), geometry g, wheel capsule world frames, obs kinematics.
 // M (packed lower triangle, NTRI) and qfs (NV) are raw pointers so that the same code serves the thread-per-env scratch
 // and the warp-per-env shared-memory layout (ZERO_M=false: the caller has zeroed M and normalised the quaternions).
-// ML selects the layout of M: 0 = packed lower triangle (tidx), 1 = full symmetric 15 x 16 row-major (both triangles
-// written; the warp kernel zeroes the never-written entries once per launch).
+// ML selects the layout of M: 0 = packed lower triangle (tidx), 1 = the two diagonal blocks of the block-diagonal mass
+// matrix, both triangles written: base+wheels 9 x 9 at M[i * 9 + j], ball 6 x 6 at M[81 + (i - 9) * 6 + (j - 9)] (the
+// group kernel zeroes the never-written entries once per launch).
 template <int ML, typename T> BB_HD void setM(T* M, int i, int j, T v) {
   if (ML == 0) M[tidx(i, j)] = v;
-  else { M[i * 16 + j] = v; M[j * 16 + i] = v; }
+  else if (i < 9) { M[i * 9 + j] = v; M[j * 9 + i] = v; }
+  else { M[81 + (i - 9) * 6 + (j - 9)] = v; M[81 + (j - 9) * 6 + (i - 9)] = v; }
 }
 template <typename T, bool ZERO_M = true, int ML = 0>
 BB_HD void smoothDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const T* ctrl, T* M, T* qfs, Geo<T>& g,

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(32 * BB_WPB, BB_WARP_MINBLOCKS) k_step_warp(En
   }
   T warm = st[NQ + NV + L.gi];
   if (L.gl == NV) S.xv[NV] = 0;
-  for (int k = L.gl; k < NV * bbg::MS; k += bbg::G) S.M[k] = 0;   // structural zeros of the mass matrix (never written again)
+  for (int k = L.gl; k < bbg::MSZ; k += bbg::G) S.M[k] = 0;   // structural zeros of the mass matrix (never written again)
   bad = __any_sync(L.mask, bad);
   const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
   if (L.gl < 3) {  // ballbot_env.py:903-907
@@ -284,7 +284,7 @@ template <typename T> __global__ void k_probe_warp(EnvParams p, DevState d, int 
   for (int k = L.gl; k < NQ + NV; k += bbg::G) { if (k < NQ) S.xq[k] = st[k]; else S.xv[k - NQ] = st[k]; }
   const T warm = st[NQ + NV + L.gi];
   if (L.gl == NV) S.xv[NV] = 0;
-  for (int k = L.gl; k < NV * bbg::MS; k += bbg::G) S.M[k] = 0;
+  for (int k = L.gl; k < bbg::MSZ; k += bbg::G) S.M[k] = 0;
   if (L.gl < 3) S.ctrl[L.gl] = (T)ctrl3[L.gl];
   __syncwarp(L.mask);
   const float* hf = d.hfield + (p.hf_per_env ? (size_t)env * HF_CELLS : 0);

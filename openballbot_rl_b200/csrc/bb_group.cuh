@@ -33,24 +33,29 @@ using namespace bb;
 
 constexpr int G = BB_GROUP;                 // lanes per environment (16: two envs per warp, 32: one env per warp)
 constexpr int EPW = 32 / G;                 // environments per warp
-constexpr int MS = 16;                      // row stride of the full symmetric mass matrix
+constexpr int MSZ = 118;                    // mass matrix: 9 x 9 base/wheel block + 6 x 6 ball block (both triangles), padded
+constexpr int LS_ = 17;                     // row stride of the Cholesky factor (column j of L in row j; odd => conflict-free transposed reads)
 // contact records (in T).  Wheel pair: rows of 16 (dofs 0..14 + zero pad); terrain pair: rows of 8 = dofs 8..15 (only the
 // ball dofs 9..14 are non-zero).  Scalar block at OS: W(6) frc(3) D0 jar(3) jv(3) LS(8).
 constexpr int CRW = 74, CRH = 50;           // strides == 10 (mod 16): one-record-per-lane access is bank-conflict-free
 constexpr int OSW = 48, OSH = 24;
 constexpr int O_W = 0, O_FRC = 6, O_D0 = 9, O_JAR = 10, O_JV = 13, O_LS = 16;
-constexpr int NHS = 9;                      // terrain records resident in shared memory
+constexpr int NHS = 8;                      // terrain records resident in shared memory
 constexpr int GSCR = (MAXH - NHS) * CRH;    // per-env global overflow scratch (in T)
 // geometry block published by the smooth-dynamics pass
+constexpr int LSP_SLOTS = 8, LSP_W = 4, LSP_ALPHA = 0, LSP_COST = 1, LSP_D1 = 2, LSP_NXT = 3;   // line-search point slots
 constexpr int GE_PB = 0, GE_PL = 3, GE_RB = 6, GE_RL = 15, GE_AW = 24, GE_HW = 33, GE_CC = 42, GE_CU = 51, GE_N = 60;
 
 template <typename T> struct GS {
   T xq[20], xv[16], q0[20], ctrl[4];
-  T M[NV * MS];
+  T M[MSZ];
   T vb[2][16];          // vectors published by the dof lanes (broadcast reads)
-  T col[2][16];         // Cholesky column exchange (double buffered)
-  T geo[GE_N];
+  union {
+    T Lf[NV * LS_ + 1]; // Cholesky factor, Lf[j * 17 + i] = L(i, j) for i > j and 0 for i <= j (Newton solve)
+    T geo[GE_N];        // geometry block of the smooth-dynamics pass (consumed by gCollide before the first factorisation)
+  };
   T kin[16];            // quatB(4) cvel_ang(3) cvel_lin(3) posB(3) of the last evaluated stage
+  T lsp[LSP_SLOTS * LSP_W];   // line-search points (alpha, cost, d1, next Newton alpha), see lsEval
   T wrec[3 * CRW];
   T hrec[NHS * CRH];
   unsigned char cst[64];   // per contact: bits 0-1 zone (0 satisfied, 1 quadratic, 2 cone)
@@ -119,8 +124,15 @@ template <typename T>
 __device__ __noinline__ T gHessSolve(GS<T>& S, const T* gs, int ncon, int nw, T b, const Ln L) {
   const int gi = L.gi;
   T h[NV];
+  {
+    const bool top = gi < 9;
+    const T* ma = S.M + (top ? gi : 0);
+    const T* mb = S.M + 81 + (top ? 0 : gi - 9);
 #pragma unroll
-  for (int k = 0; k < NV; k++) h[k] = S.M[k * MS + gi];
+    for (int k = 0; k < 9; k++) { const T v = ma[k * 9]; h[k] = top ? v : (T)0; }
+#pragma unroll
+    for (int k = 9; k < NV; k++) { const T v = mb[(k - 9) * 6]; h[k] = top ? (T)0 : v; }
+  }
   // wheel pairs: dense 15-column rows
 #pragma unroll 1
   for (int c = 0; c < nw; c++) {
@@ -159,53 +171,56 @@ __device__ __noinline__ T gHessSolve(GS<T>& S, const T* gs, int ncon, int nw, T 
       if (k + 1 < NV) h[k + 1] += r0.y * t0 + r1.y * t1 + r2.y * t2;
     }
   }
-  // ---- right-looking Cholesky, column per lane, forward substitution fused
+  // ---- right-looking Cholesky, column per lane, forward substitution fused.  The loop over the pivots is rolled: after
+  // step j every lane shifts its column up by one (folded into the update FMA), so the pivot row is always h[0] and
+  // the code is one short body (the fully unrolled triangle was 2.7 k instructions and thrashed the instruction cache).
   T myinv = 0, y = b;
-#pragma unroll
+  T* Lf = S.Lf;
+#pragma unroll 1
   for (int j = 0; j < NV; j++) {
-    T piv = gget(h[j], j, L.mask);
+    T piv = gget(h[0], j, L.mask);
     piv = piv < (T)1e-15 ? (T)1e-15 : piv;
     const T inv = brsqrt(piv);
-    const T l = h[j] * inv;                       // lanes i >= j: L(i,j)  (lane j: sqrt(pivot))
-    if (gi >= j) h[j] = l;
+    const T l = h[0] * inv;                       // lanes i >= j: L(i,j)  (lane j: sqrt(pivot))
     if (gi == j) myinv = inv;
     const T yj = gget(y, j, L.mask) * inv;        // y_j = (b_j - sum_{k<j} L(j,k) y_k) / L(j,j)
     if (gi == j) y = yj;
     const T lz = gi > j ? l : (T)0;
     y -= lz * yj;
+    Lf[j * LS_ + L.gl] = lz;
+    __syncwarp(L.mask);
     if (j < NV - 1) {
-      T* col = S.col[j & 1];
-      if (G == 16 || L.gl < 16) col[L.gl] = l;
-      __syncwarp(L.mask);
-      // lanes i > j: A(k,i) -= L(i,j) L(k,j).  Lane j keeps the unscaled column (L(k,j) = h[k] * myinv).
+      // lanes i > j: A(r,i) -= L(i,j) L(r,j) for the rows r = j+1 .. 14, stored shifted: h[k] <- A(j+1+k, i)
+      const T* cj = Lf + j * LS_ + j + 1;
 #pragma unroll
-      for (int k = (j + 1) & ~1; k < 16; k += 2) {
-        const typename V2T<T>::t cc = ld2(col + k);
-        if (k > j && k < NV) h[k] -= lz * cc.x;
-        if (k + 1 < NV) h[k + 1] -= lz * cc.y;
-      }
+      for (int k = 0; k < NV - 1; k++) h[k] = h[k + 1] - lz * cj[k];
     }
   }
-  // ---- backward substitution L' x = y
+  // ---- backward substitution L' x = y (lane k reads its own row of Lf: L(i,k), i > k)
   T x = 0, s = 0;
-#pragma unroll
-  for (int k = NV - 1; k >= 0; k--) {
-    const T cand = (y - myinv * s) * myinv;       // valid on lane k
-    const T xk = gget(cand, k, L.mask);
-    if (gi == k) x = xk;
-    if (k > 0) s += h[k] * xk;                    // lanes j < k: h[k] = L(k,j) / myinv_j
+  const T* lrow = Lf + gi * LS_;
+#pragma unroll 1
+  for (int i = NV - 1; i >= 0; i--) {
+    const T cand = (y - s) * myinv;               // valid on lane i
+    const T xi = gget(cand, i, L.mask);
+    if (gi == i) x = xi;
+    s += lrow[i] * xi;                            // lanes k < i: L(i,k); zero for k >= i
   }
   return x;
 }
 
 // r[gi] = sum_k M(gi,k) v[k] for a published vector v (shared, 16 entries, v[15] finite)
 template <typename T> __device__ __forceinline__ T gSymv(const GS<T>& S, const T* v, int gi) {
+  const bool top = gi < 9;
+  const T* m = top ? S.M + gi : S.M + 81 + (gi - 9);
+  const T* vv = top ? v : v + 9;
+  const int st = top ? 9 : 6;
   T acc = 0;
 #pragma unroll
-  for (int k = 0; k < 16; k += 2) {
-    const typename V2T<T>::t p = ld2(v + k);
-    acc += S.M[k * MS + gi] * p.x;
-    if (k + 1 < NV) acc += S.M[(k + 1) * MS + gi] * p.y;
+  for (int k = 0; k < 6; k++) acc += m[k * st] * vv[k];
+  if (top) {
+#pragma unroll
+    for (int k = 6; k < 9; k++) acc += m[k * 9] * vv[k];
   }
   return acc;
 }
@@ -257,12 +272,21 @@ __device__ __forceinline__ T coneLane(const ModelConst<T>& mc, int k, T D0, cons
   return (T)0.5 * Dm * NT * NT;
 }
 
-template <typename T> struct LsPt { T alpha, cost, d1, d2; };
+// One evaluated point of the 1-D line-search objective: alpha, cost, first / second derivative and the alpha of the next
+// 1-D Newton step (alpha - d1 / d2, computed once here so that the search logic needs no further divisions).
+template <typename T> struct LsPt { T alpha, cost, d1, d2, nxt; };
 template <typename T> struct LsCtx { T qG0, qG1, qG2; };
+template <typename T> struct Sum3 { T a, b, c; };
+template <typename T> __device__ __noinline__ Sum3<T> gsum3(T a, T b, T c, unsigned mask) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) { a += __shfl_xor_sync(mask, a, o); b += __shfl_xor_sync(mask, b, o); c += __shfl_xor_sync(mask, c, o); }
+  Sum3<T> r; r.a = a; r.b = b; r.c = c; return r;
+}
 
-// cost and derivatives of the 1-D line-search objective at alpha (PrimalEval); uniform over the group
+// cost and derivatives of the 1-D line-search objective at alpha (PrimalEval); uniform over the group.  The point is
+// also parked in slot `slot` of S.lsp so that the search logic can refer to older points by index.
 template <typename T>
-__device__ __noinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, const T* gs, int ncon, int nw, const LsCtx<T> q, T alpha, const Ln L) {
+__device__ __noinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, const T* gs, int ncon, int nw, const LsCtx<T> q, T alpha, int slot, const Ln L) {
   T cost = 0, d1 = 0, d2 = 0;
 #pragma unroll 1
   for (int c = L.gl; c < ncon; c += G) {
@@ -289,10 +313,14 @@ __device__ __noinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, const 
     }
     if (bottom) { cost += l4q.y + alpha * (lq.x + alpha * lq.y); d1 += lq.x + (T)2 * alpha * lq.y; d2 += (T)2 * lq.y; }
   }
-  cost = gsum(cost, L.mask); d1 = gsum(d1, L.mask); d2 = gsum(d2, L.mask);
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) { cost += __shfl_xor_sync(L.mask, cost, o); d1 += __shfl_xor_sync(L.mask, d1, o); d2 += __shfl_xor_sync(L.mask, d2, o); }
   LsPt<T> p; p.alpha = alpha;
   p.cost = q.qG0 + alpha * (q.qG1 + alpha * q.qG2) + cost; p.d1 = q.qG1 + (T)2 * alpha * q.qG2 + d1; p.d2 = (T)2 * q.qG2 + d2;
   if (p.d2 < (T)1e-15) p.d2 = (T)1e-15;
+  p.nxt = alpha - p.d1 / p.d2;
+  if (L.gl < LSP_W) S.lsp[slot * LSP_W + L.gl] = L.gl == LSP_ALPHA ? alpha : (L.gl == LSP_COST ? p.cost : (L.gl == LSP_D1 ? p.d1 : p.nxt));
+  __syncwarp(L.mask);
   return p;
 }
 
@@ -302,7 +330,7 @@ template <typename T> struct GNewton {
   const bool fast;   // fast solver mode: inexact line search (stop when |phi'| <= 1e-3 |phi'(0)|), same minimiser of the outer problem
   T qfs, qas;        // dof-lane registers
   T qacc, Ma, grad, search, Mv;
-  T cost, gauss;
+  T cost, gauss, gnorm2;
   __device__ GNewton(const ModelConst<T>& m, GS<T>& s, T* g, const Ln l, int n, int w, bool f, T qf, T qa)
       : mc(m), S(s), gs(g), L(l), ncon(n), nw(w), fast(f), qfs(qf), qas(qa) {}
 
@@ -324,8 +352,6 @@ template <typename T> struct GNewton {
       }
     }
     const bool dof = L.gl < NV;
-    gauss = gsum(dof ? (T)0.5 * (Ma - qfs) * (qacc - qas) : (T)0, L.mask);
-    cost = gauss + gsum(cpart, L.mask);
     __syncwarp(L.mask);
     T g = Ma - qfs;
     const int gi = L.gi;
@@ -345,18 +371,23 @@ template <typename T> struct GNewton {
       }
     }
     grad = dof ? g : (T)0;
+    const Sum3<T> r3 = gsum3(dof ? (T)0.5 * (Ma - qfs) * (qacc - qas) : (T)0, cpart, grad * grad, L.mask);
+    gauss = r3.a; cost = r3.a + r3.b; gnorm2 = r3.c;
   }
 
-  // exact line search of mj_solNewton (PrimalSearch) as a state machine around a single evaluation site
+  // exact line search of mj_solNewton (PrimalSearch) as a state machine around a single evaluation site.  Evaluated
+  // points live in S.lsp (slots of 4 words); the brackets p1 / p2 and their pending Newton points are slot indices, so
+  // "p1 = candidate" is an integer move and the whole search needs a handful of registers.
   __device__ __forceinline__ T lineSearch(T scale) {
     const bool dof = L.gl < NV;
-    const T sn2 = gsum(dof ? search * search : (T)0, L.mask);
-    if (sn2 < (T)1e-30) return 0;
-    T snorm, isn; sqrtInv(sn2, snorm, isn);
-    T gtol = mc.tolerance * mc.ls_tolerance * snorm / scale;
     if (G == 16 || L.gl < 16) S.vb[0][L.gl] = dof ? search : (T)0;
     __syncwarp(L.mask);
     Mv = gSymv(S, S.vb[0], L.gi);
+    const Sum3<T> r3 = gsum3(dof ? search * search : (T)0, dof ? search * (Ma - qfs) : (T)0, dof ? (T)0.5 * search * Mv : (T)0, L.mask);
+    const T sn2 = r3.a;
+    if (sn2 < (T)1e-30) return 0;
+    T snorm, isn; sqrtInv(sn2, snorm, isn);
+    T gtol = mc.tolerance * mc.ls_tolerance * snorm / scale;
     // jv = J search and the per-contact coefficients of the search (PrimalPrepare)
 #pragma unroll 1
     for (int c = L.gl; c < ncon; c += G) {
@@ -378,80 +409,72 @@ template <typename T> struct GNewton {
       ls[7] = (T)0.5 * (D0 * w[0] * w[0] + D1 * w[1] * w[1] + D2 * w[2] * w[2]);
     }
     LsCtx<T> q;
-    q.qG0 = gauss;
-    q.qG1 = gsum(dof ? search * (Ma - qfs) : (T)0, L.mask);
-    q.qG2 = gsum(dof ? (T)0.5 * search * Mv : (T)0, L.mask);
+    q.qG0 = gauss; q.qG1 = r3.b; q.qG2 = r3.c;
     __syncwarp(L.mask);
     // states: 0 p0, 1 first Newton point, 2 one-sided Newton iteration, 3 p1next, 4 midpoint, 5 p1 re-bracket, 6 p2 re-bracket
-    LsPt<T> p1, p2, p1n, p2n, pmid;
+    const T* P = S.lsp;
+    int i1 = 0, i2 = 0, i1n = 0, i2n = 0, imid = 0, ic0 = 0;   // slots of p1, p2, p1next, p2next, pmid, candidate 0
     T p0cost = 0, dir = 1, result = 0, a = 0;
-    int st = 0, it = 0, b1 = 0;
-    bool upd = false;
+    int st = 0, it = 0, b1 = 0, dst = 0;
     const int maxit = mc.ls_iterations;
 #pragma unroll 1
     for (;;) {
-      const LsPt<T> p = lsEval(mc, S, gs, ncon, nw, q, a, L);
+      const LsPt<T> p = lsEval(mc, S, gs, ncon, nw, q, a, dst, L);
       bool done = false;
+      int src = -1;          // slot whose Newton step is evaluated next (-1: `a` has been set explicitly)
       if (st == 0) {
-        p0cost = p.cost; p1 = p; p2 = p; pmid = p; p1n = p; p2n = p;
+        p0cost = p.cost;
         if (fast) gtol = bmax(gtol, (T)1e-3 * babs(p.d1));
-        a = p.alpha - p.d1 / p.d2; st = 1;
-      } else if (st == 1) {
-        if (!(p0cost < p.cost)) p1 = p;        // p1 = better of p0, first Newton point
-        if (babs(p1.d1) < gtol) { result = p1.alpha; done = true; }
-        else {
-          dir = p1.d1 < 0 ? (T)1 : (T)-1;
-          if (p1.d1 * dir <= -gtol && it < maxit) { p2 = p1; upd = true; a = p1.alpha - p1.d1 / p1.d2; st = 2; }
-          else { result = p1.alpha; done = true; }   // !upd
-        }
-      } else if (st == 2) {
-        p1 = p; it++;
-        if (babs(p1.d1) < gtol) { result = p1.alpha; done = true; }
-        else if (p1.d1 * dir <= -gtol && it < maxit) { p2 = p1; a = p1.alpha - p1.d1 / p1.d2; }
-        else if (it >= maxit) { result = p1.alpha; done = true; }
-        else { p2n = p1; a = p1.alpha - p1.d1 / p1.d2; st = 3; }
+        a = p.nxt; st = 1;
+      } else if (st <= 2) {
+        T d = p.d1;
+        if (st == 1) {       // p1 = better of p0, first Newton point
+          i1 = p0cost < p.cost ? 0 : dst;
+          d = P[i1 * LSP_W + LSP_D1];
+          dir = d < 0 ? (T)1 : (T)-1;
+        } else { i1 = dst; it++; }
+        if (babs(d) < gtol || it >= maxit) { result = P[i1 * LSP_W + LSP_ALPHA]; done = true; }
+        else if (d * dir <= -gtol) { i2 = i1; src = i1; st = 2; }          // keep iterating on the same side
+        else if (st == 1) { result = P[i1 * LSP_W + LSP_ALPHA]; done = true; }   // (non-finite derivative)
+        else { i2n = i1; src = i1; st = 3; }                              // crossed the minimum: p2 .. p1 is a bracket
       } else if (st == 3) {
-        p1n = p;
-        a = (T)0.5 * (p1.alpha + p2.alpha); st = 4;
+        i1n = dst; st = 4;
+        a = (T)0.5 * (P[i1 * LSP_W + LSP_ALPHA] + P[i2 * LSP_W + LSP_ALPHA]);
       } else {
-        if (st == 4) { pmid = p; it++; b1 = -1; }
-        else if (st == 5) p1n = p;
-        else p2n = p;
-        // continue the body of the bracketing loop from where the pending evaluation was requested
+        // candidates of this trip = {p1next, p2next, pmid} as they were when the midpoint was evaluated (the reference
+        // copies them before the first bracket update, so the second update still sees the old p1next: slot ic0)
+        if (st == 4) { imid = dst; it++; b1 = -1; ic0 = i1n; }
+        else if (st == 5) i1n = dst;
+        else i2n = dst;
+        const T dc0 = P[ic0 * LSP_W + LSP_D1], dc1 = P[i2n * LSP_W + LSP_D1], dc2 = P[imid * LSP_W + LSP_D1];
         if (st == 4) {
-          if (babs(p1n.d1) < gtol) { result = p1n.alpha; done = true; }
-          else if (babs(p2n.d1) < gtol) { result = p2n.alpha; done = true; }
-          else if (babs(pmid.d1) < gtol) { result = pmid.alpha; done = true; }
+          if (babs(dc0) < gtol) { result = P[ic0 * LSP_W + LSP_ALPHA]; done = true; }
+          else if (babs(dc1) < gtol) { result = P[i2n * LSP_W + LSP_ALPHA]; done = true; }
+          else if (babs(dc2) < gtol) { result = p.alpha; done = true; }
         }
         if (!done) {
           bool need = false;
-          if (st == 4) {   // bracket(p1, cand, p1n)
-            int flag = 0;
-            const LsPt<T> cand[3] = {p1n, p2n, pmid};
+#pragma unroll 1
+          for (int side = st == 4 ? 0 : 1; side < 2 && !need && st != 6; side++) {   // bracket(p1, ..), then bracket(p2, ..)
+            int ip = side ? i2 : i1, flag = 0;
+            T dp = P[ip * LSP_W + LSP_D1];
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-              if (p1.d1 < 0 && cand[i].d1 < 0 && p1.d1 < cand[i].d1) { p1 = cand[i]; flag = 1; }
-              else if (p1.d1 > 0 && cand[i].d1 > 0 && p1.d1 > cand[i].d1) { p1 = cand[i]; flag = 2; }
+              const T dc = i == 0 ? dc0 : (i == 1 ? dc1 : dc2);
+              const int ic = i == 0 ? ic0 : (i == 1 ? i2n : imid);
+              if (dp < 0 && dc < 0 && dp < dc) { ip = ic; dp = dc; flag = 1; }
+              else if (dp > 0 && dc > 0 && dp > dc) { ip = ic; dp = dc; flag = 2; }
             }
-            b1 = flag;
-            if (flag) { a = p1.alpha - p1.d1 / p1.d2; st = 5; need = true; }
-          }
-          if (!need && st != 6) {   // bracket(p2, cand, p2n); cand uses the (possibly refreshed) p1n
-            int flag = 0;
-            const LsPt<T> cand[3] = {p1n, p2n, pmid};
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-              if (p2.d1 < 0 && cand[i].d1 < 0 && p2.d1 < cand[i].d1) { p2 = cand[i]; flag = 1; }
-              else if (p2.d1 > 0 && cand[i].d1 > 0 && p2.d1 > cand[i].d1) { p2 = cand[i]; flag = 2; }
-            }
-            if (flag) { a = p2.alpha - p2.d1 / p2.d2; st = 6; need = true; }
-            else if (!b1) { result = pmid.cost < p0cost ? pmid.alpha : (T)0; done = true; }
+            if (side == 0) { i1 = ip; b1 = flag; } else i2 = ip;
+            if (flag) { src = ip; st = 5 + side; need = true; }
+            else if (side == 1 && !b1) { result = P[imid * LSP_W + LSP_COST] < p0cost ? P[imid * LSP_W + LSP_ALPHA] : (T)0; done = true; }
           }
           if (!need && !done) {   // next trip of the bracketing loop
-            if (it < maxit) { a = (T)0.5 * (p1.alpha + p2.alpha); st = 4; }
+            if (it < maxit) { a = (T)0.5 * (P[i1 * LSP_W + LSP_ALPHA] + P[i2 * LSP_W + LSP_ALPHA]); st = 4; }
             else {
-              if (p1.cost <= p2.cost && p1.cost < p0cost) result = p1.alpha;
-              else if (p2.cost <= p1.cost && p2.cost < p0cost) result = p2.alpha;
+              const T c1 = P[i1 * LSP_W + LSP_COST], c2 = P[i2 * LSP_W + LSP_COST];
+              if (c1 <= c2 && c1 < p0cost) result = P[i1 * LSP_W + LSP_ALPHA];
+              else if (c2 <= c1 && c2 < p0cost) result = P[i2 * LSP_W + LSP_ALPHA];
               else result = 0;
               done = true;
             }
@@ -459,6 +482,10 @@ template <typename T> struct GNewton {
         }
       }
       if (done) break;
+      if (src >= 0) a = P[src * LSP_W + LSP_NXT];
+      // next evaluation goes to a slot that none of the live points occupies (slot 0 = p0 stays)
+      const unsigned live = 1u | (1u << i1) | (1u << i2) | (1u << i1n) | (1u << i2n) | (1u << imid) | (1u << ic0);
+      dst = __ffs(~live) - 1;
     }
     return result;
   }
@@ -486,8 +513,8 @@ template <typename T> struct GNewton {
       sc[O_JAR] = jw[0]; sc[O_JAR + 1] = jw[1]; sc[O_JAR + 2] = jw[2];
       sc[O_LS] = js[0]; sc[O_LS + 1] = js[1]; sc[O_LS + 2] = js[2];
     }
-    cw = gsum(cw, L.mask); cs = gsum(cs, L.mask);
-    const bool useSmooth = cw > cs;
+    const Sum3<T> r3 = gsum3(cw, cs, (T)0, L.mask);
+    const bool useSmooth = r3.a > r3.b;
     if (useSmooth) {
       qacc = qas; Ma = qfs;
 #pragma unroll 1
@@ -514,8 +541,7 @@ template <typename T> struct GNewton {
       const T old = cost;
       costGrad();
       iter++;
-      const T gn = gsum(grad * grad, L.mask);
-      if (scale * (old - cost) < mc.tolerance || scale * bsqrt(gn) < mc.tolerance) break;
+      if (scale * (old - cost) < mc.tolerance || scale * bsqrt(gnorm2) < mc.tolerance) break;
     }
     niter = iter;
     return qacc;
@@ -683,10 +709,10 @@ __device__ __noinline__ T gForward(const ModelConst<T>& mc, GS<T>& S, const floa
   __syncwarp(L.mask);
   const T qfs = L.gl < NV ? S.vb[0][L.gi] : (T)0;
   __syncwarp(L.mask);
+  int nw;
+  const int ncon = gCollide(mc, S, hf, zscale, gs, L, nw);   // consumes S.geo, which shares storage with the Cholesky factor
   const T qas = gHessSolve(S, gs, 0, 0, qfs, L);   // qacc_smooth = M^-1 qfrc_smooth
   if (qasOut) { *qasOut = qas; *qfsOut = qfs; }
-  int nw;
-  const int ncon = gCollide(mc, S, hf, zscale, gs, L, nw);
   nconOut = ncon; niterOut = 0;
   if (ncon == 0) return qas;
   GNewton<T> nwt(mc, S, gs, L, ncon, nw, fast, qfs, qas);

@@ -1,6 +1,6 @@
 """Attribute the executed warp instructions of one kernel in an .ncu-rep to device functions and source lines.
 
-usage: python scripts/ncu_lines.py REPORT.ncu-rep LIB.so KERNEL_SUBSTRING [--lines N] [--id K]
+usage: python scripts/ncu_lines.py REPORT.ncu-rep LIB.so KERNEL_SUBSTRING [--lines N] [--id K | --name DEMANGLED_SUBSTRING]
 
 Joins the SASS page of the report (instruction address, executed count, stall samples) with `nvdisasm --print-line-info`
 of the cubin inside LIB.so (function labels of the __noinline__ device functions, `//## File ..., line N` markers).
@@ -48,31 +48,33 @@ def sass_page(rep, kid):
             cur = {"name": l, "rows": []}; blocks.append(cur)
         elif cur is not None:
             cur["rows"].append(l)
-    b = blocks[kid]
+    b = [x for x in blocks if kid in x["name"]][0] if isinstance(kid, str) else blocks[kid]
     rows = list(csv.reader(b["rows"]))
     hdr = rows[0]
     ia, ie, isamp, ithr = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
-    out = [(int(r[ia], 16), int(r[ie]), int(r[isamp]), int(r[ithr])) for r in rows[1:] if len(r) > ie and r[ia].startswith("0x")]
+    ini = hdr.index("stall_no_inst")
+    out = [(int(r[ia], 16), int(r[ie]), int(r[isamp]), int(r[ithr]), int(r[ini] or 0)) for r in rows[1:] if len(r) > ie and r[ia].startswith("0x")]
     base = out[0][0]
-    return b["name"], [(a - base, e, s, t) for a, e, s, t in out]
+    return b["name"], [(a - base, e, s, t, n) for a, e, s, t, n in out]
 
 
 if __name__ == "__main__":
     rep, lib, ksub = sys.argv[1:4]
     nlines = int(sys.argv[sys.argv.index("--lines") + 1]) if "--lines" in sys.argv else 40
-    kid = int(sys.argv[sys.argv.index("--id") + 1]) if "--id" in sys.argv else 0
+    kid = sys.argv[sys.argv.index("--name") + 1] if "--name" in sys.argv else (int(sys.argv[sys.argv.index("--id") + 1]) if "--id" in sys.argv else 0)
     info = disasm(lib, ksub)
     name, rows = sass_page(rep, kid)
-    tot = sum(e for _, e, _, _ in rows); tots = sum(s for _, _, s, _ in rows)
+    tot = sum(r[1] for r in rows); tots = sum(r[2] for r in rows); totn = sum(r[4] for r in rows)
+    noi = collections.Counter()
     byfn = collections.Counter(); sfn = collections.Counter(); byline = collections.Counter(); sline = collections.Counter(); thr = collections.Counter()
     nins = collections.Counter()
-    for off, e, s, t in rows:
+    for off, e, s, t, n in rows:
         fn, line, _ = info.get(off, ("?", ("?", 0), ""))
-        byfn[fn] += e; sfn[fn] += s; byline[(fn,) + line] += e; sline[(fn,) + line] += s; thr[fn] += t; nins[fn] += 1
+        byfn[fn] += e; sfn[fn] += s; byline[(fn,) + line] += e; sline[(fn,) + line] += s; thr[fn] += t; nins[fn] += 1; noi[fn] += n
     print(f"{name[:120]}\nexecuted warp instructions {tot:.4g}, stall samples {tots}, static SASS instructions {len(rows)}")
-    print(f"{'function':28s} {'static':>7s} {'executed':>12s} {'share':>7s} {'samples':>8s} {'lanes/inst':>10s}")
+    print(f"{'function':28s} {'static':>7s} {'executed':>12s} {'share':>7s} {'samples':>8s} {'lanes/inst':>10s} {'no_inst':>8s}")
     for fn, e in byfn.most_common():
-        print(f"{fn[:28]:28s} {nins[fn]:7d} {e:12.4g} {100 * e / tot:6.1f}% {100 * sfn[fn] / max(tots, 1):7.1f}% {thr[fn] / max(e, 1):10.1f}")
+        print(f"{fn[:28]:28s} {nins[fn]:7d} {e:12.4g} {100 * e / tot:6.1f}% {100 * sfn[fn] / max(tots, 1):7.1f}% {thr[fn] / max(e, 1):10.1f} {100 * noi[fn] / max(totn, 1):7.1f}%")
     print(f"\ntop {nlines} source lines (function, file:line, executed share, sample share)")
     for k, e in byline.most_common(nlines):
         print(f"  {k[0][:22]:22s} {k[1]}:{k[2]:<5d} {100 * e / tot:6.2f}% {100 * sline[k] / max(tots, 1):6.2f}%")
