@@ -493,16 +493,11 @@ __device__ float hitPrim(F3 o, F3 dir, const Prim& p) {
   }
   return best;
 }
-__device__ __forceinline__ float hitTri(F3 o, F3 dir, F3 a, F3 b, F3 c) {
-  const F3 e1 = b - a, e2 = c - a, pv = fcross(dir, e2); const float det = fdot(e1, pv);
-  if (fabsf(det) < 1e-18f) return -1.f;
-  const float inv = 1.f / det; const F3 tv = o - a; const float u = fdot(tv, pv) * inv; if (u < 0.f || u > 1.f) return -1.f;
-  const F3 q = fcross(tv, e1); const float v = fdot(dir, q) * inv; if (v < 0.f || u + v > 1.f) return -1.f;
-  const float t = fdot(e2, q) * inv; return t > 0.f ? t : -1.f;
-}
-// ray vs heightfield: 2-D DDA over the cells, both triangles of each visited cell
+// ray vs heightfield: 2-D DDA over the cells in grid coordinates (cell units, raw height units), both triangles of each
+// visited cell.  The two triangles of a cell are graphs over the cell (split along the (0,0)-(1,1) diagonal, the same
+// diagonal as the collision prisms), so each test is one ray/plane solve plus a range check in cell coordinates.
 __device__ float hitHfield(F3 o, F3 dir, const float* __restrict__ hf, float sx, float sz, float tmax) {
-  const int n = HN; const float dx = 2.f * sx / (n - 1);
+  const int n = HN; const float dx = 2.f * sx / (n - 1), idx = 1.f / dx, isz = 1.f / sz;
   float t0 = 0.f, t1 = tmax;
   {
     const float oo[2] = {o.x, o.y}, dv[2] = {dir.x, dir.y};
@@ -512,24 +507,43 @@ __device__ float hitHfield(F3 o, F3 dir, const float* __restrict__ hf, float sx,
     }
   }
   if (t0 >= t1) return -1.f;
-  const float px = o.x + (t0 + 1e-6f) * dir.x, py = o.y + (t0 + 1e-6f) * dir.y;
-  int cx = (int)floorf((px + sx) / dx), cy = (int)floorf((py + sx) / dx);
+  const float gx0 = (o.x + sx) * idx, gy0 = (o.y + sx) * idx, dgx = dir.x * idx, dgy = dir.y * idx;   // grid coordinates of the ray
+  const float oz = o.z * isz, dz = dir.z * isz;                                                       // raw height units
+  int cx = (int)floorf(gx0 + (t0 + 1e-6f) * dgx), cy = (int)floorf(gy0 + (t0 + 1e-6f) * dgy);
   cx = min(max(cx, 0), n - 2); cy = min(max(cy, 0), n - 2);
+  const bool zx = fabsf(dir.x) < 1e-18f, zy = fabsf(dir.y) < 1e-18f;
   const int stx = dir.x > 0.f ? 1 : -1, sty = dir.y > 0.f ? 1 : -1;
-  const float tdx = fabsf(dir.x) < 1e-18f ? 3e38f : dx / fabsf(dir.x), tdy = fabsf(dir.y) < 1e-18f ? 3e38f : dx / fabsf(dir.y);
-  float tmx = fabsf(dir.x) < 1e-18f ? 3e38f : (-sx + (cx + (stx > 0 ? 1 : 0)) * dx - o.x) / dir.x;
-  float tmy = fabsf(dir.y) < 1e-18f ? 3e38f : (-sx + (cy + (sty > 0 ? 1 : 0)) * dx - o.y) / dir.y;
+  const float ix = zx ? 0.f : 1.f / dgx, iy = zy ? 0.f : 1.f / dgy;
+  const float tdx = zx ? 3e38f : fabsf(ix), tdy = zy ? 3e38f : fabsf(iy);
+  float tmx = zx ? 3e38f : ((float)(cx + (stx > 0 ? 1 : 0)) - gx0) * ix;
+  float tmy = zy ? 3e38f : ((float)(cy + (sty > 0 ? 1 : 0)) - gy0) * iy;
   float tcur = t0;
+  const float e = 1e-5f;
   for (int it = 0; it < 4 * n; it++) {
     if (cx < 0 || cx > n - 2 || cy < 0 || cy > n - 2 || tcur > t1) return -1.f;
-    const float h00 = hf[cy * n + cx] * sz, h10 = hf[cy * n + cx + 1] * sz, h01 = hf[(cy + 1) * n + cx] * sz, h11 = hf[(cy + 1) * n + cx + 1] * sz;
+    const float* h = hf + cy * n + cx;
+    const float h00 = h[0], h10 = h[1], h01 = h[n], h11 = h[n + 1];
     const float texit = fminf(fminf(tmx, tmy), t1);
-    const float zlow = fminf(o.z + tcur * dir.z, o.z + texit * dir.z);       // lowest point of the ray inside this cell
+    const float zlow = fminf(oz + tcur * dz, oz + texit * dz);               // lowest point of the ray inside this cell
     if (zlow <= fmaxf(fmaxf(h00, h10), fmaxf(h01, h11))) {                    // otherwise the ray passes above both triangles
-      const float x0 = -sx + cx * dx, y0 = -sx + cy * dx;
-      const F3 v00 = f3(x0, y0, h00), v10 = f3(x0 + dx, y0, h10), v01 = f3(x0, y0 + dx, h01), v11 = f3(x0 + dx, y0 + dx, h11);
-      const float ta = hitTri(o, dir, v01, v00, v11), tb = hitTri(o, dir, v00, v11, v10);
-      float best = -1.f; if (ta > 0.f) best = ta; if (tb > 0.f && (best < 0.f || tb < best)) best = tb;
+      const float u0 = gx0 - (float)cx, v0 = gy0 - (float)cy, c0 = h00 - oz;
+      float best = -1.f;
+      {  // triangle (0,0) (1,1) (1,0): u >= v, z = h00 + (h10 - h00) u + (h11 - h10) v
+        const float a = h10 - h00, b = h11 - h10;
+        const float den = dz - a * dgx - b * dgy, num = c0 + a * u0 + b * v0;
+        if (fabsf(den) > 1e-18f) {
+          const float t = num / den, u = u0 + t * dgx, v = v0 + t * dgy;
+          if (t > 0.f && v >= -e && u <= 1.f + e && u >= v - e) best = t;
+        }
+      }
+      {  // triangle (0,1) (0,0) (1,1): v >= u, z = h00 + (h11 - h01) u + (h01 - h00) v
+        const float a = h11 - h01, b = h01 - h00;
+        const float den = dz - a * dgx - b * dgy, num = c0 + a * u0 + b * v0;
+        if (fabsf(den) > 1e-18f) {
+          const float t = num / den, u = u0 + t * dgx, v = v0 + t * dgy;
+          if (t > 0.f && u >= -e && v <= 1.f + e && v >= u - e && (best < 0.f || t < best)) best = t;
+        }
+      }
       if (best > 0.f && best <= tmax) return best;
     }
     if (tmx < tmy) { cx += stx; tcur = tmx; tmx += tdx; } else { cy += sty; tcur = tmy; tmy += tdy; }
@@ -582,8 +596,13 @@ __global__ void __launch_bounds__(256) k_depth(EnvParams p, DevState d, const in
     const float* hf = d.hfield + (p.hf_per_env ? (size_t)env * HF_CELLS : 0);
     float* out = (cam ? img1 : img0) + (size_t)env * npix;
     const F3 o = sc.cam_o[cam];
-    for (int px = threadIdx.x; px < npix; px += blockDim.x) {
-      const int r = px / p.im_w, c = px - r * p.im_w;
+    // each warp renders tiles of 8 x 4 pixels (neighbouring rays traverse similar cells => less divergence than row segments)
+    const int tiles_x = (p.im_w + 7) >> 3, tiles = tiles_x * ((p.im_h + 3) >> 2);
+    const int lx = threadIdx.x & 7, ly = (threadIdx.x >> 3) & 3;
+    for (int tile = threadIdx.x >> 5; tile < tiles; tile += blockDim.x >> 5) {
+      const int r = (tile / tiles_x) * 4 + ly, c = (tile % tiles_x) * 8 + lx;
+      if (r >= p.im_h || c >= p.im_w) continue;
+      const int px = r * p.im_w + c;
       const float xn = (2.f * (c + 0.5f) / p.im_w - 1.f) * ((float)p.im_w / p.im_h), yn = 1.f - 2.f * (r + 0.5f) / p.im_h;  // fovy 90
       const F3 dir = sc.cam_x[cam] * xn + sc.cam_y[cam] * yn - sc.cam_z[cam];
       const float inv_dd = 1.f / fdot(dir, dir);
