@@ -158,6 +158,14 @@ int bb_reset_host(bb_engine* e, const uint8_t* mask_host, const bb_host_io* out)
 int bb_profile_begin(bb_engine* e, int32_t max_steps);
 int bb_profile_end(bb_engine* e, double* ms4, int32_t* nsteps);
 
+/* Generalised advantage estimation on device-resident rollout tensors (engine-independent).  Replaces
+ * RolloutBuffer.compute_returns_and_advantage of the reference's learner (SB3 PPO.collect_rollouts, driven from
+ * ballbot_rl/training/train.py:126-141,284): rewards float[T,N], values float[T+1,N] (row T = value of the observation
+ * after the last step), dones uint8[T,N] (done[t] = episode ended by the transition of step t, i.e. SB3's
+ * episode_starts[t+1]); outputs advantages / returns float[T,N] with returns = advantages + values[:T]. */
+int bb_gae(const float* rewards_dev, const float* values_dev, const uint8_t* dones_dev, int32_t T, int32_t N, float gamma,
+           float gae_lambda, float* advantages_dev, float* returns_dev, void* cuda_stream);
+
 /* number of kernel launches issued by this engine so far (bench.py's gpu_launches claim) */
 int64_t bb_launch_count(const bb_engine* e);
 /* engine model constants for tests: dA[4], meaninertia, masses (m0, mw, mL) */

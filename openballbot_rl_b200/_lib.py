@@ -10,7 +10,8 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libballbot_b200.so")
-_SOURCES = ["bb_engine.cu", "bb_core.cuh", "bb_group.cuh", "bb_model.h"]
+_SOURCES = ["bb_engine.cu", "bb_rollout.cu", "bb_core.cuh", "bb_group.cuh", "bb_model.h"]
+_UNITS = ["bb_engine.cu", "bb_rollout.cu"]   # translation units of the library
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 
@@ -54,7 +55,7 @@ class HostIO(C.Structure):
 EXPORTED = ["bb_create", "bb_destroy", "bb_default_config", "bb_last_error", "bb_num_envs", "bb_reset", "bb_step",
             "bb_add_reward", "bb_set_state", "bb_get_state", "bb_set_hfield", "bb_get_hfield", "bb_get_terrain_seeds",
             "bb_perlin_terrain", "bb_render_depth", "bb_step_host", "bb_reset_host", "bb_launch_count",
-            "bb_model_constants", "bb_probe_forward", "bb_profile_begin", "bb_profile_end", "bb_perlin_grid"]
+            "bb_model_constants", "bb_probe_forward", "bb_profile_begin", "bb_profile_end", "bb_perlin_grid", "bb_gae"]
 
 
 def needs_build():
@@ -69,7 +70,7 @@ def build(force=False, verbose=False):
     """Compile csrc/bb_engine.cu for sm_100a into libballbot_b200.so (nvcc cross-compiles without a GPU)."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(_CSRC, "bb_engine.cu")]
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + [os.path.join(_CSRC, u) for u in _UNITS]
     subprocess.check_call(cmd)
     return LIB_PATH
 
@@ -109,6 +110,7 @@ def lib():
     L.bb_launch_count.argtypes = [vp]
     L.bb_launch_count.restype = C.c_int64
     L.bb_perlin_grid.argtypes = [C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float, vp, C.c_int32, vp]
+    L.bb_gae.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_float, C.c_float, vp, vp, vp]
     L.bb_profile_begin.argtypes = [vp, C.c_int32]
     L.bb_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     L.bb_probe_forward.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp]

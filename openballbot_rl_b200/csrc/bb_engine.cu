@@ -29,7 +29,6 @@ namespace {
 #ifndef BB_WARP_MINBLOCKS
 #define BB_WARP_MINBLOCKS (12 / BB_WPB)
 #endif
-constexpr int NST = NQ + NV + NV;  // qpos, qvel, qacc_warmstart
 constexpr int SST = 48;            // per-env stride of the state array  T[N][SST] (one coalesced 384/192-byte record per env)
 constexpr int CST = 20;            // per-env stride of the camera configuration array T[N][CST]
 constexpr int HF_CELLS = HN * HN;
@@ -456,7 +455,6 @@ __device__ __forceinline__ F3 operator+(F3 a, F3 b) { return f3(a.x + b.x, a.y +
 __device__ __forceinline__ F3 operator-(F3 a, F3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ F3 operator*(F3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ float fdot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ F3 fcross(F3 a, F3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 struct Prim { F3 c, u; float r, hl; int type; };  // type 0 sphere, 1 capsule, 2 cylinder
 struct Scene { F3 cam_o[2]; F3 cam_x[2], cam_y[2], cam_z[2]; Prim prim[7]; float brad2[7]; };
 

@@ -29,7 +29,7 @@ class BallbotPolicy(nn.Module):
         super().__init__()
         self.cameras = cameras
         self.encoders = nn.ModuleDict({k: make_depth_encoder(im_h, im_w) for k in ("rgbd_0", "rgbd_1")}) if cameras else nn.ModuleDict()
-        feat = 3 * 5 + 1 + (40 if cameras else 0)
+        feat = 3 * 5 + ((1 + 40) if cameras else 0)   # no image timestamp without cameras (ballbot_env.py:803-811)
 
         def mlp(out):
             layers, d = [], feat
@@ -47,7 +47,7 @@ class BallbotPolicy(nn.Module):
             if k.startswith("rgbd_"):
                 if self.cameras:
                     parts.append(self.encoders[k](obs[k]))
-            else:
+            elif k in obs:
                 parts.append(obs[k].flatten(1))
         return torch.cat(parts, dim=1)
 
