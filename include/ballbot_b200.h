@@ -60,7 +60,7 @@ typedef struct bb_config {
   float distance_scale;
   uint64_t seed;             /* base seed of the counter-based per-env terrain-seed generator */
   int32_t auto_reset;        /* 1: VecEnv semantics (done envs are reset inside bb_step) */
-  int32_t step_kernel;       /* 0: warp-per-env kernel (default); 1: thread-per-env reference mapping (cross-check) */
+  int32_t step_kernel;       /* 0: lane-group kernels, split-phase (default); 1: thread-per-env reference mapping (cross-check); 2: lane-group kernel, fused RK4 step (cross-check) */
   int32_t solver_mode;       /* 0: MuJoCo-faithful iteration path (every RK4 stage warm-starts from qacc_warmstart);
                                 1: fast -- stages 2..4 warm-start from the previous stage (same minimiser within tolerance) */
 } bb_config;

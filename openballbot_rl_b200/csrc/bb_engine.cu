@@ -26,8 +26,14 @@ namespace {
 #ifndef BB_WPB
 #define BB_WPB 1          // warps per CTA of the step kernel (2 envs per warp); 1 avoids waiting for the slowest warp of a CTA
 #endif
+#ifndef BB_STAGE_SYNC
+#define BB_STAGE_SYNC 0
+#endif
 #ifndef BB_WARP_MINBLOCKS
-#define BB_WARP_MINBLOCKS (12 / BB_WPB)
+#define BB_WARP_MINBLOCKS (12 / BB_WPB)    // fp64: 12 warps per SM (shared memory: 18.3 KB per warp; 168 registers)
+#endif
+#ifndef BB_WARP_MINBLOCKS32
+#define BB_WARP_MINBLOCKS32 (12 / BB_WPB)  // fp32 instantiation
 #endif
 constexpr int SST = 48;            // per-env stride of the state array  T[N][SST] (one coalesced 384/192-byte record per env)
 constexpr int CST = 20;            // per-env stride of the camera configuration array T[N][CST]
@@ -52,6 +58,9 @@ struct DevState {
   void* st;        // T[N][SST]
   void* camq;      // T[N][CST]  configuration the cameras see (last RK stage / reset state)
   void* gscr;      // T[N][bbg::GSCR] overflow scratch of the group kernel (contact records beyond shared memory)
+  void* rk;        // T[N][bbg::RKN]  split-phase step: RK4 bookkeeping between the stage kernels
+  void* ctx;       // T[N][bbg::CTXN] split-phase step: solver input (M, qfrc_smooth, qacc_smooth, contact records)
+  int* meta;       // int[N][4]       split-phase step: ncon, nw, Newton iterations, flags
   int* step_count; int* cam_steps; unsigned* episode; int* tseed;
   float* hfield;   // [N][HF_CELLS] (hf_per_env) or [HF_CELLS]
   float* ep_ret; int* ep_len;
@@ -167,55 +176,52 @@ __global__ void __launch_bounds__(64) k_step(EnvParams p, DevState d, const floa
 
 // --------------------------------------------------------------------------------------------- step, lane group per env
 // One 16-lane group per env (two envs per warp, bb_group.cuh); solver state in dynamic shared memory (bbg::GS<T> per env).
+// stepLoad / stepFinish are shared by the fused kernel (k_step_warp) and the split-phase kernels (k_stage / k_newton).
+
+// state record -> S.xq / S.xv / warm, action -> S.ctrl (ballbot_env.py:903-907), structural zeros of M.  Returns "state is not finite".
 template <typename T>
-__global__ void __launch_bounds__(32 * BB_WPB, BB_WARP_MINBLOCKS) k_step_warp(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const bbg::Ln L = bbg::makeLn();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / bbg::G;
-  const int slot = (blockIdx.x * (blockDim.x >> 5) + warp) * bbg::EPW + grp;
-  if (slot >= p.N) return;
-  const int i = d.order[slot];
-  bbg::GS<T>& S = reinterpret_cast<bbg::GS<T>*>(smem_raw)[warp * bbg::EPW + grp];
-  T* st = (T*)d.st + (size_t)i * SST;
-  // one coalesced record per env: qpos[17] qvel[15] warm[15]
+__device__ __forceinline__ bool stepLoad(const EnvParams& p, const DevState& d, const float* __restrict__ actions, int i, bbg::GS<T>& S,
+                                         const bbg::Ln& L, T& warm) {
+  const T* st = (const T*)d.st + (size_t)i * SST;
   bool bad = false;
-  for (int k = L.gl; k < NQ + NV; k += bbg::G) {
+  for (int k = L.gl; k < NQ + NV; k += bbg::G) {   // one coalesced record per env: qpos[17] qvel[15] warm[15]
     const T v = st[k];
     bad |= !(babs(v) < (T)1e10);
     if (k < NQ) S.xq[k] = v; else S.xv[k - NQ] = v;
   }
-  T warm = st[NQ + NV + L.gi];
+  warm = st[NQ + NV + L.gi];
   if (L.gl == NV) S.xv[NV] = 0;
   for (int k = L.gl; k < bbg::MSZ; k += bbg::G) S.M[k] = 0;   // structural zeros of the mass matrix (never written again)
   bad = __any_sync(L.mask, bad);
-  const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
-  if (L.gl < 3) {  // ballbot_env.py:903-907
-    const float av = L.gl == 0 ? a0 : (L.gl == 1 ? a1 : a2);
-    T u = (T)av * (T)p.max_wheel_vel; u = u > (T)p.max_wheel_vel ? (T)p.max_wheel_vel : (u < -(T)p.max_wheel_vel ? -(T)p.max_wheel_vel : u);
+  if (L.gl < 3) {
+    T u = (T)actions[3 * i + L.gl] * (T)p.max_wheel_vel; u = u > (T)p.max_wheel_vel ? (T)p.max_wheel_vel : (u < -(T)p.max_wheel_vel ? -(T)p.max_wheel_vel : u);
     S.ctrl[L.gl] = -u;
   }
   __syncwarp(L.mask);
+  return bad;
+}
+__device__ __forceinline__ bool cameraRefresh(const EnvParams& p, const DevState& d, int i, int& cs) {
+  cs = d.cam_steps[i] + 1;
+  if (p.cameras && cs >= p.cam_period) { cs = 0; return true; }
+  return false;
+}
+// in: S.xq / S.xv = new state, S.kin = last-stage kinematics, warm.  Writes the state record, observation, reward,
+// termination, Monitor accumulators, work key and the reset / refresh work lists.
+template <typename T>
+__device__ __forceinline__ void stepFinish(const EnvParams& p, const DevState& d, const float* __restrict__ actions, const bb_io& io, int i, bbg::GS<T>& S,
+                                           const bbg::Ln& L, T warm, bool bad, int ncmax, int nit) {
   KinOut<T> kin;
-  int cs = d.cam_steps[i] + 1;
-  bool refresh = false;
-  if (p.cameras && cs >= p.cam_period) { refresh = true; cs = 0; }
-  int status = 0, key = 0;
+  int status = ncmax << 8;
+  const int key = bad ? 0 : (nit < WORK_BINS ? nit : WORK_BINS - 1);
   if (!bad) {
-    const float* hf = d.hfield + (p.hf_per_env ? (size_t)i * HF_CELLS : 0);
-    T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
-    T* cq = refresh ? (T*)d.camq + (size_t)i * CST : nullptr;
-    int ncmax, nit;
-    bbg::gRk4(cmc<T>(), S, hf, (T)p.zscale, gs, cq, L, warm, p.solver_mode != 0, ncmax, nit);
     bool b2 = (L.gl < NV && !(babs(S.xv[L.gl]) < (T)1e10));
     for (int k = L.gl; k < NQ; k += bbg::G) b2 |= !(babs(S.xq[k]) < (T)1e10);
     bad = __any_sync(L.mask, b2);
-    status = ncmax << 8;
-    key = nit < WORK_BINS ? nit : WORK_BINS - 1;
 #pragma unroll
     for (int k = 0; k < 4; k++) kin.quatB[k] = S.kin[k];
 #pragma unroll
     for (int k = 0; k < 3; k++) { kin.cvel_ang[k] = S.kin[4 + k]; kin.cvel_lin[k] = S.kin[7 + k]; kin.posB[k] = S.kin[10 + k]; }
-  }
+  } else status = 0;
   if (bad) {
     status |= 1;
     kin.quatB[0] = 1; kin.quatB[1] = kin.quatB[2] = kin.quatB[3] = 0;
@@ -223,10 +229,13 @@ __global__ void __launch_bounds__(32 * BB_WPB, BB_WARP_MINBLOCKS) k_step_warp(En
     if (L.gl < NV) S.xv[L.gl] = 0;
     __syncwarp(L.mask);
   }
+  int cs; const bool refresh = cameraRefresh(p, d, i, cs);
+  T* st = (T*)d.st + (size_t)i * SST;
   // write the state record back (coalesced)
   for (int k = L.gl; k < NQ + NV; k += bbg::G) st[k] = k < NQ ? S.xq[k] : S.xv[k - NQ];
   if (L.gl < NV) st[NQ + NV + L.gl] = warm;
   // ---- observation / reward / termination: every lane evaluates the few scalars, lane 0 (or a few lanes) store
+  const float a0 = actions[3 * i], a1 = actions[3 * i + 1], a2 = actions[3 * i + 2];
   float ob[16];
   proprioObs(kin, (const T*)S.xv, (T)p.max_wheel_vel, ob, ob + 3, ob + 6, ob + 9);
   ob[12] = a0; ob[13] = a1; ob[14] = a2;
@@ -272,6 +281,141 @@ __global__ void __launch_bounds__(32 * BB_WPB, BB_WARP_MINBLOCKS) k_step_warp(En
       d.reset_list[atomicAdd(&d.counters[0], 1)] = i;
     } else if (refresh) d.refresh_list[atomicAdd(&d.counters[1], 1)] = i;
   }
+}
+
+// fused variant: the whole RK4 step of an env inside one launch (step_kernel = 2; cross-check of the split-phase path)
+template <typename T>
+__global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCKS32 : BB_WARP_MINBLOCKS) k_step_warp(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const bbg::Ln L = bbg::makeLn();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / bbg::G;
+  const int slot = (blockIdx.x * (blockDim.x >> 5) + warp) * bbg::EPW + grp;
+  if (slot >= p.N) return;
+  const int i = d.order[slot];
+  bbg::GS<T>& S = reinterpret_cast<bbg::GS<T>*>(smem_raw)[warp * bbg::EPW + grp];
+  T warm;
+  const bool bad = stepLoad(p, d, actions, i, S, L, warm);
+  int ncmax = 0, nit = 0;
+  if (!bad) {
+    int cs; const bool refresh = cameraRefresh(p, d, i, cs);
+    const float* hf = d.hfield + (p.hf_per_env ? (size_t)i * HF_CELLS : 0);
+    T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
+    T* cq = refresh ? (T*)d.camq + (size_t)i * CST : nullptr;
+    bbg::gRk4(cmc<T>(), S, hf, (T)p.zscale, gs, cq, L, warm, p.solver_mode != 0, ncmax, nit);
+  }
+  stepFinish(p, d, actions, io, i, S, L, warm, bad, ncmax, nit);
+}
+
+// split-phase variant (default), see bb_group.cuh "split-phase step".
+// k_stage<T>(stage): stage 0 loads the state; stages 1..3 fold the previous stage into the RK4 sums and advance the
+// stage state; every stage < 4 then runs mj_forward up to the solver and parks the solver input; stage 4 applies the RK4
+// update and finishes the step (observation, reward, termination, work lists).
+template <typename T>
+__global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCKS32 : BB_WARP_MINBLOCKS) k_stage(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io, int stage) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const bbg::Ln L = bbg::makeLn();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / bbg::G;
+  const int i = (blockIdx.x * (blockDim.x >> 5) + warp) * bbg::EPW + grp;
+  if (i >= p.N) return;
+  bbg::GS<T>& S = reinterpret_cast<bbg::GS<T>*>(smem_raw)[warp * bbg::EPW + grp];
+  const ModelConst<T>& mc = cmc<T>();
+  T* rk = (T*)d.rk + (size_t)i * bbg::RKN;
+  int* meta = d.meta + 4 * (size_t)i;
+  const bool dof = L.gl < NV;
+  const T h = mc.timestep;
+  T v0, sumv = 0, suma = 0, xv, warm = 0;
+  int ncmax = 0;
+  if (stage == 0) {
+    const bool bad = stepLoad(p, d, actions, i, S, L, warm);
+    if (L.gl == 0) { meta[bbg::META_NCON] = 0; meta[bbg::META_NW] = 0; meta[bbg::META_NIT] = 0; meta[bbg::META_FLAGS] = bad ? 1 : 0; }
+    if (bad) return;
+    if (L.gl == 0) bb::normalizeQuats(S.xq);
+    __syncwarp(L.mask);
+    for (int k = L.gl; k < NQ; k += bbg::G) rk[bbg::RK_Q0 + k] = S.xq[k];
+    v0 = S.xv[L.gi]; xv = v0;
+    if (dof) { rk[bbg::RK_V0 + L.gl] = v0; rk[bbg::RK_WARM + L.gl] = warm; }
+    if (L.gl < 3) rk[bbg::RK_CTRL + L.gl] = S.ctrl[L.gl];
+  } else {
+    const int flags = meta[bbg::META_FLAGS];
+    ncmax = flags >> 8;
+    if (flags & 1) {   // non-finite state: nothing was integrated; stage 4 reports the failure
+      if (stage == 4) { T w0 = 0; stepLoad(p, d, actions, i, S, L, w0); stepFinish(p, d, actions, io, i, S, L, w0, true, 0, 0); }
+      return;
+    }
+    for (int k = L.gl; k < NQ; k += bbg::G) S.q0[k] = rk[bbg::RK_Q0 + k];
+    for (int k = L.gl; k < bbg::MSZ; k += bbg::G) S.M[k] = 0;
+    if (L.gl < 3) S.ctrl[L.gl] = rk[bbg::RK_CTRL + L.gl];
+    v0 = rk[bbg::RK_V0 + L.gi];
+    const T xvp = rk[bbg::RK_XV + L.gi], qacc = rk[bbg::RK_QACC + L.gi];
+    if (stage > 1) { sumv = rk[bbg::RK_SUMV + L.gi]; suma = rk[bbg::RK_SUMA + L.gi]; }
+    const int sp = stage - 1;                                   // the stage that has just been solved
+    const T bw = (sp == 0 || sp == 3) ? (T)(1.0 / 6.0) : (T)(1.0 / 3.0);
+    sumv += bw * xvp; suma += bw * qacc;
+    const T ha = stage == 4 ? h : (sp == 2 ? h : (T)0.5 * h);
+    if (bbg::G == 16 || L.gl < 16) S.vb[0][L.gl] = dof ? (stage == 4 ? sumv : xvp) : (T)0;
+    __syncwarp(L.mask);
+    if (L.gl == 0) bbg::gIntegrate(S.xq, S.q0, (const T*)S.vb[0], ha);
+    xv = v0 + ha * (stage == 4 ? suma : qacc);
+    if (dof) S.xv[L.gl] = xv;
+    if (L.gl == NV) S.xv[NV] = 0;
+    __syncwarp(L.mask);
+    if (stage == 4) {
+      if (L.gl < 13) S.kin[L.gl] = rk[bbg::RK_KIN + L.gl];
+      __syncwarp(L.mask);
+      stepFinish(p, d, actions, io, i, S, L, qacc, false, ncmax, meta[bbg::META_NIT]);   // qacc_warmstart := last-stage qacc
+      return;
+    }
+  }
+  // ---- mj_forward up to the solver
+  const float* hf = d.hfield + (p.hf_per_env ? (size_t)i * HF_CELLS : 0);
+  T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
+  int nw; T qfs, qas;
+  const int ncon = bbg::gForwardPre(mc, S, hf, (T)p.zscale, gs, L, stage == 3, nw, qfs, qas);
+  if (dof) {
+    rk[bbg::RK_XV + L.gl] = xv;
+    if (stage > 0) { rk[bbg::RK_SUMV + L.gl] = sumv; rk[bbg::RK_SUMA + L.gl] = suma; }
+    if (ncon == 0) {
+      rk[bbg::RK_QACC + L.gl] = qas;
+      if (p.solver_mode != 0 && stage < 3) rk[bbg::RK_WARM + L.gl] = qas;
+    }
+  }
+  if (stage == 3) {
+    if (L.gl < 13) rk[bbg::RK_KIN + L.gl] = S.kin[L.gl];
+    int cs;
+    if (cameraRefresh(p, d, i, cs)) { T* cq = (T*)d.camq + (size_t)i * CST; for (int k = L.gl; k < NQ; k += bbg::G) cq[k] = S.xq[k]; }
+  }
+  if (L.gl == 0) {
+    meta[bbg::META_NCON] = ncon; meta[bbg::META_NW] = nw;
+    if (ncon > ncmax) meta[bbg::META_FLAGS] = ncon << 8;
+  }
+  if (ncon > 0) bbg::ctxSave((T*)d.ctx + (size_t)i * bbg::CTXN, S, ncon, nw, qfs, qas, L);
+}
+// k_newton<T>: constraint solve of one RK stage for the envs that have contacts, in work-sorted order.
+template <typename T>
+__global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCKS32 : BB_WARP_MINBLOCKS) k_newton(EnvParams p, DevState d, int stage) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const bbg::Ln L = bbg::makeLn();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / bbg::G;
+  const int slot = (blockIdx.x * (blockDim.x >> 5) + warp) * bbg::EPW + grp;
+  if (slot >= p.N) return;
+  const int i = d.order[slot];
+  int* meta = d.meta + 4 * (size_t)i;
+  const int ncon = meta[bbg::META_NCON], nw = meta[bbg::META_NW];
+  if (ncon == 0 || (meta[bbg::META_FLAGS] & 1)) return;
+  bbg::GS<T>& S = reinterpret_cast<bbg::GS<T>*>(smem_raw)[warp * bbg::EPW + grp];
+  T* rk = (T*)d.rk + (size_t)i * bbg::RKN;
+  T qfs, qas;
+  bbg::ctxLoad((const T*)d.ctx + (size_t)i * bbg::CTXN, S, ncon, nw, qfs, qas, L);
+  const T warm = L.gl < NV ? rk[bbg::RK_WARM + L.gl] : (T)0;
+  T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
+  bbg::GNewton<T> nwt(cmc<T>(), S, gs, L, ncon, nw, p.solver_mode != 0, qfs, qas);
+  int niter;
+  const T qacc = nwt.run(warm, niter);
+  if (L.gl < NV) {
+    rk[bbg::RK_QACC + L.gl] = qacc;
+    if (p.solver_mode != 0 && stage < 3) rk[bbg::RK_WARM + L.gl] = qacc;
+  }
+  if (L.gl == 0) meta[bbg::META_NIT] += niter;
 }
 // forward-dynamics probe through the group path (same outputs as k_probe)
 template <typename T> __global__ void k_probe_warp(EnvParams p, DevState d, int env, const double* ctrl3, double* out) {
@@ -834,11 +978,24 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   BB_CUDA_C(cudaMalloc(&d.st, e->tsize * SST * N));
   BB_CUDA_C(cudaMalloc(&d.camq, e->tsize * CST * N));
   BB_CUDA_C(cudaMalloc(&d.gscr, e->tsize * (size_t)bbg::GSCR * N));
+  BB_CUDA_C(cudaMalloc(&d.rk, e->tsize * (size_t)bbg::RKN * N)); BB_CUDA_C(cudaMalloc(&d.ctx, e->tsize * (size_t)bbg::CTXN * N));
+  BB_CUDA_C(cudaMalloc(&d.meta, sizeof(int) * 4 * (size_t)N));
+  BB_CUDA_C(cudaMemset(d.rk, 0, e->tsize * (size_t)bbg::RKN * N)); BB_CUDA_C(cudaMemset(d.meta, 0, sizeof(int) * 4 * (size_t)N));
   BB_CUDA_C(cudaMalloc(&d.step_count, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.cam_steps, sizeof(int) * N));
   BB_CUDA_C(cudaMalloc(&d.episode, sizeof(unsigned) * N)); BB_CUDA_C(cudaMalloc(&d.tseed, sizeof(int) * N));
   BB_CUDA_C(cudaMalloc(&d.ep_ret, sizeof(float) * N)); BB_CUDA_C(cudaMalloc(&d.ep_len, sizeof(int) * N));
   BB_CUDA_C(cudaMalloc(&d.counters, sizeof(int) * 2));
   BB_CUDA_C(cudaMalloc(&d.work, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.order, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.bins, sizeof(int) * 2 * WORK_BINS));
+  {  // CTAs of more than one warp may need more than the default 48 KB of dynamic shared memory
+    const int epb = BB_WPB * bbg::EPW;
+    const int sm64 = (int)(epb * sizeof(bbg::GS<double>)), sm32 = (int)(epb * sizeof(bbg::GS<float>));
+    BB_CUDA_C(cudaFuncSetAttribute(k_step_warp<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm64));
+    BB_CUDA_C(cudaFuncSetAttribute(k_step_warp<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm32));
+    BB_CUDA_C(cudaFuncSetAttribute(k_stage<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm64));
+    BB_CUDA_C(cudaFuncSetAttribute(k_stage<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm32));
+    BB_CUDA_C(cudaFuncSetAttribute(k_newton<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm64));
+    BB_CUDA_C(cudaFuncSetAttribute(k_newton<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm32));
+  }
   k_init_order<<<blocksFor(N > 2 * WORK_BINS ? N : 2 * WORK_BINS, 256), 256>>>(N, d);
   BB_CUDA_C(cudaMalloc(&d.reset_list, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.refresh_list, sizeof(int) * N));
   const size_t hfbytes = sizeof(float) * HF_CELLS * (p.hf_per_env ? (size_t)N : 1);
@@ -858,7 +1015,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
 int bb_destroy(bb_engine* e) {
   if (!e) return BB_OK;
   DevState& d = e->d;
-  cudaFree(d.st); cudaFree(d.camq); cudaFree(d.gscr); cudaFree(d.step_count); cudaFree(d.cam_steps); cudaFree(d.episode); cudaFree(d.tseed);
+  cudaFree(d.st); cudaFree(d.camq); cudaFree(d.gscr); cudaFree(d.rk); cudaFree(d.ctx); cudaFree(d.meta); cudaFree(d.step_count); cudaFree(d.cam_steps); cudaFree(d.episode); cudaFree(d.tseed);
   cudaFree(d.work); cudaFree(d.order); cudaFree(d.bins);
   cudaFree(d.ep_ret); cudaFree(d.ep_len); cudaFree(d.counters); cudaFree(d.reset_list); cudaFree(d.refresh_list); cudaFree(d.hfield);
   if (e->prof_ev) { for (int i = 0; i < 5 * e->prof_cap; i++) cudaEventDestroy(e->prof_ev[i]); free(e->prof_ev); }
@@ -903,11 +1060,24 @@ int bb_step(bb_engine* e, const float* actions_dev, const bb_io* io, void* strea
   if (e->cfg.step_kernel == 1) {   // thread-per-env reference mapping
     if (e->cfg.precision == 64) k_step<double><<<blocksFor(N, bs), bs, 0, s>>>(e->p, e->d, actions_dev, *io);
     else k_step<float><<<blocksFor(N, bs), bs, 0, s>>>(e->p, e->d, actions_dev, *io);
-  } else {                         // warp-per-env (default)
+  } else {                         // lane group per env: split-phase (default) or fused
     const int wpb = BB_WPB;
     const int epb = wpb * bbg::EPW;   // envs per CTA
-    if (e->cfg.precision == 64) k_step_warp<double><<<blocksFor(N, epb), wpb * 32, epb * sizeof(bbg::GS<double>), s>>>(e->p, e->d, actions_dev, *io);
-    else k_step_warp<float><<<blocksFor(N, epb), wpb * 32, epb * sizeof(bbg::GS<float>), s>>>(e->p, e->d, actions_dev, *io);
+    const int grid = blocksFor(N, epb), bt = wpb * 32;
+    const size_t sm64 = epb * sizeof(bbg::GS<double>), sm32 = epb * sizeof(bbg::GS<float>);
+    if (e->cfg.step_kernel == 2) {
+      if (e->cfg.precision == 64) k_step_warp<double><<<grid, bt, sm64, s>>>(e->p, e->d, actions_dev, *io);
+      else k_step_warp<float><<<grid, bt, sm32, s>>>(e->p, e->d, actions_dev, *io);
+    } else {
+      for (int stage = 0; stage <= 4; stage++) {
+        if (e->cfg.precision == 64) k_stage<double><<<grid, bt, sm64, s>>>(e->p, e->d, actions_dev, *io, stage);
+        else k_stage<float><<<grid, bt, sm32, s>>>(e->p, e->d, actions_dev, *io, stage);
+        if (stage == 4) break;
+        if (e->cfg.precision == 64) k_newton<double><<<grid, bt, sm64, s>>>(e->p, e->d, stage);
+        else k_newton<float><<<grid, bt, sm32, s>>>(e->p, e->d, stage);
+      }
+      e->launches += 8;
+    }
   }
   if (ev) cudaEventRecord(ev[1], s);
   e->launches += 2;

@@ -699,19 +699,28 @@ __device__ __noinline__ int gCollide(const ModelConst<T>& mc, GS<T>& S, const fl
 }
 
 // ---------------------------------------------------------------------------------------------- one mj_forward (group)
-// in: S.xq, S.xv, S.ctrl, warm (dof-lane register)   out: returns qacc of this dof lane (and S.xq normalised).
+// Everything of mj_forward before the constraint solver: kinematics / mass matrix / bias (gSmooth), contact generation and
+// constraint rows (gCollide), qacc_smooth.  in: S.xq, S.xv, S.ctrl   out: contact count (nw wheel contacts first),
+// qfrc_smooth / qacc_smooth of this dof lane, S.M, the contact records (and S.xq normalised, S.kin when wantKin).
 template <typename T>
-__device__ __noinline__ T gForward(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, const Ln L, T warm, bool fast,
-                                   bool wantKin, int& nconOut, int& niterOut, T* qasOut = nullptr, T* qfsOut = nullptr) {
+__device__ __forceinline__ int gForwardPre(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, const Ln L, bool wantKin,
+                                           int& nw, T& qfs, T& qas) {
   if (L.gl == 0) normalizeQuats(S.xq);
   __syncwarp(L.mask);
   gSmooth(mc, S, wantKin);
   __syncwarp(L.mask);
-  const T qfs = L.gl < NV ? S.vb[0][L.gi] : (T)0;
+  qfs = L.gl < NV ? S.vb[0][L.gi] : (T)0;
   __syncwarp(L.mask);
-  int nw;
   const int ncon = gCollide(mc, S, hf, zscale, gs, L, nw);   // consumes S.geo, which shares storage with the Cholesky factor
-  const T qas = gHessSolve(S, gs, 0, 0, qfs, L);   // qacc_smooth = M^-1 qfrc_smooth
+  qas = gHessSolve(S, gs, 0, 0, qfs, L);   // qacc_smooth = M^-1 qfrc_smooth
+  return ncon;
+}
+// in: S.xq, S.xv, S.ctrl, warm (dof-lane register)   out: returns qacc of this dof lane (and S.xq normalised).
+template <typename T>
+__device__ __noinline__ T gForward(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, const Ln L, T warm, bool fast,
+                                   bool wantKin, int& nconOut, int& niterOut, T* qasOut = nullptr, T* qfsOut = nullptr) {
+  int nw; T qfs, qas;
+  const int ncon = gForwardPre(mc, S, hf, zscale, gs, L, wantKin, nw, qfs, qas);
   if (qasOut) { *qasOut = qas; *qfsOut = qfs; }
   nconOut = ncon; niterOut = 0;
   if (ncon == 0) return qas;
@@ -733,7 +742,7 @@ template <typename T> __device__ __noinline__ void gIntegrate(T* dst, const T* s
 // qlast (global, NQ) receives the last-stage configuration when non-null.
 template <typename T>
 __device__ void gRk4(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, T* qlast, const Ln L, T& warm, bool chain_warm,
-                     int& ncmax, int& nitsum) {
+                     int& ncmax, int& nitsum, bool stage_sync = false) {
   const T h = mc.timestep;
   const bool dof = L.gl < NV;
   if (L.gl == 0) normalizeQuats(S.xq);
@@ -747,6 +756,7 @@ __device__ void gRk4(const ModelConst<T>& mc, GS<T>& S, const float* __restrict_
   for (int st = 0; st < 5; st++) {
     if (st < 4) {
       int nc, ni;
+      if (stage_sync) __syncthreads();
       qacc = gForward(mc, S, hf, zscale, gs, L, warm, chain_warm, st == 3, nc, ni);
       ncmax = nc > ncmax ? nc : ncmax; nitsum += ni;
       const T bw = (st == 0 || st == 3) ? (T)(1.0 / 6.0) : (T)(1.0 / 3.0);
@@ -769,6 +779,41 @@ __device__ void gRk4(const ModelConst<T>& mc, GS<T>& S, const float* __restrict_
       __syncwarp(L.mask);
     }
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------- split-phase step
+// The fused kernel (gRk4) keeps a whole RK4 step of one env inside one warp.  Its instruction stream is ~150 KB and the
+// single-warp CTAs of an SM sit at unrelated program counters, so the kernel is bound by instruction fetch (ncu:
+// no_instruction is the top stall, fp32 and higher occupancy buy nothing).  The split-phase path runs every RK stage as
+// two launches -- k_stage (state advance, smooth dynamics, collision, constraint rows: straight-line code that all warps
+// stream through together) and k_newton (only the solver loop, ~30 KB of hot code) -- and parks the per-env context in
+// HBM between them: RK bookkeeping (RKN words) and the solver input (CTXN words: M, qfrc_smooth, qacc_smooth, contact
+// records).  ~6 KB per env and stage, i.e. < 0.3 ms per step of HBM time at 65,536 envs.
+constexpr int RK_Q0 = 0, RK_V0 = 20, RK_SUMV = 36, RK_SUMA = 52, RK_XV = 68, RK_QACC = 84, RK_WARM = 100, RK_CTRL = 116, RK_KIN = 120, RKN = 136;
+constexpr int CTX_M = 0, CTX_QFS = 120, CTX_QAS = 136, CTX_W = 152, CTX_H = CTX_W + 3 * CRW + 2, CTXN = CTX_H + NHS * CRH;
+constexpr int META_NCON = 0, META_NW = 1, META_NIT = 2, META_FLAGS = 3;   // int[N][4]; flags: bit 0 bad, bits 8.. max ncon
+
+template <typename T> __device__ __forceinline__ void gcopy(T* __restrict__ dst, const T* __restrict__ src, int n, const Ln L) {
+  // n even, both 16-byte aligned
+  for (int k = 2 * L.gl; k < n; k += 2 * G) *reinterpret_cast<typename V2T<T>::t*>(dst + k) = ld2(src + k);
+}
+// solver input of one env -> HBM (after gForwardPre) and back (before GNewton::run)
+template <typename T> __device__ __forceinline__ void ctxSave(T* __restrict__ cx, const GS<T>& S, int ncon, int nw, T qfs, T qas, const Ln L) {
+  gcopy(cx + CTX_M, S.M, MSZ, L);
+  if (G == 16 || L.gl < 16) { cx[CTX_QFS + L.gl] = qfs; cx[CTX_QAS + L.gl] = qas; }
+  gcopy(cx + CTX_W, S.wrec, nw * CRW, L);
+  const int nh = ncon - nw < NHS ? ncon - nw : NHS;
+  gcopy(cx + CTX_H, S.hrec, nh * CRH, L);
+}
+template <typename T> __device__ __forceinline__ void ctxLoad(const T* __restrict__ cx, GS<T>& S, int ncon, int nw, T& qfs, T& qas, const Ln L) {
+  gcopy(S.M, cx + CTX_M, MSZ, L);
+  qfs = cx[CTX_QFS + L.gi]; qas = cx[CTX_QAS + L.gi];
+  if (L.gl >= NV) { qfs = 0; qas = 0; }
+  gcopy(S.wrec, cx + CTX_W, nw * CRW, L);
+  const int nh = ncon - nw < NHS ? ncon - nw : NHS;
+  gcopy(S.hrec, cx + CTX_H, nh * CRH, L);
+  __syncwarp(L.mask);
 }
 
 }  // namespace bbg

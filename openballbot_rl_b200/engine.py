@@ -45,7 +45,7 @@ class BallbotEngine:
         cfg.target_direction[0], cfg.target_direction[1] = float(target_direction[0]), float(target_direction[1])
         cfg.goal_position[0], cfg.goal_position[1] = float(goal_position[0]), float(goal_position[1])
         cfg.distance_scale = float(distance_scale); cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF; cfg.auto_reset = int(bool(auto_reset))
-        cfg.step_kernel = {"warp": 0, "thread": 1}[step_kernel]
+        cfg.step_kernel = {"warp": 0, "split": 0, "thread": 1, "fused": 2}[step_kernel]
         cfg.solver_mode = {"exact": 0, "fast": 1}[solver]
         self.cfg = cfg
         self._L = L

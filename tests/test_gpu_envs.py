@@ -141,6 +141,30 @@ def test_thread_and_warp_kernels_agree():
     e1.close(); e2.close()
 
 
+def test_split_phase_and_fused_group_kernels_agree():
+    """The split-phase path (k_stage / k_newton, context parked in HBM between the launches) runs the same algorithm as the
+    fused group kernel: same termination pattern and rewards through auto-resets and terrain regeneration, states equal to
+    rounding (the two compilations contract a few multiply-adds differently: 1e-15 per step in fp64), both solver modes."""
+    from openballbot_rl_b200.engine import BallbotEngine
+    for solver in ("exact", "fast"):
+        for prec, steps, tol in ((64, 260, 1e-8), (32, 60, 2e-3)):
+            N = 67   # odd: the last warp carries a single env
+            e1 = BallbotEngine(num_envs=N, precision=prec, terrain="perlin", cameras=True, seed=9, step_kernel="split", solver=solver)
+            e2 = BallbotEngine(num_envs=N, precision=prec, terrain="perlin", cameras=True, seed=9, step_kernel="fused", solver=solver)
+            e1.reset(); e2.reset()
+            g = torch.Generator(device="cuda"); g.manual_seed(1)
+            for t in range(steps):
+                a = torch.rand(N, 3, device="cuda", generator=g) * 2 - 1
+                e1.step(a); e2.step(a)
+                assert torch.equal(e1.terminated, e2.terminated), (solver, prec, t)
+                assert float((e1.reward - e2.reward).abs().max()) < tol, (solver, prec, t)
+            (q1, v1, w1), (q2, v2, w2) = e1.get_state(), e2.get_state()
+            assert float((q1 - q2).abs().max()) < tol and float((v1 - v2).abs().max()) < 10 * tol, (solver, prec)
+            assert float((e1.obs["rgbd_0"] - e2.obs["rgbd_0"]).abs().max()) < 1e-3 and torch.equal(e1.status >> 8, e2.status >> 8)
+            assert int(e1.episode_length.max()) > 0 or prec == 32
+            e1.close(); e2.close()
+
+
 def test_fast_solver_mode_within_baseline_tolerance(oracle_mod):
     """solver='fast' (stage-chained warm start) reaches the same minimiser: single-step 1e-5 relative (BASELINE tolerance)."""
     from openballbot_rl_b200.engine import BallbotEngine
