@@ -83,7 +83,7 @@ typedef struct bb_io {
   float* terminal_obs;     /* [N,16] proprio obs before auto-reset (info["terminal_observation"]), valid where terminated */
   float* episode_return;   /* [N]    Monitor info["episode"]["r"], valid where terminated */
   int32_t* episode_length; /* [N]    Monitor info["episode"]["l"], valid where terminated */
-  int32_t* status;         /* [N]    bit0: numerical failure (NaN / |x|>1e10) -> env was reset; bits 8..: max contacts seen */
+  int32_t* status;         /* [N]    bit0: numerical failure (NaN / |x|>1e10) -> env was reset; bits 8..15: max contacts of the RK stages; bits 16..: Newton iterations of the step */
 } bb_io;
 
 typedef struct bb_engine bb_engine;
@@ -150,6 +150,10 @@ typedef struct bb_host_io {
   float* img_0;        /* [N,H*W] or NULL */
   float* img_1;
 } bb_host_io;
+/* The engine's own page-locked staging buffers (valid until bb_destroy): a caller that passes these pointers to
+ * bb_step_host / bb_reset_host gets the results in place, without the extra host-to-host copy (like SubprocVecEnv's
+ * reused observation buffers, the contents are overwritten by the next call). img_0 / img_1 stay NULL. */
+int bb_host_buffers(bb_engine* e, float** actions_host, bb_host_io* out);
 int bb_step_host(bb_engine* e, const float* actions_host, const bb_host_io* out);
 int bb_reset_host(bb_engine* e, const uint8_t* mask_host, const bb_host_io* out);
 

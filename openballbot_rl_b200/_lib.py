@@ -55,7 +55,7 @@ class HostIO(C.Structure):
 EXPORTED = ["bb_create", "bb_destroy", "bb_default_config", "bb_last_error", "bb_num_envs", "bb_reset", "bb_step",
             "bb_add_reward", "bb_set_state", "bb_get_state", "bb_set_hfield", "bb_get_hfield", "bb_get_terrain_seeds",
             "bb_perlin_terrain", "bb_render_depth", "bb_step_host", "bb_reset_host", "bb_launch_count",
-            "bb_model_constants", "bb_probe_forward", "bb_profile_begin", "bb_profile_end", "bb_perlin_grid", "bb_gae"]
+            "bb_model_constants", "bb_probe_forward", "bb_profile_begin", "bb_profile_end", "bb_perlin_grid", "bb_gae", "bb_host_buffers"]
 
 
 def needs_build():
@@ -105,6 +105,7 @@ def lib():
     L.bb_get_terrain_seeds.argtypes = [vp, vp, vp]
     L.bb_perlin_terrain.argtypes = [vp, vp, C.c_int32, vp, vp]
     L.bb_render_depth.argtypes = [vp, vp, vp, vp]
+    L.bb_host_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(HostIO)]
     L.bb_step_host.argtypes = [vp, vp, C.POINTER(HostIO)]
     L.bb_reset_host.argtypes = [vp, vp, C.POINTER(HostIO)]
     L.bb_launch_count.argtypes = [vp]

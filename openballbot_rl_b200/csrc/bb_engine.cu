@@ -26,8 +26,8 @@ namespace {
 #ifndef BB_WPB
 #define BB_WPB 1          // warps per CTA of the step kernel (2 envs per warp); 1 avoids waiting for the slowest warp of a CTA
 #endif
-#ifndef BB_STAGE_SYNC
-#define BB_STAGE_SYNC 0
+#ifndef BB_WPB_STAGE
+#define BB_WPB_STAGE 4    // warps per CTA of k_stage (straight-line phase code: CTA-synchronised phases share instruction fetch)
 #endif
 #ifndef BB_WARP_MINBLOCKS
 #define BB_WARP_MINBLOCKS (12 / BB_WPB)    // fp64: 12 warps per SM (shared memory: 18.3 KB per warp; 168 registers)
@@ -211,7 +211,7 @@ template <typename T>
 __device__ __forceinline__ void stepFinish(const EnvParams& p, const DevState& d, const float* __restrict__ actions, const bb_io& io, int i, bbg::GS<T>& S,
                                            const bbg::Ln& L, T warm, bool bad, int ncmax, int nit) {
   KinOut<T> kin;
-  int status = ncmax << 8;
+  int status = (ncmax << 8) | (nit << 16);   // bit 0: numerical failure, bits 8-15: max contacts of the stages, bits 16+: Newton iterations
   const int key = bad ? 0 : (nit < WORK_BINS ? nit : WORK_BINS - 1);
   if (!bad) {
     bool b2 = (L.gl < NV && !(babs(S.xv[L.gl]) < (T)1e10));
@@ -311,66 +311,74 @@ __global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCK
 // stage state; every stage < 4 then runs mj_forward up to the solver and parks the solver input; stage 4 applies the RK4
 // update and finishes the step (observation, reward, termination, work lists).
 template <typename T>
-__global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCKS32 : BB_WARP_MINBLOCKS) k_stage(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io, int stage) {
+__global__ void __launch_bounds__(32 * BB_WPB_STAGE, (sizeof(T) == 4 ? BB_WARP_MINBLOCKS32 : BB_WARP_MINBLOCKS) * BB_WPB / BB_WPB_STAGE)
+k_stage(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io, int stage) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const bbg::Ln L = bbg::makeLn();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / bbg::G;
-  const int i = (blockIdx.x * (blockDim.x >> 5) + warp) * bbg::EPW + grp;
-  if (i >= p.N) return;
+  const int slot = (blockIdx.x * (blockDim.x >> 5) + warp) * bbg::EPW + grp;
+  const bool live = slot < p.N;              // threads beyond the last env only take part in the CTA barriers
+  const int i = live ? slot : p.N - 1;
+  bool skip = !live;
   bbg::GS<T>& S = reinterpret_cast<bbg::GS<T>*>(smem_raw)[warp * bbg::EPW + grp];
   const ModelConst<T>& mc = cmc<T>();
   T* rk = (T*)d.rk + (size_t)i * bbg::RKN;
   int* meta = d.meta + 4 * (size_t)i;
   const bool dof = L.gl < NV;
   const T h = mc.timestep;
-  T v0, sumv = 0, suma = 0, xv, warm = 0;
+  T v0 = 0, sumv = 0, suma = 0, xv = 0, warm = 0;
   int ncmax = 0;
   if (stage == 0) {
     const bool bad = stepLoad(p, d, actions, i, S, L, warm);
-    if (L.gl == 0) { meta[bbg::META_NCON] = 0; meta[bbg::META_NW] = 0; meta[bbg::META_NIT] = 0; meta[bbg::META_FLAGS] = bad ? 1 : 0; }
-    if (bad) return;
-    if (L.gl == 0) bb::normalizeQuats(S.xq);
-    __syncwarp(L.mask);
-    for (int k = L.gl; k < NQ; k += bbg::G) rk[bbg::RK_Q0 + k] = S.xq[k];
-    v0 = S.xv[L.gi]; xv = v0;
-    if (dof) { rk[bbg::RK_V0 + L.gl] = v0; rk[bbg::RK_WARM + L.gl] = warm; }
-    if (L.gl < 3) rk[bbg::RK_CTRL + L.gl] = S.ctrl[L.gl];
+    if (live && L.gl == 0) { meta[bbg::META_NCON] = 0; meta[bbg::META_NW] = 0; meta[bbg::META_NIT] = 0; meta[bbg::META_FLAGS] = bad ? 1 : 0; }
+    skip |= bad;
+    if (!skip) {
+      if (L.gl == 0) bb::normalizeQuats(S.xq);
+      __syncwarp(L.mask);
+      for (int k = L.gl; k < NQ; k += bbg::G) rk[bbg::RK_Q0 + k] = S.xq[k];
+      v0 = S.xv[L.gi]; xv = v0;
+      if (dof) { rk[bbg::RK_V0 + L.gl] = v0; rk[bbg::RK_WARM + L.gl] = warm; }
+      if (L.gl < 3) rk[bbg::RK_CTRL + L.gl] = S.ctrl[L.gl];
+    }
   } else {
     const int flags = meta[bbg::META_FLAGS];
     ncmax = flags >> 8;
     if (flags & 1) {   // non-finite state: nothing was integrated; stage 4 reports the failure
-      if (stage == 4) { T w0 = 0; stepLoad(p, d, actions, i, S, L, w0); stepFinish(p, d, actions, io, i, S, L, w0, true, 0, 0); }
-      return;
+      if (stage == 4 && live) { T w0 = 0; stepLoad(p, d, actions, i, S, L, w0); stepFinish(p, d, actions, io, i, S, L, w0, true, 0, 0); }
+      skip = true;
     }
-    for (int k = L.gl; k < NQ; k += bbg::G) S.q0[k] = rk[bbg::RK_Q0 + k];
-    for (int k = L.gl; k < bbg::MSZ; k += bbg::G) S.M[k] = 0;
-    if (L.gl < 3) S.ctrl[L.gl] = rk[bbg::RK_CTRL + L.gl];
-    v0 = rk[bbg::RK_V0 + L.gi];
-    const T xvp = rk[bbg::RK_XV + L.gi], qacc = rk[bbg::RK_QACC + L.gi];
-    if (stage > 1) { sumv = rk[bbg::RK_SUMV + L.gi]; suma = rk[bbg::RK_SUMA + L.gi]; }
-    const int sp = stage - 1;                                   // the stage that has just been solved
-    const T bw = (sp == 0 || sp == 3) ? (T)(1.0 / 6.0) : (T)(1.0 / 3.0);
-    sumv += bw * xvp; suma += bw * qacc;
-    const T ha = stage == 4 ? h : (sp == 2 ? h : (T)0.5 * h);
-    if (bbg::G == 16 || L.gl < 16) S.vb[0][L.gl] = dof ? (stage == 4 ? sumv : xvp) : (T)0;
-    __syncwarp(L.mask);
-    if (L.gl == 0) bbg::gIntegrate(S.xq, S.q0, (const T*)S.vb[0], ha);
-    xv = v0 + ha * (stage == 4 ? suma : qacc);
-    if (dof) S.xv[L.gl] = xv;
-    if (L.gl == NV) S.xv[NV] = 0;
-    __syncwarp(L.mask);
-    if (stage == 4) {
-      if (L.gl < 13) S.kin[L.gl] = rk[bbg::RK_KIN + L.gl];
+    if (!skip) {
+      for (int k = L.gl; k < NQ; k += bbg::G) S.q0[k] = rk[bbg::RK_Q0 + k];
+      for (int k = L.gl; k < bbg::MSZ; k += bbg::G) S.M[k] = 0;
+      if (L.gl < 3) S.ctrl[L.gl] = rk[bbg::RK_CTRL + L.gl];
+      v0 = rk[bbg::RK_V0 + L.gi];
+      const T xvp = rk[bbg::RK_XV + L.gi], qacc = rk[bbg::RK_QACC + L.gi];
+      if (stage > 1) { sumv = rk[bbg::RK_SUMV + L.gi]; suma = rk[bbg::RK_SUMA + L.gi]; }
+      const int sp = stage - 1;                                   // the stage that has just been solved
+      const T bw = (sp == 0 || sp == 3) ? (T)(1.0 / 6.0) : (T)(1.0 / 3.0);
+      sumv += bw * xvp; suma += bw * qacc;
+      const T ha = stage == 4 ? h : (sp == 2 ? h : (T)0.5 * h);
+      if (bbg::G == 16 || L.gl < 16) S.vb[0][L.gl] = dof ? (stage == 4 ? sumv : xvp) : (T)0;
       __syncwarp(L.mask);
-      stepFinish(p, d, actions, io, i, S, L, qacc, false, ncmax, meta[bbg::META_NIT]);   // qacc_warmstart := last-stage qacc
-      return;
+      if (L.gl == 0) bbg::gIntegrate(S.xq, S.q0, (const T*)S.vb[0], ha);
+      xv = v0 + ha * (stage == 4 ? suma : qacc);
+      if (dof) S.xv[L.gl] = xv;
+      if (L.gl == NV) S.xv[NV] = 0;
+      __syncwarp(L.mask);
+      if (stage == 4) {
+        if (L.gl < 13) S.kin[L.gl] = rk[bbg::RK_KIN + L.gl];
+        __syncwarp(L.mask);
+        stepFinish(p, d, actions, io, i, S, L, qacc, false, ncmax, meta[bbg::META_NIT]);   // qacc_warmstart := last-stage qacc
+      }
     }
   }
-  // ---- mj_forward up to the solver
+  if (stage == 4) return;
+  // ---- mj_forward up to the solver (CTA-synchronised phases)
   const float* hf = d.hfield + (p.hf_per_env ? (size_t)i * HF_CELLS : 0);
   T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
   int nw; T qfs, qas;
-  const int ncon = bbg::gForwardPre(mc, S, hf, (T)p.zscale, gs, L, stage == 3, nw, qfs, qas);
+  const int ncon = bbg::gForwardPre(mc, S, hf, (T)p.zscale, gs, L, stage == 3, nw, qfs, qas, skip, BB_WPB_STAGE > 1);
+  if (skip) return;
   if (dof) {
     rk[bbg::RK_XV + L.gl] = xv;
     if (stage > 0) { rk[bbg::RK_SUMV + L.gl] = sumv; rk[bbg::RK_SUMA + L.gl] = suma; }
@@ -991,8 +999,9 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
     const int sm64 = (int)(epb * sizeof(bbg::GS<double>)), sm32 = (int)(epb * sizeof(bbg::GS<float>));
     BB_CUDA_C(cudaFuncSetAttribute(k_step_warp<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm64));
     BB_CUDA_C(cudaFuncSetAttribute(k_step_warp<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm32));
-    BB_CUDA_C(cudaFuncSetAttribute(k_stage<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm64));
-    BB_CUDA_C(cudaFuncSetAttribute(k_stage<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm32));
+    const int sepb = BB_WPB_STAGE * bbg::EPW;
+    BB_CUDA_C(cudaFuncSetAttribute(k_stage<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sepb * sizeof(bbg::GS<double>))));
+    BB_CUDA_C(cudaFuncSetAttribute(k_stage<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sepb * sizeof(bbg::GS<float>))));
     BB_CUDA_C(cudaFuncSetAttribute(k_newton<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm64));
     BB_CUDA_C(cudaFuncSetAttribute(k_newton<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm32));
   }
@@ -1069,9 +1078,10 @@ int bb_step(bb_engine* e, const float* actions_dev, const bb_io* io, void* strea
       if (e->cfg.precision == 64) k_step_warp<double><<<grid, bt, sm64, s>>>(e->p, e->d, actions_dev, *io);
       else k_step_warp<float><<<grid, bt, sm32, s>>>(e->p, e->d, actions_dev, *io);
     } else {
+      const int sepb = BB_WPB_STAGE * bbg::EPW, sgrid = blocksFor(N, sepb);
       for (int stage = 0; stage <= 4; stage++) {
-        if (e->cfg.precision == 64) k_stage<double><<<grid, bt, sm64, s>>>(e->p, e->d, actions_dev, *io, stage);
-        else k_stage<float><<<grid, bt, sm32, s>>>(e->p, e->d, actions_dev, *io, stage);
+        if (e->cfg.precision == 64) k_stage<double><<<sgrid, BB_WPB_STAGE * 32, sepb * sizeof(bbg::GS<double>), s>>>(e->p, e->d, actions_dev, *io, stage);
+        else k_stage<float><<<sgrid, BB_WPB_STAGE * 32, sepb * sizeof(bbg::GS<float>), s>>>(e->p, e->d, actions_dev, *io, stage);
         if (stage == 4) break;
         if (e->cfg.precision == 64) k_newton<double><<<grid, bt, sm64, s>>>(e->p, e->d, stage);
         else k_newton<float><<<grid, bt, sm32, s>>>(e->p, e->d, stage);
@@ -1255,20 +1265,29 @@ static int hostReadback(bb_engine* e, const bb_host_io* out) {
   if (e->cfg.cameras && out->img_0) BB_CUDA(cudaMemcpyAsync(out->img_0, o.rgbd_0, sizeof(float) * npix * N, cudaMemcpyDeviceToHost, s));
   if (e->cfg.cameras && out->img_1) BB_CUDA(cudaMemcpyAsync(out->img_1, o.rgbd_1, sizeof(float) * npix * N, cudaMemcpyDeviceToHost, s));
   BB_CUDA(cudaStreamSynchronize(s));
-  if (out->obs16) memcpy(out->obs16, e->h_obs16, sizeof(float) * 16 * N);
-  if (out->reward) memcpy(out->reward, e->h_reward, sizeof(float) * N);
-  if (out->terminated) memcpy(out->terminated, e->h_term, N);
-  if (out->failure) memcpy(out->failure, e->h_fail, N);
-  if (out->pos2d) memcpy(out->pos2d, e->h_pos2d, sizeof(float) * 2 * N);
-  if (out->terminal_obs) memcpy(out->terminal_obs, e->h_term_obs, sizeof(float) * 16 * N);
-  if (out->episode_return) memcpy(out->episode_return, e->h_epret, sizeof(float) * N);
-  if (out->episode_length) memcpy(out->episode_length, e->h_eplen, sizeof(int) * N);
+  if (out->obs16 && out->obs16 != e->h_obs16) memcpy(out->obs16, e->h_obs16, sizeof(float) * 16 * N);
+  if (out->reward && out->reward != e->h_reward) memcpy(out->reward, e->h_reward, sizeof(float) * N);
+  if (out->terminated && out->terminated != e->h_term) memcpy(out->terminated, e->h_term, N);
+  if (out->failure && out->failure != e->h_fail) memcpy(out->failure, e->h_fail, N);
+  if (out->pos2d && out->pos2d != e->h_pos2d) memcpy(out->pos2d, e->h_pos2d, sizeof(float) * 2 * N);
+  if (out->terminal_obs && out->terminal_obs != e->h_term_obs) memcpy(out->terminal_obs, e->h_term_obs, sizeof(float) * 16 * N);
+  if (out->episode_return && out->episode_return != e->h_epret) memcpy(out->episode_return, e->h_epret, sizeof(float) * N);
+  if (out->episode_length && out->episode_length != e->h_eplen) memcpy(out->episode_length, e->h_eplen, sizeof(int) * N);
+  return BB_OK;
+}
+int bb_host_buffers(bb_engine* e, float** actions_host, bb_host_io* out) {
+  if (!e || !out) return BB_ERR_INVALID;
+  int rc = hostInit(e); if (rc) return rc;
+  if (actions_host) *actions_host = e->h_act;
+  memset(out, 0, sizeof(*out));
+  out->obs16 = e->h_obs16; out->reward = e->h_reward; out->terminated = e->h_term; out->failure = e->h_fail; out->pos2d = e->h_pos2d;
+  out->terminal_obs = e->h_term_obs; out->episode_return = e->h_epret; out->episode_length = e->h_eplen;
   return BB_OK;
 }
 int bb_step_host(bb_engine* e, const float* actions_host, const bb_host_io* out) {
   if (!e || !actions_host || !out) return BB_ERR_INVALID;
   int rc = hostInit(e); if (rc) return rc;
-  memcpy(e->h_act, actions_host, sizeof(float) * 3 * e->N);
+  if (actions_host != e->h_act) memcpy(e->h_act, actions_host, sizeof(float) * 3 * e->N);
   BB_CUDA(cudaMemcpyAsync(e->d_act, e->h_act, sizeof(float) * 3 * e->N, cudaMemcpyHostToDevice, e->hstream));
   rc = bb_step(e, e->d_act, &e->dio, e->hstream); if (rc) return rc;
   return hostReadback(e, out);

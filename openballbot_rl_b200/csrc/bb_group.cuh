@@ -174,28 +174,34 @@ __device__ __noinline__ T gHessSolve(GS<T>& S, const T* gs, int ncon, int nw, T 
   // ---- right-looking Cholesky, column per lane, forward substitution fused.  The loop over the pivots is rolled: after
   // step j every lane shifts its column up by one (folded into the update FMA), so the pivot row is always h[0] and
   // the code is one short body (the fully unrolled triangle was 2.7 k instructions and thrashed the instruction cache).
+  // The trailing update touches the 14 - j live rows only up to the granularity of three loop bodies (14 / 9 / 4 rows).
   T myinv = 0, y = b;
   T* Lf = S.Lf;
-#pragma unroll 1
-  for (int j = 0; j < NV; j++) {
-    T piv = gget(h[0], j, L.mask);
-    piv = piv < (T)1e-15 ? (T)1e-15 : piv;
-    const T inv = brsqrt(piv);
-    const T l = h[0] * inv;                       // lanes i >= j: L(i,j)  (lane j: sqrt(pivot))
-    if (gi == j) myinv = inv;
-    const T yj = gget(y, j, L.mask) * inv;        // y_j = (b_j - sum_{k<j} L(j,k) y_k) / L(j,j)
-    if (gi == j) y = yj;
-    const T lz = gi > j ? l : (T)0;
-    y -= lz * yj;
-    Lf[j * LS_ + L.gl] = lz;
-    __syncwarp(L.mask);
-    if (j < NV - 1) {
-      // lanes i > j: A(r,i) -= L(i,j) L(r,j) for the rows r = j+1 .. 14, stored shifted: h[k] <- A(j+1+k, i)
-      const T* cj = Lf + j * LS_ + j + 1;
-#pragma unroll
-      for (int k = 0; k < NV - 1; k++) h[k] = h[k + 1] - lz * cj[k];
-    }
+#define BB_PIVOT_STEP(NUPD)                                                                                               \
+  {                                                                                                                       \
+    T piv = gget(h[0], j, L.mask);                                                                                        \
+    piv = piv < (T)1e-15 ? (T)1e-15 : piv;                                                                                \
+    const T inv = brsqrt(piv);                                                                                            \
+    const T l = h[0] * inv;                       /* lanes i >= j: L(i,j)  (lane j: sqrt(pivot)) */                      \
+    if (gi == j) myinv = inv;                                                                                             \
+    const T yj = gget(y, j, L.mask) * inv;        /* y_j = (b_j - sum_{k<j} L(j,k) y_k) / L(j,j) */                      \
+    if (gi == j) y = yj;                                                                                                  \
+    const T lz = gi > j ? l : (T)0;                                                                                       \
+    y -= lz * yj;                                                                                                         \
+    Lf[j * LS_ + L.gl] = lz;                                                                                              \
+    __syncwarp(L.mask);                                                                                                   \
+    /* lanes i > j: A(r,i) -= L(i,j) L(r,j) for the rows r = j+1 .., stored shifted: h[k] <- A(j+1+k, i) */               \
+    const T* cj = Lf + j * LS_ + j + 1;                                                                                   \
+    _Pragma("unroll") for (int k = 0; k < (NUPD); k++) h[k] = h[k + 1] - lz * cj[k];                                      \
   }
+  int j = 0;
+#pragma unroll 1
+  for (; j < 5; j++) BB_PIVOT_STEP(14)
+#pragma unroll 1
+  for (; j < 10; j++) BB_PIVOT_STEP(9)
+#pragma unroll 1
+  for (; j < NV; j++) BB_PIVOT_STEP(4)
+#undef BB_PIVOT_STEP
   // ---- backward substitution L' x = y (lane k reads its own row of Lf: L(i,k), i > k)
   T x = 0, s = 0;
   const T* lrow = Lf + gi * LS_;
@@ -702,17 +708,26 @@ __device__ __noinline__ int gCollide(const ModelConst<T>& mc, GS<T>& S, const fl
 // Everything of mj_forward before the constraint solver: kinematics / mass matrix / bias (gSmooth), contact generation and
 // constraint rows (gCollide), qacc_smooth.  in: S.xq, S.xv, S.ctrl   out: contact count (nw wheel contacts first),
 // qfrc_smooth / qacc_smooth of this dof lane, S.M, the contact records (and S.xq normalised, S.kin when wantKin).
+// cta_sync: the warps of the CTA enter the three phases together (every thread of the CTA must make the call; `skip`
+// marks threads that only take part in the barriers), so the large straight-line phase code is fetched once per CTA.
 template <typename T>
 __device__ __forceinline__ int gForwardPre(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, const Ln L, bool wantKin,
-                                           int& nw, T& qfs, T& qas) {
-  if (L.gl == 0) normalizeQuats(S.xq);
-  __syncwarp(L.mask);
-  gSmooth(mc, S, wantKin);
-  __syncwarp(L.mask);
-  qfs = L.gl < NV ? S.vb[0][L.gi] : (T)0;
-  __syncwarp(L.mask);
-  const int ncon = gCollide(mc, S, hf, zscale, gs, L, nw);   // consumes S.geo, which shares storage with the Cholesky factor
-  qas = gHessSolve(S, gs, 0, 0, qfs, L);   // qacc_smooth = M^-1 qfrc_smooth
+                                           int& nw, T& qfs, T& qas, bool skip = false, bool cta_sync = false) {
+  int ncon = 0;
+  nw = 0; qfs = 0; qas = 0;
+  if (cta_sync) __syncthreads();
+  if (!skip) {
+    if (L.gl == 0) normalizeQuats(S.xq);
+    __syncwarp(L.mask);
+    gSmooth(mc, S, wantKin);
+    __syncwarp(L.mask);
+    qfs = L.gl < NV ? S.vb[0][L.gi] : (T)0;
+    __syncwarp(L.mask);
+  }
+  if (cta_sync) __syncthreads();
+  if (!skip) ncon = gCollide(mc, S, hf, zscale, gs, L, nw);   // consumes S.geo, which shares storage with the Cholesky factor
+  if (cta_sync) __syncthreads();
+  if (!skip) qas = gHessSolve(S, gs, 0, 0, qfs, L);           // qacc_smooth = M^-1 qfrc_smooth
   return ncon;
 }
 // in: S.xq, S.xv, S.ctrl, warm (dof-lane register)   out: returns qacc of this dof lane (and S.xq normalised).
@@ -742,7 +757,7 @@ template <typename T> __device__ __noinline__ void gIntegrate(T* dst, const T* s
 // qlast (global, NQ) receives the last-stage configuration when non-null.
 template <typename T>
 __device__ void gRk4(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, T* qlast, const Ln L, T& warm, bool chain_warm,
-                     int& ncmax, int& nitsum, bool stage_sync = false) {
+                     int& ncmax, int& nitsum) {
   const T h = mc.timestep;
   const bool dof = L.gl < NV;
   if (L.gl == 0) normalizeQuats(S.xq);
@@ -756,7 +771,6 @@ __device__ void gRk4(const ModelConst<T>& mc, GS<T>& S, const float* __restrict_
   for (int st = 0; st < 5; st++) {
     if (st < 4) {
       int nc, ni;
-      if (stage_sync) __syncthreads();
       qacc = gForward(mc, S, hf, zscale, gs, L, warm, chain_warm, st == 3, nc, ni);
       ncmax = nc > ncmax ? nc : ncmax; nitsum += ni;
       const T bw = (st == 0 || st == 3) ? (T)(1.0 / 6.0) : (T)(1.0 / 3.0);

@@ -205,9 +205,17 @@ class BallbotEngine:
     def _host_io(self, images):
         N = self.num_envs
         if not hasattr(self, "_hbuf"):
-            self._hbuf = dict(obs16=np.zeros((N, 16), np.float32), reward=np.zeros(N, np.float32), terminated=np.zeros(N, np.uint8),
-                              failure=np.zeros(N, np.uint8), pos2d=np.zeros((N, 2), np.float32), terminal_obs=np.zeros((N, 16), np.float32),
-                              episode_return=np.zeros(N, np.float32), episode_length=np.zeros(N, np.int32))
+            # numpy views of the engine's page-locked staging buffers: results land in place (no second host copy)
+            h = _lib.HostIO(); act = C.c_void_p()
+            self._check(self._L.bb_host_buffers(self._h, C.byref(act), C.byref(h)), "bb_host_buffers")
+
+            def view(ptr, ctype, shape):
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=shape)
+            self._hact = view(act, C.c_float, (N, 3))
+            self._hbuf = dict(obs16=view(h.obs16, C.c_float, (N, 16)), reward=view(h.reward, C.c_float, (N,)),
+                              terminated=view(h.terminated, C.c_uint8, (N,)), failure=view(h.failure, C.c_uint8, (N,)),
+                              pos2d=view(h.pos2d, C.c_float, (N, 2)), terminal_obs=view(h.terminal_obs, C.c_float, (N, 16)),
+                              episode_return=view(h.episode_return, C.c_float, (N,)), episode_length=view(h.episode_length, C.c_int32, (N,)))
             if self.cameras:
                 self._hbuf["img_0"] = np.ones((N, 1, self.im_h, self.im_w), np.float32)
                 self._hbuf["img_1"] = np.ones((N, 1, self.im_h, self.im_w), np.float32)

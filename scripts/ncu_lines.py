@@ -11,8 +11,11 @@ import collections, csv, os, re, subprocess, sys, tempfile
 def disasm(lib, kernel_sub):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, check=True, capture_output=True)
-    cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    txt = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
+    txt = []
+    for cub in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):   # one cubin per translation unit
+        t = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+        if kernel_sub in t:
+            txt = t.splitlines(); break
     # find the kernel's .text section
     start = None
     for i, l in enumerate(txt):

@@ -20,4 +20,4 @@ for t in range(a.steps):
     eng.step(act[t % 8])
 e1.record(); torch.cuda.synchronize()
 st = eng.status.cpu()
-print(a.solver, a.precision, a.envs, "last 5 steps ms/step", e0.elapsed_time(e1) / 5, "ncon max", int((st >> 8).max()), "mean", float((st >> 8).float().mean()))
+print(a.solver, a.precision, a.envs, "last 5 steps ms/step", e0.elapsed_time(e1) / 5, "ncon max", int(((st >> 8) & 255).max()), "mean", float(((st >> 8) & 255).float().mean()))

@@ -86,7 +86,7 @@ def test_random_state_single_step_parity(oracle_mod):
     a = rng.uniform(-1, 1, (N, 3)).astype(np.float32)
     eng.step(torch.from_numpy(a).cuda())
     q1, v1, w1 = [x.cpu().numpy() for x in eng.get_state()]
-    ncon = (eng.status.cpu().numpy() >> 8)
+    ncon = (eng.status.cpu().numpy() >> 8) & 255
     e = oracle_mod.OracleEnv()
     for i in range(N):
         e.set_state(qpos[i], qvel[i], warm[i])
