@@ -33,7 +33,7 @@ namespace {
 #define BB_WARP_MINBLOCKS (12 / BB_WPB)    // fp64: 12 warps per SM (shared memory: 18.3 KB per warp; 168 registers)
 #endif
 #ifndef BB_WARP_MINBLOCKS32
-#define BB_WARP_MINBLOCKS32 (12 / BB_WPB)  // fp32 instantiation
+#define BB_WARP_MINBLOCKS32 (24 / BB_WPB)  // fp32 instantiation: half the shared memory and registers => 24 warps per SM (+14 % measured)
 #endif
 constexpr int SST = 48;            // per-env stride of the state array  T[N][SST] (one coalesced 384/192-byte record per env)
 constexpr int CST = 20;            // per-env stride of the camera configuration array T[N][CST]
@@ -647,34 +647,34 @@ __device__ float hitPrim(F3 o, F3 dir, const Prim& p) {
 // visited cell.  The two triangles of a cell are graphs over the cell (split along the (0,0)-(1,1) diagonal, the same
 // diagonal as the collision prisms), so each test is one ray/plane solve plus a range check in cell coordinates.
 __device__ float hitHfield(F3 o, F3 dir, const float* __restrict__ hf, float sx, float sz, float tmax) {
-  const int n = HN; const float dx = 2.f * sx / (n - 1), idx = 1.f / dx, isz = 1.f / sz;
-  float t0 = 0.f, t1 = tmax;
-  {
-    const float oo[2] = {o.x, o.y}, dv[2] = {dir.x, dir.y};
-    for (int ax = 0; ax < 2; ax++) {
-      if (fabsf(dv[ax]) < 1e-18f) { if (oo[ax] < -sx || oo[ax] > sx) return -1.f; }
-      else { float ta = (-sx - oo[ax]) / dv[ax], tb = (sx - oo[ax]) / dv[ax]; if (ta > tb) { const float q = ta; ta = tb; tb = q; } t0 = fmaxf(t0, ta); t1 = fminf(t1, tb); }
-    }
-  }
-  if (t0 >= t1) return -1.f;
+  const int n = HN; const float idx = (float)(n - 1) / (2.f * sx), isz = 1.f / sz;
   const float gx0 = (o.x + sx) * idx, gy0 = (o.y + sx) * idx, dgx = dir.x * idx, dgy = dir.y * idx;   // grid coordinates of the ray
   const float oz = o.z * isz, dz = dir.z * isz;                                                       // raw height units
+  const bool zx = fabsf(dir.x) < 1e-18f, zy = fabsf(dir.y) < 1e-18f;
+  const float ix = zx ? 0.f : 1.f / dgx, iy = zy ? 0.f : 1.f / dgy;
+  // clip the ray to the field [0, n-1]^2 (grid units)
+  float t0 = 0.f, t1 = tmax;
+  if (zx) { if (gx0 < 0.f || gx0 > (float)(n - 1)) return -1.f; }
+  else { const float ta = -gx0 * ix, tb = ((float)(n - 1) - gx0) * ix; t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb)); }
+  if (zy) { if (gy0 < 0.f || gy0 > (float)(n - 1)) return -1.f; }
+  else { const float ta = -gy0 * iy, tb = ((float)(n - 1) - gy0) * iy; t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb)); }
+  if (t0 >= t1) return -1.f;
   int cx = (int)floorf(gx0 + (t0 + 1e-6f) * dgx), cy = (int)floorf(gy0 + (t0 + 1e-6f) * dgy);
   cx = min(max(cx, 0), n - 2); cy = min(max(cy, 0), n - 2);
-  const bool zx = fabsf(dir.x) < 1e-18f, zy = fabsf(dir.y) < 1e-18f;
   const int stx = dir.x > 0.f ? 1 : -1, sty = dir.y > 0.f ? 1 : -1;
-  const float ix = zx ? 0.f : 1.f / dgx, iy = zy ? 0.f : 1.f / dgy;
   const float tdx = zx ? 3e38f : fabsf(ix), tdy = zy ? 3e38f : fabsf(iy);
   float tmx = zx ? 3e38f : ((float)(cx + (stx > 0 ? 1 : 0)) - gx0) * ix;
   float tmy = zy ? 3e38f : ((float)(cy + (sty > 0 ? 1 : 0)) - gy0) * iy;
   float tcur = t0;
+  const bool down = dz < 0.f;
   const float e = 1e-5f;
   for (int it = 0; it < 4 * n; it++) {
-    if (cx < 0 || cx > n - 2 || cy < 0 || cy > n - 2 || tcur > t1) return -1.f;
+    if (tcur > t1) return -1.f;                                               // left the field or the depth range
     const float* h = hf + cy * n + cx;
     const float h00 = h[0], h10 = h[1], h01 = h[n], h11 = h[n + 1];
-    const float texit = fminf(fminf(tmx, tmy), t1);
-    const float zlow = fminf(oz + tcur * dz, oz + texit * dz);               // lowest point of the ray inside this cell
+    const bool xs = tmx < tmy;
+    const float tn = xs ? tmx : tmy, texit = fminf(tn, t1);
+    const float zlow = oz + (down ? texit : tcur) * dz;                       // lowest point of the ray inside this cell
     if (zlow <= fmaxf(fmaxf(h00, h10), fmaxf(h01, h11))) {                    // otherwise the ray passes above both triangles
       const float u0 = gx0 - (float)cx, v0 = gy0 - (float)cy, c0 = h00 - oz;
       float best = -1.f;
@@ -696,39 +696,48 @@ __device__ float hitHfield(F3 o, F3 dir, const float* __restrict__ hf, float sx,
       }
       if (best > 0.f && best <= tmax) return best;
     }
-    if (tmx < tmy) { cx += stx; tcur = tmx; tmx += tdx; } else { cy += sty; tcur = tmy; tmy += tdy; }
+    // next cell (indices are clamped: beyond the field edge tcur exceeds t1 and the loop ends)
+    if (xs) { cx = min(max(cx + stx, 0), n - 2); tmx += tdx; } else { cy = min(max(cy + sty, 0), n - 2); tmy += tdy; }
+    tcur = tn;
   }
   return -1.f;
 }
+// scene item `item` of env i: 0,1 cameras; 2 ball; 3..5 wheel capsules; 6 tower cylinder; 7,8 camera sticks (one thread each)
 template <typename T>
-__device__ void buildScene(const ModelConst<float>& mc, const T* __restrict__ cq, int stride, int i, Scene& sc) {
+__device__ void buildScene(const ModelConst<float>& mc, const T* __restrict__ cq, int stride, int i, Scene& sc, int item) {
   float q[NQ]; for (int k = 0; k < NQ; k++) q[k] = (float)cq[(size_t)i * stride + k];
-  const Rot<float> RB = quat2rot(q[3], q[4], q[5], q[6]), RL = quat2rot(q[13], q[14], q[15], q[16]);
-  const V3<float> pB = mk(q[0], q[1], q[2]), pL = mk(q[10], q[11], q[12]);
+  const Rot<float> RB = quat2rot(q[3], q[4], q[5], q[6]);
+  const V3<float> pB = mk(q[0], q[1], q[2]);
   auto toF = [](const V3<float>& v) { return f3(v.x, v.y, v.z); };
-  for (int c = 0; c < 2; c++) {
+  if (item < 2) {
+    const int c = item;
     sc.cam_o[c] = toF(pB + rot(RB, ld3(mc.cam_pos[c])));
     const float* m = mc.cam_rot[c];   // row-major camera->base rotation
     sc.cam_x[c] = toF(rot(RB, mk(m[0], m[3], m[6]))); sc.cam_y[c] = toF(rot(RB, mk(m[1], m[4], m[7]))); sc.cam_z[c] = toF(rot(RB, mk(m[2], m[5], m[8])));
+    return;
   }
-  Prim& b = sc.prim[0]; b.type = 0; b.c = toF(pL + rot(RL, mk(0.f, 0.f, mc.dz))); b.r = mc.ball_r; b.hl = 0.f; b.u = f3(0, 0, 1);
-  for (int w = 0; w < 3; w++) {
+  const int g = item - 2;
+  Prim& pr = sc.prim[g];
+  if (g == 0) {
+    const Rot<float> RL = quat2rot(q[13], q[14], q[15], q[16]);
+    pr.type = 0; pr.c = toF(mk(q[10], q[11], q[12]) + rot(RL, mk(0.f, 0.f, mc.dz))); pr.r = mc.ball_r; pr.hl = 0.f; pr.u = f3(0, 0, 1);
+  } else if (g < 4) {
+    const int w = g - 1;
     float sq, cq2; sincosf(q[7 + w], &sq, &cq2);
     const V3<float> a = ld3(mc.ax[w]);
     const V3<float> si = rodrigues(a, ld3(mc.s0[w]), sq, cq2), ui = rodrigues(a, ld3(mc.u0[w]), sq, cq2);
-    Prim& pr = sc.prim[1 + w]; pr.type = 1; pr.r = mc.wheel_r; pr.hl = mc.wheel_hl;
+    pr.type = 1; pr.r = mc.wheel_r; pr.hl = mc.wheel_hl;
     pr.c = toF(pB + rot(RB, ld3(mc.anc[w]) + si)); pr.u = toF(rot(RB, ui));
-  }
-  Prim& tw = sc.prim[4]; tw.type = 2; tw.r = mc.tower_r; tw.hl = mc.tower_hl; tw.c = toF(pB + rot(RB, ld3(mc.tower_c))); tw.u = toF(RB.c2);
-  for (int k = 0; k < 2; k++) {
-    Prim& pr = sc.prim[5 + k]; pr.type = 1; pr.r = mc.stick_r; pr.hl = mc.stick_hl;
+  } else if (g == 4) {
+    pr.type = 2; pr.r = mc.tower_r; pr.hl = mc.tower_hl; pr.c = toF(pB + rot(RB, ld3(mc.tower_c))); pr.u = toF(RB.c2);
+  } else {
+    const int k = g - 5;
+    pr.type = 1; pr.r = mc.stick_r; pr.hl = mc.stick_hl;
     pr.c = toF(pB + rot(RB, ld3(mc.stick_c[k]))); pr.u = toF(rot(RB, ld3(mc.stick_u[k])));
   }
-  for (int g = 0; g < 7; g++) {   // squared bounding-sphere radii (sphere r, capsule hl + r, cylinder sqrt(r^2 + hl^2)), 1 mm slack
-    const Prim& pr = sc.prim[g];
-    const float br = pr.type == 0 ? pr.r : (pr.type == 1 ? pr.hl + pr.r : sqrtf(pr.r * pr.r + pr.hl * pr.hl));
-    sc.brad2[g] = (br + 1e-3f) * (br + 1e-3f);
-  }
+  // squared bounding-sphere radius (sphere r, capsule hl + r, cylinder sqrt(r^2 + hl^2)), 1 mm slack
+  const float br = pr.type == 0 ? pr.r : (pr.type == 1 ? pr.hl + pr.r : sqrtf(pr.r * pr.r + pr.hl * pr.hl));
+  sc.brad2[g] = (br + 1e-3f) * (br + 1e-3f);
 }
 // block = (env from work list, camera); threads stride over the pixels
 template <typename T>
@@ -741,7 +750,7 @@ __global__ void __launch_bounds__(256) k_depth(EnvParams p, DevState d, const in
   for (int k = blockIdx.x; k < n; k += gridDim.x) {
     const int env = list ? list[k] : k;
     __syncthreads();
-    if (threadIdx.x == 0) buildScene(c_mc32, cfgq, cfg_stride, env, sc);
+    if (threadIdx.x < 9) buildScene(c_mc32, cfgq, cfg_stride, env, sc, threadIdx.x);
     __syncthreads();
     const float* hf = d.hfield + (p.hf_per_env ? (size_t)env * HF_CELLS : 0);
     float* out = (cam ? img1 : img0) + (size_t)env * npix;
