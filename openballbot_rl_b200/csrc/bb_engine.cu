@@ -64,7 +64,7 @@ struct DevState {
   int* step_count; int* cam_steps; unsigned* episode; int* tseed;
   float* hfield;   // [N][HF_CELLS] (hf_per_env) or [HF_CELLS]
   float* ep_ret; int* ep_len;
-  int* counters;   // [0] reset-list length, [1] refresh-list length
+  int* counters;   // [0] reset-list length, [1] refresh-list length, [2] depth work-unit cursor
   int* reset_list; int* refresh_list;
   // work-sorted scheduling of the group step kernel: key = Newton iterations of the env's previous step (capped)
   int* work;       // [N] key of the previous step
@@ -456,11 +456,11 @@ __global__ void k_mask_to_list(EnvParams p, DevState d, const uint8_t* __restric
 }
 // k_begin_step, one block of WORK_BINS threads: clears the work-list counters and turns the key histogram of the previous step into
 // the scatter cursors of k_order (descending keys: the longest solves are scheduled first).
-__global__ void k_clear_counters(DevState d) { d.counters[0] = 0; d.counters[1] = 0; }
+__global__ void k_clear_counters(DevState d) { d.counters[0] = 0; d.counters[1] = 0; d.counters[2] = 0; }
 __global__ void k_begin_step(DevState d) {
   __shared__ int h[WORK_BINS];
   const int t = threadIdx.x;
-  if (t == 0) { d.counters[0] = 0; d.counters[1] = 0; }
+  if (t == 0) { d.counters[0] = 0; d.counters[1] = 0; d.counters[2] = 0; }
   h[t] = d.bins[t];
   __syncthreads();
   int start = 0;
@@ -739,26 +739,38 @@ __device__ void buildScene(const ModelConst<float>& mc, const T* __restrict__ cq
   const float br = pr.type == 0 ? pr.r : (pr.type == 1 ? pr.hl + pr.r : sqrtf(pr.r * pr.r + pr.hl * pr.hl));
   sc.brad2[g] = (br + 1e-3f) * (br + 1e-3f);
 }
-// block = (env from work list, camera); threads stride over the pixels
+// Persistent warps, no CTA barriers: a unit of work is (env from the work list, camera, quarter of the image); every warp
+// draws units from a global counter (d.counters[2], cleared at the start of each bb_step / bb_reset / bb_render_depth),
+// builds the scene in its own shared-memory slot (9 lanes, one item each) and renders the unit's 8 x 4-pixel tiles
+// (neighbouring rays traverse similar cells => less divergence than row segments).  Consecutive units belong to the same
+// env, so the warps of a CTA share heightfield lines in L1/L2.
+constexpr int DEPTH_PARTS = 4;
 template <typename T>
 __global__ void __launch_bounds__(256) k_depth(EnvParams p, DevState d, const int* __restrict__ list, const int* __restrict__ count,
                                                int fixed_count, const T* __restrict__ cfgq, int cfg_stride, float* __restrict__ img0, float* __restrict__ img1) {
-  __shared__ Scene sc;
+  __shared__ Scene scs[8];
+  const int lane = threadIdx.x & 31;
+  Scene& sc = scs[threadIdx.x >> 5];
   const int n = count ? *count : fixed_count;
-  const int cam = blockIdx.y;
+  const int units = n * 2 * DEPTH_PARTS;
   const int npix = p.im_h * p.im_w;
-  for (int k = blockIdx.x; k < n; k += gridDim.x) {
+  const int tiles_x = (p.im_w + 7) >> 3, tiles = tiles_x * ((p.im_h + 3) >> 2), chunk = (tiles + DEPTH_PARTS - 1) / DEPTH_PARTS;
+  const int lx = lane & 7, ly = lane >> 3;
+  for (;;) {
+    int u = 0;
+    if (lane == 0) u = atomicAdd(&d.counters[2], 1);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= units) break;
+    const int k = u / (2 * DEPTH_PARTS), cam = (u / DEPTH_PARTS) & 1, part = u % DEPTH_PARTS;
     const int env = list ? list[k] : k;
-    __syncthreads();
-    if (threadIdx.x < 9) buildScene(c_mc32, cfgq, cfg_stride, env, sc, threadIdx.x);
-    __syncthreads();
+    __syncwarp();
+    if (lane < 9) buildScene(c_mc32, cfgq, cfg_stride, env, sc, lane);
+    __syncwarp();
     const float* hf = d.hfield + (p.hf_per_env ? (size_t)env * HF_CELLS : 0);
     float* out = (cam ? img1 : img0) + (size_t)env * npix;
     const F3 o = sc.cam_o[cam];
-    // each warp renders tiles of 8 x 4 pixels (neighbouring rays traverse similar cells => less divergence than row segments)
-    const int tiles_x = (p.im_w + 7) >> 3, tiles = tiles_x * ((p.im_h + 3) >> 2);
-    const int lx = threadIdx.x & 7, ly = (threadIdx.x >> 3) & 3;
-    for (int tile = threadIdx.x >> 5; tile < tiles; tile += blockDim.x >> 5) {
+    const int tend = min(tiles, (part + 1) * chunk);
+    for (int tile = part * chunk; tile < tend; tile++) {
       const int r = (tile / tiles_x) * 4 + ly, c = (tile % tiles_x) * 8 + lx;
       if (r >= p.im_h || c >= p.im_w) continue;
       const int px = r * p.im_w + c;
@@ -897,6 +909,8 @@ static int checkIo(bb_engine* e, const bb_io* io) {
   return BB_OK;
 }
 
+// persistent grid of k_depth: 4 CTAs of 8 warps per SM, never more warps than work units
+static inline int depthGrid(int N) { const int need = (N * 2 * DEPTH_PARTS + 7) / 8; return need < 148 * 4 ? need : 148 * 4; }
 // terrain regeneration + state reset + depth refresh for whatever is in the work lists
 static int launchResetAndRender(bb_engine* e, const bb_io* io, cudaStream_t s, bool do_reset, cudaEvent_t* ev = nullptr) {
   const int N = e->N;
@@ -913,7 +927,7 @@ static int launchResetAndRender(bb_engine* e, const bb_io* io, cudaStream_t s, b
   } else if (ev) cudaEventRecord(ev[2], s);
   if (ev) cudaEventRecord(ev[3], s);
   if (e->cfg.cameras) {
-    dim3 grid(N < 148 * 8 ? N : 148 * 8, 2);
+    const int grid = depthGrid(N);
     if (e->cfg.precision == 64) k_depth<double><<<grid, 256, 0, s>>>(e->p, e->d, e->d.refresh_list, e->d.counters + 1, 0, (const double*)e->d.camq, CST, io->rgbd_0, io->rgbd_1);
     else k_depth<float><<<grid, 256, 0, s>>>(e->p, e->d, e->d.refresh_list, e->d.counters + 1, 0, (const float*)e->d.camq, CST, io->rgbd_0, io->rgbd_1);
     e->launches++;
@@ -1001,7 +1015,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   BB_CUDA_C(cudaMalloc(&d.step_count, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.cam_steps, sizeof(int) * N));
   BB_CUDA_C(cudaMalloc(&d.episode, sizeof(unsigned) * N)); BB_CUDA_C(cudaMalloc(&d.tseed, sizeof(int) * N));
   BB_CUDA_C(cudaMalloc(&d.ep_ret, sizeof(float) * N)); BB_CUDA_C(cudaMalloc(&d.ep_len, sizeof(int) * N));
-  BB_CUDA_C(cudaMalloc(&d.counters, sizeof(int) * 2));
+  BB_CUDA_C(cudaMalloc(&d.counters, sizeof(int) * 4));
   BB_CUDA_C(cudaMalloc(&d.work, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.order, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.bins, sizeof(int) * 2 * WORK_BINS));
   {  // CTAs of more than one warp may need more than the default 48 KB of dynamic shared memory
     const int epb = BB_WPB * bbg::EPW;
@@ -1023,7 +1037,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   BB_CUDA_C(cudaMemset(d.step_count, 0, sizeof(int) * N)); BB_CUDA_C(cudaMemset(d.cam_steps, 0, sizeof(int) * N));
   BB_CUDA_C(cudaMemset(d.episode, 0, sizeof(unsigned) * N)); BB_CUDA_C(cudaMemset(d.tseed, 0, sizeof(int) * N));
   BB_CUDA_C(cudaMemset(d.ep_ret, 0, sizeof(float) * N)); BB_CUDA_C(cudaMemset(d.ep_len, 0, sizeof(int) * N));
-  BB_CUDA_C(cudaMemset(d.counters, 0, sizeof(int) * 2));
+  BB_CUDA_C(cudaMemset(d.counters, 0, sizeof(int) * 4));
   BB_CUDA_C(cudaDeviceSynchronize());
 #undef BB_CUDA_C
   *out = e;
@@ -1164,7 +1178,8 @@ int bb_perlin_terrain(bb_engine* e, const int32_t* seeds, int32_t n, float* out,
 int bb_render_depth(bb_engine* e, float* img0, float* img1, void* stream) {
   if (!e || !img0 || !img1) return BB_ERR_INVALID;
   const int N = e->N; cudaStream_t s = (cudaStream_t)stream;
-  dim3 grid(N < 148 * 8 ? N : 148 * 8, 2);
+  const int grid = depthGrid(N);
+  BB_CUDA(cudaMemsetAsync(e->d.counters + 2, 0, sizeof(int), s));   // work-unit cursor of k_depth
   if (e->cfg.precision == 64) k_depth<double><<<grid, 256, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const double*)e->d.st, SST, img0, img1);
   else k_depth<float><<<grid, 256, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const float*)e->d.st, SST, img0, img1);
   e->launches++;
