@@ -33,11 +33,13 @@ BYTES_STATE = {64: 874.0, 32: 498.0}       # state + action read, state + obs + 
 BYTES_HF_FOOTPRINT = 400.0                 # ~100 heightfield cells under the robot, once per step
 BYTES_DEPTH_REFRESH = 32768.0 + 13600.0    # 2 images written + unique heightfield read, per camera refresh
 BYTES_TERRAIN = 343396.0                   # one regenerated 293x293 float32 heightfield per reset
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-# (profiles/r01b_ncu_full_perlin32k.txt: perlin, fp64, 32,768 envs), expressed per env / per refreshed env so that it
-# scales to the launch sizes of this run.  The step kernel's excess over its algorithmic bytes is written-back
-# local-memory (register spill) lines of the smooth-dynamics pass, not re-read state.
-NCU_TRAFFIC = {"step": (59.30e6 + 346.50e6) / 32768.0, "depth": (104.16e6 + 162.20e6) / (32768.0 / 6.0)}
+# dram__bytes_read.sum + dram__bytes_write.sum from the committed `ncu --set full` capture
+# (profiles/r01c_ncu_full_perlin32k.txt: perlin, fp64, 32,768 envs), expressed per env / per refreshed env so that it
+# scales to the launch sizes of this run.  "step" = the 9 launches of one step (5 x k_stage + 4 x k_newton): 736.5 MB +
+# 329.0 MB + 37.3 MB.  The excess over the algorithmic bytes is the split-phase context that is parked in HBM between
+# the stage and solver launches on purpose (~6 KB per env and stage written and read back; it buys the instruction-fetch
+# fix described in DESIGN.md and costs ~0.2 ms of HBM time per step), plus register-spill lines of the smooth-dynamics pass.
+NCU_TRAFFIC = {"step": (736.5e6 + 329.0e6 + 37.3e6) / 32768.0, "depth": (104.36e6 + 163.02e6) / (32768.0 / 6.0)}
 
 
 def load_peaks():
@@ -256,10 +258,10 @@ def main():
                 "dtype": f"f{args.precision}", "data": "synthetic",
                 "config": dict(config, preroll_steps=preroll, l2="working set (state + per-env heightfields + images) exceeds the 126 MB L2; no flush needed",
                                resets_in_timed_region=total_resets, mean_episode_len=(world * envs * steps / total_resets) if total_resets else None),
-                "roofline": {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "roofline": {"bound": "hbm", "kernel": "k_stage x5 + k_newton x4 (one step)" if dom == "step" else f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (NCU_TRAFFIC[dom] * (envs if dom == "step" else refresh_per_step + resets_per_step_gpu)
                                          if perlin and args.precision == 64 and dom in NCU_TRAFFIC else None),
-                             "traffic_source": "profiles/r01b_ncu_full_perlin32k.txt (per-env figure of the 32,768-env capture x this launch's envs)",
+                             "traffic_source": "profiles/r01c_ncu_full_perlin32k.txt (per-env figure of the 32,768-env capture x this launch's envs)",
                              "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
                              "alg_bytes_per_launch": alg[dom], "kernel_ms_per_launch": kern[dom], "kernel_ms_all": kern,
                              "whole_step_achieved_gbs": whole, "whole_step_frac": whole / peak,
