@@ -90,6 +90,18 @@ __device__ __forceinline__ void sqrtInv(double x, double& s, double& is) {
   s = fma(fma(-s0, s0, x), 0.5 * is, s0);
 }
 
+// a / b for b >= 1e-15 (the clamped second derivative of the line search): reciprocal seed + two Newton steps + one
+// residual correction instead of the IEEE division sequence (shorter dependent chain; the result is within 1 ulp)
+__device__ __forceinline__ float fdivPos(float a, float b) { return a / b; }
+__device__ __forceinline__ double fdivPos(double a, double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  r = fma(fma(-b, r, 1.0), r, r);
+  r = fma(fma(-b, r, 1.0), r, r);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+
 template <typename T> __device__ __forceinline__ T* crec(GS<T>& S, T* gs, int c, int nw) {
   return c < nw ? S.wrec + c * CRW : (c - nw < NHS ? S.hrec + (c - nw) * CRH : gs + (c - nw - NHS) * CRH);
 }
@@ -324,7 +336,7 @@ __device__ __noinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, const 
   LsPt<T> p; p.alpha = alpha;
   p.cost = q.qG0 + alpha * (q.qG1 + alpha * q.qG2) + cost; p.d1 = q.qG1 + (T)2 * alpha * q.qG2 + d1; p.d2 = (T)2 * q.qG2 + d2;
   if (p.d2 < (T)1e-15) p.d2 = (T)1e-15;
-  p.nxt = alpha - p.d1 / p.d2;
+  p.nxt = alpha - fdivPos(p.d1, p.d2);
   if (L.gl < LSP_W) S.lsp[slot * LSP_W + L.gl] = L.gl == LSP_ALPHA ? alpha : (L.gl == LSP_COST ? p.cost : (L.gl == LSP_D1 ? p.d1 : p.nxt));
   __syncwarp(L.mask);
   return p;
