@@ -265,7 +265,7 @@ def main():
                              "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
                              "alg_bytes_per_launch": alg[dom], "kernel_ms_per_launch": kern[dom], "kernel_ms_all": kern,
                              "whole_step_achieved_gbs": whole, "whole_step_frac": whole / peak,
-                             "note": "compute-bound physics: see profiles/ for FP64/FP32 pipe utilisation"},
+                             "note": "not HBM-bound: the constraint solver (k_newton, 64 % of the step) is bound by the latency of its dependent chain (ncu: wait 2.6 cycles per issue, IPC 1.6 of 4, FP64 pipe 16 %, DRAM 1 %); depth ray-cast and terrain noise are instruction-issue bound (IPC 3.0 / 3.5); see profiles/README.md"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "bb_step_host (C ABI, host buffers); depth images stay device-resident for the policy encoder"},
                 "gpu_launches": int(launches),
