@@ -215,3 +215,28 @@ def test_fixed_policy_episode_on_engine_matches_reference_eval(oracle_mod):
     assert abs(int(L[0]) - ref_len) <= 0.08 * ref_len, (L, ref_len)
     assert abs(float(G[0]) - ref_ret) <= 0.06 * ref_ret, (G, ref_ret)
     venv.close()
+
+
+def test_random_policy_statistics_on_engine_match_reference_records():
+    """Statistical pin at GPU scale (BASELINE: "episode-return distributions ... statistically indistinguishable"): the
+    reference's first PPO rollout -- N(0,1) actions clipped to [-1,1], 2048 steps per env, Monitor statistics of the
+    episodes completed inside the rollout -- recorded ep_len_mean 446.1 / ep_rew_mean 8.887 on flat terrain and
+    157.8 / 3.186 on perlin (outputs/experiments/archived_models/*/progress.csv:2, 10 envs => ~45 / ~130 episodes, i.e. a
+    standard error of roughly 20 / 5 steps on the recorded means).  Same protocol here with 1024 envs per terrain."""
+    from openballbot_rl_b200.engine import BallbotEngine
+    ref = {"flat": (446.1, 8.887, 60.0, 1.0), "perlin": (157.8, 3.186, 15.0, 0.5)}
+    for terrain, (len_ref, ret_ref, len_tol, ret_tol) in ref.items():
+        N = 1024
+        eng = BallbotEngine(num_envs=N, precision=64, terrain=terrain, cameras=False, seed=4)
+        eng.reset()
+        g = torch.Generator(device="cuda"); g.manual_seed(123)
+        n_ep = torch.zeros((), device="cuda"); s_len = torch.zeros((), device="cuda"); s_ret = torch.zeros((), device="cuda")
+        for t in range(2048):
+            a = torch.randn(N, 3, device="cuda", generator=g).clamp_(-1, 1)
+            eng.step(a)
+            d = eng.terminated.bool()
+            n_ep += d.sum(); s_len += eng.episode_length[d].sum(); s_ret += eng.episode_return[d].sum()
+        n = float(n_ep); ml, mr = float(s_len) / n, float(s_ret) / n
+        assert n > 3 * N, (terrain, n)
+        assert abs(ml - len_ref) < len_tol and abs(mr - ret_ref) < ret_tol, (terrain, ml, mr, n)
+        eng.close()
