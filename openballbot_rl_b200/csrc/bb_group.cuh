@@ -133,7 +133,7 @@ template <typename T> __device__ __noinline__ void gSmooth(const ModelConst<T>& 
 // Assembles column gi of H = M + sum_{c < ncon, zone != 0} J_c' W_c J_c in registers, factorises H = L L' across the
 // group and returns x[gi] of H x = b (b: one value per dof lane).  ncon = 0 gives M^-1 b (qacc_smooth).
 template <typename T>
-__device__ __noinline__ T gHessSolve(GS<T>& S, const T* gs, int ncon, int nw, T b, const Ln L) {
+__device__ __forceinline__ T gHessSolve(GS<T>& S, const T* gs, int ncon, int nw, T b, const Ln L) {
   const int gi = L.gi;
   T h[NV];
   {
@@ -304,7 +304,7 @@ template <typename T> __device__ __noinline__ Sum3<T> gsum3(T a, T b, T c, unsig
 // cost and derivatives of the 1-D line-search objective at alpha (PrimalEval); uniform over the group.  The point is
 // also parked in slot `slot` of S.lsp so that the search logic can refer to older points by index.
 template <typename T>
-__device__ __noinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, const T* gs, int ncon, int nw, const LsCtx<T> q, T alpha, int slot, const Ln L) {
+__device__ __forceinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, const T* gs, int ncon, int nw, const LsCtx<T> q, T alpha, int slot, const Ln L) {
   T cost = 0, d1 = 0, d2 = 0;
 #pragma unroll 1
   for (int c = L.gl; c < ncon; c += G) {
