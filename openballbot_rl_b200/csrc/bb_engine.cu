@@ -398,27 +398,36 @@ k_stage(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io, in
   }
   if (ncon > 0) bbg::ctxSave((T*)d.ctx + (size_t)i * bbg::CTXN, S, ncon, nw, qfs, qas, L);
 }
-// k_newton<T>: constraint solve of one RK stage for the envs that have contacts, in work-sorted order.
+// k_newton<T>: constraint solve of one RK stage for the envs that have contacts, in work-sorted order.  Uniform-warp
+// solver (GNewton<T, true>): a warp leaves only when neither of its envs has contacts; otherwise both groups run the solver
+// loops together and every collective uses the constant full-warp mask.
 template <typename T>
 __global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCKS32 : BB_WARP_MINBLOCKS) k_newton(EnvParams p, DevState d, int stage) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const bbg::Ln L = bbg::makeLn();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / bbg::G;
   const int slot = (blockIdx.x * (blockDim.x >> 5) + warp) * bbg::EPW + grp;
-  if (slot >= p.N) return;
-  const int i = d.order[slot];
+  const bool live = slot < p.N;
+  const int i = d.order[live ? slot : p.N - 1];
   int* meta = d.meta + 4 * (size_t)i;
-  const int ncon = meta[bbg::META_NCON], nw = meta[bbg::META_NW];
-  if (ncon == 0 || (meta[bbg::META_FLAGS] & 1)) return;
+  int ncon = meta[bbg::META_NCON], nw = meta[bbg::META_NW];
+  const bool act = live && ncon > 0 && !(meta[bbg::META_FLAGS] & 1);
+  if (!__any_sync(0xffffffffu, act)) return;
+  if (!act) { ncon = 0; nw = 0; }                      // passenger group: empty contact loops, results discarded
   bbg::GS<T>& S = reinterpret_cast<bbg::GS<T>*>(smem_raw)[warp * bbg::EPW + grp];
   T* rk = (T*)d.rk + (size_t)i * bbg::RKN;
-  T qfs, qas;
-  bbg::ctxLoad((const T*)d.ctx + (size_t)i * bbg::CTXN, S, ncon, nw, qfs, qas, L);
-  const T warm = L.gl < NV ? rk[bbg::RK_WARM + L.gl] : (T)0;
+  T qfs = 0, qas = 0, warm = 0;
+  if (act) {
+    bbg::ctxLoad((const T*)d.ctx + (size_t)i * bbg::CTXN, S, ncon, nw, qfs, qas, L);
+    warm = L.gl < NV ? rk[bbg::RK_WARM + L.gl] : (T)0;
+  }
+  __syncwarp();
   T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
-  bbg::GNewton<T> nwt(cmc<T>(), S, gs, L, ncon, nw, p.solver_mode != 0, qfs, qas);
+  bbg::Ln LU = L; LU.mask = 0xffffffffu;               // compile-time constant member mask for everything inlined below
+  bbg::GNewton<T, true> nwt(cmc<T>(), S, gs, LU, ncon, nw, p.solver_mode != 0, qfs, qas);
   int niter;
-  const T qacc = nwt.run(warm, niter);
+  const T qacc = nwt.run(warm, niter, act);
+  if (!act) return;
   if (L.gl < NV) {
     rk[bbg::RK_QACC + L.gl] = qacc;
     if (p.solver_mode != 0 && stage < 3) rk[bbg::RK_WARM + L.gl] = qacc;

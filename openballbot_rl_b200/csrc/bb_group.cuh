@@ -295,7 +295,7 @@ __device__ __forceinline__ T coneLane(const ModelConst<T>& mc, int k, T D0, cons
 template <typename T> struct LsPt { T alpha, cost, d1, d2, nxt; };
 template <typename T> struct LsCtx { T qG0, qG1, qG2; };
 template <typename T> struct Sum3 { T a, b, c; };
-template <typename T> __device__ __noinline__ Sum3<T> gsum3(T a, T b, T c, unsigned mask) {
+template <typename T> __device__ __forceinline__ Sum3<T> gsum3(T a, T b, T c, unsigned mask) {
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) { a += __shfl_xor_sync(mask, a, o); b += __shfl_xor_sync(mask, b, o); c += __shfl_xor_sync(mask, c, o); }
   Sum3<T> r; r.a = a; r.b = b; r.c = c; return r;
@@ -343,7 +343,12 @@ __device__ __forceinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, con
 }
 
 // ---------------------------------------------------------------------------------------------- group Newton solver
-template <typename T> struct GNewton {
+// U (uniform warp): both groups of the warp run every loop of the solver together -- a group whose solve has finished (or
+// that has no contacts) keeps executing as a passenger with its state frozen -- so every collective is reached by the whole
+// warp and L.mask can be the compile-time constant 0xffffffff (set by the caller; everything below is inlined).  That
+// removes the convergence pre-check (MATCH / REDUX / VOTE / branch) ptxas emits in front of every shuffle group with a
+// run-time member mask: ~5 % of the solver's instructions and ~12 % of its stall samples.
+template <typename T, bool U = false> struct GNewton {
   const ModelConst<T>& mc; GS<T>& S; T* gs; const Ln L; const int ncon, nw;
   const bool fast;   // fast solver mode: inexact line search (stop when |phi'| <= 1e-3 |phi'(0)|), same minimiser of the outer problem
   T qfs, qas;        // dof-lane registers
@@ -396,14 +401,15 @@ template <typename T> struct GNewton {
   // exact line search of mj_solNewton (PrimalSearch) as a state machine around a single evaluation site.  Evaluated
   // points live in S.lsp (slots of 4 words); the brackets p1 / p2 and their pending Newton points are slot indices, so
   // "p1 = candidate" is an integer move and the whole search needs a handful of registers.
-  __device__ __forceinline__ T lineSearch(T scale) {
+  __device__ __forceinline__ T lineSearch(T scale, bool on = true) {
     const bool dof = L.gl < NV;
     if (G == 16 || L.gl < 16) S.vb[0][L.gl] = dof ? search : (T)0;
     __syncwarp(L.mask);
     Mv = gSymv(S, S.vb[0], L.gi);
     const Sum3<T> r3 = gsum3(dof ? search * search : (T)0, dof ? search * (Ma - qfs) : (T)0, dof ? (T)0.5 * search * Mv : (T)0, L.mask);
     const T sn2 = r3.a;
-    if (sn2 < (T)1e-30) return 0;
+    if (U) on = on && !(sn2 < (T)1e-30);
+    else if (sn2 < (T)1e-30) return 0;
     T snorm, isn; sqrtInv(sn2, snorm, isn);
     T gtol = mc.tolerance * mc.ls_tolerance * snorm / scale;
     // jv = J search and the per-contact coefficients of the search (PrimalPrepare)
@@ -437,7 +443,9 @@ template <typename T> struct GNewton {
     const int maxit = mc.ls_iterations;
 #pragma unroll 1
     for (;;) {
+      if (U && !__any_sync(0xffffffffu, on)) break;      // both searches of the warp have finished
       const LsPt<T> p = lsEval(mc, S, gs, ncon, nw, q, a, dst, L);
+      if (U && !on) continue;                             // passenger: state frozen
       bool done = false;
       int src = -1;          // slot whose Newton step is evaluated next (-1: `a` has been set explicitly)
       if (st == 0) {
@@ -499,7 +507,7 @@ template <typename T> struct GNewton {
           }
         }
       }
-      if (done) break;
+      if (done) { if (U) { on = false; continue; } else break; }
       if (src >= 0) a = P[src * LSP_W + LSP_NXT];
       // next evaluation goes to a slot that none of the live points occupies (slot 0 = p0 stays)
       const unsigned live = 1u | (1u << i1) | (1u << i2) | (1u << i1n) | (1u << i2n) | (1u << imid) | (1u << ic0);
@@ -509,7 +517,7 @@ template <typename T> struct GNewton {
   }
 
   // in: aref parked in the jv slot of every record, `warm` = qacc_warmstart of this dof lane.  Returns qacc; niter by reference.
-  __device__ __forceinline__ T run(T warm, int& niter) {
+  __device__ __forceinline__ T run(T warm, int& niter, bool act = true) {
     const bool dof = L.gl < NV;
     // warm-start choice: total cost at qacc_warmstart (-> vb[0]) and at qacc_smooth (-> vb[1])
     if (G == 16 || L.gl < 16) { S.vb[0][L.gl] = dof ? warm : (T)0; S.vb[1][L.gl] = dof ? qas : (T)0; }
@@ -545,6 +553,29 @@ template <typename T> struct GNewton {
     const T scale = (T)1 / (mc.meaninertia * (T)NV);
     int iter = 0;
     costGrad();
+    if (U) {
+      bool on = act && iter < mc.iterations;
+#pragma unroll 1
+      while (__any_sync(0xffffffffu, on)) {
+        search = -gHessSolve(S, gs, ncon, nw, grad, L);
+        const T alpha = lineSearch(scale, on);
+        const bool step = on && alpha != 0;               // alpha == 0 ends the solve without touching the state
+        if (step) {
+          qacc += alpha * search; Ma += alpha * Mv;
+#pragma unroll 1
+          for (int c = L.gl; c < ncon; c += G) {
+            T* sc = crec(S, gs, c, nw) + (c < nw ? OSW : OSH);
+            sc[O_JAR] += alpha * sc[O_JV]; sc[O_JAR + 1] += alpha * sc[O_JV + 1]; sc[O_JAR + 2] += alpha * sc[O_JV + 2];
+          }
+        }
+        const T old = cost;
+        costGrad();                                       // idempotent for a group that did not step
+        if (step) iter++;
+        on = step && iter < mc.iterations && !(scale * (old - cost) < mc.tolerance || scale * bsqrt(gnorm2) < mc.tolerance);
+      }
+      niter = iter;
+      return qacc;
+    }
 #pragma unroll 1
     while (iter < mc.iterations) {
       search = -gHessSolve(S, gs, ncon, nw, grad, L);
