@@ -304,12 +304,13 @@ template <typename T> __device__ __forceinline__ Sum3<T> gsum3(T a, T b, T c, un
 // cost and derivatives of the 1-D line-search objective at alpha (PrimalEval); uniform over the group.  The point is
 // also parked in slot `slot` of S.lsp so that the search logic can refer to older points by index.
 template <typename T>
-__device__ __forceinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, const T* gs, int ncon, int nw, const LsCtx<T> q, T alpha, int slot, const Ln L) {
+__device__ __forceinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, const T* gs, int ncon, int nw, const LsCtx<T> q, T alpha, int slot, const Ln L,
+                                          const T* rec0) {
   T cost = 0, d1 = 0, d2 = 0;
 #pragma unroll 1
   for (int c = L.gl; c < ncon; c += G) {
     const bool wheel = c < nw;
-    const T* sc = crec(S, (T*)gs, c, nw) + (wheel ? OSW : OSH);
+    const T* sc = (c < G ? rec0 : (const T*)crec(S, (T*)gs, c, nw)) + (wheel ? OSW : OSH);
     const int k = wheel ? 0 : 1;
     const T mu = mc.mu[k];
     const typename V2T<T>::t l01 = ld2(sc + O_LS), l23 = ld2(sc + O_LS + 2), l4q = ld2(sc + O_LS + 4), lq = ld2(sc + O_LS + 6);
@@ -354,8 +355,10 @@ template <typename T, bool U = false> struct GNewton {
   T qfs, qas;        // dof-lane registers
   T qacc, Ma, grad, search, Mv;
   T cost, gauss, gnorm2;
+  T* rec0;           // record of the contact this lane owns in every per-contact loop (c = gl; loop-invariant for the whole solve)
   __device__ GNewton(const ModelConst<T>& m, GS<T>& s, T* g, const Ln l, int n, int w, bool f, T qf, T qa)
-      : mc(m), S(s), gs(g), L(l), ncon(n), nw(w), fast(f), qfs(qf), qas(qa) {}
+      : mc(m), S(s), gs(g), L(l), ncon(n), nw(w), fast(f), qfs(qf), qas(qa) { rec0 = crec(S, gs, L.gl, nw); }
+  __device__ __forceinline__ T* recOf(int c) const { return c < G ? rec0 : crec(S, gs, c, nw); }
 
   // forces / zones / cone Hessian blocks at the current jar (contact lanes), cost, gradient (dof lanes)
   __device__ __forceinline__ void costGrad() {
@@ -363,7 +366,7 @@ template <typename T, bool U = false> struct GNewton {
 #pragma unroll 1
     for (int c = L.gl; c < ncon; c += G) {
       const bool wheel = c < nw;
-      T* sc = crec(S, gs, c, nw) + (wheel ? OSW : OSH);
+      T* sc = recOf(c) + (wheel ? OSW : OSH);
       T h[6], f[3]; int st;
       const T jr[3] = {sc[O_JAR], sc[O_JAR + 1], sc[O_JAR + 2]};
       cpart += coneLane(mc, wheel ? 0 : 1, sc[O_D0], jr, f, h, st, true);
@@ -416,7 +419,7 @@ template <typename T, bool U = false> struct GNewton {
 #pragma unroll 1
     for (int c = L.gl; c < ncon; c += G) {
       const bool wheel = c < nw;
-      T* rec = crec(S, gs, c, nw);
+      T* rec = recOf(c);
       T* sc = rec + (wheel ? OSW : OSH);
       T w[3]; rowsDot(rec, wheel, S.vb[0], w);
       sc[O_JV] = w[0]; sc[O_JV + 1] = w[1]; sc[O_JV + 2] = w[2];
@@ -444,7 +447,7 @@ template <typename T, bool U = false> struct GNewton {
 #pragma unroll 1
     for (;;) {
       if (U && !__any_sync(0xffffffffu, on)) break;      // both searches of the warp have finished
-      const LsPt<T> p = lsEval(mc, S, gs, ncon, nw, q, a, dst, L);
+      const LsPt<T> p = lsEval(mc, S, gs, ncon, nw, q, a, dst, L, rec0);
       if (U && !on) continue;                             // passenger: state frozen
       bool done = false;
       int src = -1;          // slot whose Newton step is evaluated next (-1: `a` has been set explicitly)
@@ -527,7 +530,7 @@ template <typename T, bool U = false> struct GNewton {
 #pragma unroll 1
     for (int c = L.gl; c < ncon; c += G) {
       const bool wheel = c < nw;
-      T* rec = crec(S, gs, c, nw);
+      T* rec = recOf(c);
       T* sc = rec + (wheel ? OSW : OSH);
       T jw[3], js[3], f[3], h[6]; int st;
       rowsDot(rec, wheel, S.vb[0], jw); rowsDot(rec, wheel, S.vb[1], js);
@@ -545,7 +548,7 @@ template <typename T, bool U = false> struct GNewton {
       qacc = qas; Ma = qfs;
 #pragma unroll 1
       for (int c = L.gl; c < ncon; c += G) {
-        T* sc = crec(S, gs, c, nw) + (c < nw ? OSW : OSH);
+        T* sc = recOf(c) + (c < nw ? OSW : OSH);
         sc[O_JAR] = sc[O_LS]; sc[O_JAR + 1] = sc[O_LS + 1]; sc[O_JAR + 2] = sc[O_LS + 2];
       }
     } else { qacc = warm; Ma = mw; }
@@ -564,7 +567,7 @@ template <typename T, bool U = false> struct GNewton {
           qacc += alpha * search; Ma += alpha * Mv;
 #pragma unroll 1
           for (int c = L.gl; c < ncon; c += G) {
-            T* sc = crec(S, gs, c, nw) + (c < nw ? OSW : OSH);
+            T* sc = recOf(c) + (c < nw ? OSW : OSH);
             sc[O_JAR] += alpha * sc[O_JV]; sc[O_JAR + 1] += alpha * sc[O_JV + 1]; sc[O_JAR + 2] += alpha * sc[O_JV + 2];
           }
         }
@@ -584,7 +587,7 @@ template <typename T, bool U = false> struct GNewton {
       qacc += alpha * search; Ma += alpha * Mv;
 #pragma unroll 1
       for (int c = L.gl; c < ncon; c += G) {
-        T* sc = crec(S, gs, c, nw) + (c < nw ? OSW : OSH);
+        T* sc = recOf(c) + (c < nw ? OSW : OSH);
         sc[O_JAR] += alpha * sc[O_JV]; sc[O_JAR + 1] += alpha * sc[O_JV + 1]; sc[O_JAR + 2] += alpha * sc[O_JV + 2];
       }
       const T old = cost;
