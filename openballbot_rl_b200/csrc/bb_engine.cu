@@ -63,6 +63,7 @@ struct DevState {
   int* meta;       // int[N][4]       split-phase step: ncon, nw, Newton iterations, flags
   int* step_count; int* cam_steps; unsigned* episode; int* tseed;
   float* hfield;   // [N][HF_CELLS] (hf_per_env) or [HF_CELLS]
+  float* ptab;     // [2][293] circle coordinates of the tiled simplex noise (sin, cos) per grid index
   float* ep_ret; int* ep_len;
   int* counters;   // [0] reset-list length, [1] refresh-list length, [2] depth work-unit cursor
   int* reset_list; int* refresh_list;
@@ -497,7 +498,7 @@ __global__ void k_init_order(int N, DevState d) {
 
 // --------------------------------------------------------------------------------------------- simplex fBm terrain
 __constant__ unsigned char c_perm[256];
-__device__ __forceinline__ int dperm(int i) { return c_perm[i & 255]; }
+__device__ __forceinline__ int dperm(const int* __restrict__ perm, int i) { return perm[i & 255]; }   // perm: shared-memory copy of c_perm
 // All arithmetic below uses unfused round-to-nearest single-precision ops (__fmul_rn/__fadd_rn/__fsub_rn are never
 // contracted into FMAs): the tiled-noise coordinates are ~1e4 where one float ulp is 1e-3, so the heights are only
 // reproducible if every rounding step matches the plain C evaluation order of noise._simplex.
@@ -515,7 +516,7 @@ __device__ __forceinline__ float grad4(int gi, float x, float y, float z, float 
     default: return FA(FA(FM(s0, x), FM(s1, y)), FM(s2, z));
   }
 }
-__device__ float simplex4(float x, float y, float z, float w) {
+__device__ float simplex4(const int* __restrict__ perm, float x, float y, float z, float w) {
   const float F4 = 0.309016994f, G4 = 0.138196601f;
   const float sk = FM(FA(FA(FA(x, y), z), w), F4);
   const float fi = floorf(FA(x, sk)), fj = floorf(FA(y, sk)), fk = floorf(FA(z, sk)), fl = floorf(FA(w, sk));
@@ -535,54 +536,73 @@ __device__ float simplex4(float x, float y, float z, float w) {
     const float xc = FA(FS(x0, (float)i1), off), yc = FA(FS(y0, (float)j1), off), zc = FA(FS(z0, (float)k1), off), wc = FA(FS(w0, (float)l1), off);
     float tt = FS(FS(FS(FS(0.6f, FM(xc, xc)), FM(yc, yc)), FM(zc, zc)), FM(wc, wc));
     if (tt >= 0.f) {
-      const int gi = dperm(I + i1 + dperm(J + j1 + dperm(K + k1 + dperm(L + l1)))) & 31;
+      const int gi = dperm(perm, I + i1 + dperm(perm, J + j1 + dperm(perm, K + k1 + dperm(perm, L + l1)))) & 31;
       tt = FM(tt, tt);
       total = FA(total, FM(FM(tt, tt), grad4(gi, xc, yc, zc, wc)));
     }
   }
   return FM(27.f, total);
 }
-// snoise2(x, y, octaves, persistence, lacunarity, repeatx=1024, repeaty=1024, base=seed): tiled branch = 4-D fBm on two circles
-__device__ float perlinHeight(int i, int j, int seed, float scale, int oct, float pers, float lac, float amp) {
-  float x = (float)((double)i / (double)scale), y = (float)((double)j / (double)scale);
-  float z = (float)seed, w = z;
+// snoise2(x, y, octaves, persistence, lacunarity, repeatx=1024, repeaty=1024, base=seed): tiled branch = 4-D fBm on two circles.
+// The circle coordinates depend on the grid index only (not on the seed): perlinCircle(idx) = (sin, cos) * R of one axis.
+__device__ __forceinline__ void perlinCircle(int idx, float scale, float& s, float& c) {
+  const float x = (float)((double)idx / (double)scale);
   const float rr = (float)(1024.0 * 0.3183098861837907 * 0.5);
-  const float yf = (float)((double)y * 2.0 / 1024.0), xf = (float)((double)x * 2.0 / 1024.0);
-  y = FM(sinf(yf), rr); w = FA(w, FM(cosf(yf), rr));
-  x = FM(sinf(xf), rr); z = FA(z, FM(cosf(xf), rr));
-  float freq = 1.f, a = 1.f, mx = 1.f, total = simplex4(x, y, z, w);
+  const float xf = (float)((double)x * 2.0 / 1024.0);
+  s = FM(sinf(xf), rr); c = FM(cosf(xf), rr);
+}
+__device__ float perlinFbm(const int* __restrict__ perm, float si, float ci, float sj, float cj, int seed, int oct, float pers, float lac, float amp) {
+  const float x = si, y = sj, z = FA((float)seed, ci), w = FA((float)seed, cj);
+  float freq = 1.f, a = 1.f, mx = 1.f, total = simplex4(perm, x, y, z, w);
   for (int o = 1; o < oct; o++) {
     freq = FM(freq, lac); a = FM(a, pers); mx = FA(mx, a);
-    total = FA(total, FM(simplex4(FM(x, freq), FM(y, freq), FM(z, freq), FM(w, freq)), a));
+    total = FA(total, FM(simplex4(perm, FM(x, freq), FM(y, freq), FM(z, freq), FM(w, freq)), a));
   }
   const double v = ((double)__fdiv_rn(total, mx) + 1.0) / 2.0 * (double)amp;
   return (float)(v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v));
 }
+__device__ float perlinHeight(const int* __restrict__ perm, int i, int j, int seed, float scale, int oct, float pers, float lac, float amp) {
+  float si, ci, sj, cj;
+  perlinCircle(i, scale, si, ci); perlinCircle(j, scale, sj, cj);
+  return perlinFbm(perm, si, ci, sj, cj, seed, oct, pers, lac, amp);
+}
 #undef FM
 #undef FA
 #undef FS
+// circle coordinates of the 293 grid indices (engine constant: depends on perlin_scale only)
+__global__ void k_perlin_table(float scale, float* __restrict__ tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < HN) perlinCircle(i, scale, tab[i], tab[HN + i]);
+}
 // grid.x covers the cells of one heightfield, grid.y strides over the work list
 __global__ void __launch_bounds__(256) k_terrain(EnvParams p, DevState d, const int* __restrict__ list, const int* __restrict__ count,
                                                  int fixed_count, const int* __restrict__ seeds, float* __restrict__ out) {
+  __shared__ int perm[256];
+  perm[threadIdx.x] = c_perm[threadIdx.x];
+  __syncthreads();
   const int n = count ? *count : fixed_count;
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= HF_CELLS) return;
   const int r = cell / HN, c = cell - r * HN;
+  const float si = d.ptab[r], ci = d.ptab[HN + r], sj = d.ptab[c], cj = d.ptab[HN + c];
   for (int k = blockIdx.y; k < n; k += gridDim.y) {
     const int env = list ? list[k] : k;
     const int seed = seeds ? seeds[k] : d.tseed[env];
     float* dst = out ? out + (size_t)k * HF_CELLS : d.hfield + (size_t)env * HF_CELLS;
-    dst[cell] = perlinHeight(r, c, seed, p.pscale, p.poct, p.ppers, p.plac, p.pamp);
+    dst[cell] = perlinFbm(perm, si, ci, sj, cj, seed, p.poct, p.ppers, p.plac, p.pamp);
   }
 }
 
 // general n x n grid (registry callable `perlin`, terrain/perlin.py:8-74 at arbitrary n)
 __global__ void __launch_bounds__(256) k_perlin_grid(int n, float scale, int oct, float pers, float lac, float amp, const int* __restrict__ seeds,
                                                       int nseeds, float* __restrict__ out) {
+  __shared__ int perm[256];
+  perm[threadIdx.x] = c_perm[threadIdx.x];
+  __syncthreads();
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= n * n) return;
   const int r = cell / n, c = cell - r * n;
-  for (int k = blockIdx.y; k < nseeds; k += gridDim.y) out[(size_t)k * n * n + cell] = perlinHeight(r, c, seeds[k], scale, oct, pers, lac, amp);
+  for (int k = blockIdx.y; k < nseeds; k += gridDim.y) out[(size_t)k * n * n + cell] = perlinHeight(perm, r, c, seeds[k], scale, oct, pers, lac, amp);
 }
 
 // --------------------------------------------------------------------------------------------- reset
@@ -1042,6 +1062,8 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   const size_t hfbytes = sizeof(float) * HF_CELLS * (p.hf_per_env ? (size_t)N : 1);
   BB_CUDA_C(cudaMalloc(&d.hfield, hfbytes));
   BB_CUDA_C(cudaMemset(d.hfield, 0, hfbytes));
+  BB_CUDA_C(cudaMalloc(&d.ptab, sizeof(float) * 2 * HN));
+  k_perlin_table<<<blocksFor(HN, 128), 128>>>(cfg->perlin_scale, d.ptab);
   BB_CUDA_C(cudaMemset(d.st, 0, e->tsize * SST * N)); BB_CUDA_C(cudaMemset(d.camq, 0, e->tsize * CST * N));
   BB_CUDA_C(cudaMemset(d.step_count, 0, sizeof(int) * N)); BB_CUDA_C(cudaMemset(d.cam_steps, 0, sizeof(int) * N));
   BB_CUDA_C(cudaMemset(d.episode, 0, sizeof(unsigned) * N)); BB_CUDA_C(cudaMemset(d.tseed, 0, sizeof(int) * N));
@@ -1058,7 +1080,7 @@ int bb_destroy(bb_engine* e) {
   DevState& d = e->d;
   cudaFree(d.st); cudaFree(d.camq); cudaFree(d.gscr); cudaFree(d.rk); cudaFree(d.ctx); cudaFree(d.meta); cudaFree(d.step_count); cudaFree(d.cam_steps); cudaFree(d.episode); cudaFree(d.tseed);
   cudaFree(d.work); cudaFree(d.order); cudaFree(d.bins);
-  cudaFree(d.ep_ret); cudaFree(d.ep_len); cudaFree(d.counters); cudaFree(d.reset_list); cudaFree(d.refresh_list); cudaFree(d.hfield);
+  cudaFree(d.ep_ret); cudaFree(d.ep_len); cudaFree(d.counters); cudaFree(d.reset_list); cudaFree(d.refresh_list); cudaFree(d.hfield); cudaFree(d.ptab);
   if (e->prof_ev) { for (int i = 0; i < 5 * e->prof_cap; i++) cudaEventDestroy(e->prof_ev[i]); free(e->prof_ev); }
   if (e->host_ready) {
     cudaFreeHost(e->h_act); cudaFree(e->d_act); cudaFree(e->d_obs16); cudaFreeHost(e->h_obs16); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_pos2d);
