@@ -51,7 +51,8 @@ template <typename T> struct GS {
   T M[MSZ];
   T vb[2][16];          // vectors published by the dof lanes (broadcast reads)
   union {
-    T Lf[NV * LS_ + 1]; // Cholesky factor, Lf[j * 17 + i] = L(i, j) for i > j and 0 for i <= j (Newton solve)
+    T Lf[NV * LS_ + 3]; // Cholesky factor, Lf[j * 17 + i] = L(i, j) for i > j and 0 for i <= j (Newton solve); the last
+                        // pivot's (unused) trailing update reads up to index 256
     T geo[GE_N];        // geometry block of the smooth-dynamics pass (consumed by gCollide before the first factorisation)
   };
   T kin[16];            // quatB(4) cvel_ang(3) cvel_lin(3) posB(3) of the last evaluated stage

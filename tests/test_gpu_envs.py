@@ -240,3 +240,35 @@ def test_random_policy_statistics_on_engine_match_reference_records():
         assert n > 3 * N, (terrain, n)
         assert abs(ml - len_ref) < len_tol and abs(mr - ret_ref) < ret_tol, (terrain, ml, mr, n)
         eng.close()
+
+
+def test_bb_step_is_cuda_graph_capturable():
+    """bb_step neither allocates nor synchronises (include/ballbot_b200.h contract): a captured step replays to the same
+    trajectory as eager launches, with auto-reset, terrain regeneration and depth refresh inside the graph."""
+    from openballbot_rl_b200.engine import BallbotEngine
+    N = 200
+    kw = dict(num_envs=N, precision=64, terrain="perlin", cameras=True, seed=21, max_ep_steps=40)
+    e1, e2 = BallbotEngine(**kw), BallbotEngine(**kw)
+    e1.reset(); e2.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    acts = torch.rand(90, N, 3, device="cuda", generator=g) * 2 - 1
+    a_static = torch.zeros(N, 3, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                      # warm-up on the capture stream (lazy CUDA state), then capture one step
+        a_static.copy_(acts[0]); e1.step(a_static)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    a_static.copy_(acts[1])
+    with torch.cuda.graph(graph, stream=side):
+        e1.step(a_static)
+    e2.step(acts[0])
+    for t in range(1, 90):
+        a_static.copy_(acts[t]); graph.replay()
+        e2.step(acts[t])
+        assert torch.equal(e1.terminated, e2.terminated) and torch.equal(e1.reward, e2.reward), t
+    torch.cuda.synchronize()
+    (q1, v1, _), (q2, v2, _) = e1.get_state(), e2.get_state()
+    assert torch.equal(q1, q2) and torch.equal(v1, v2) and torch.equal(e1.obs["rgbd_1"], e2.obs["rgbd_1"])
+    assert int(e1.episode_length.max()) > 0            # resets happened inside the replayed graph
+    e1.close(); e2.close()
