@@ -201,16 +201,9 @@ def test_fixed_policy_episode_on_engine_matches_reference_eval(oracle_mod):
     N = 4
     venv = BallbotVecEnv(N, terrain_config={"type": "flat", "config": {}}, reward_config=REWARD, env_config=ENV_CFG, precision=64)
     venv.engine.cfg  # noqa: B018
-    obs = venv.reset()
-    ret = torch.zeros(N, device="cuda"); length = torch.zeros(N, dtype=torch.int32, device="cuda"); alive = torch.ones(N, dtype=torch.bool, device="cuda")
-    with torch.no_grad():
-        for t in range(600):
-            obs, rew, dones, info = venv.step(pol(obs))
-            ret += rew * alive; length += alive.int()
-            alive &= ~dones
-            if not bool(alive.any()):
-                break
-    L, G = length.cpu().numpy(), ret.cpu().numpy()
+    from openballbot_rl_b200.training.evaluate import evaluate_policy
+    out = evaluate_policy(venv, pol, max_steps=600, deterministic=True)
+    L, G = out["lengths"].cpu().numpy(), out["returns"].cpu().numpy()
     assert (L == L[0]).all()                                        # identical envs, deterministic policy
     assert abs(int(L[0]) - ref_len) <= 0.08 * ref_len, (L, ref_len)
     assert abs(float(G[0]) - ref_ret) <= 0.06 * ref_ret, (G, ref_ret)
