@@ -196,7 +196,7 @@ def test_fixed_policy_episode_on_engine_matches_reference_eval(oracle_mod):
     from openballbot_rl_b200.envs import BallbotVecEnv
     from openballbot_rl_b200.training.policy import BallbotPolicy
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policy_flat_10M.npz"))
-    pol = BallbotPolicy().load_sb3_state({k: z[k] for k in z.files if not k.startswith("eval_")}).eval().cuda()
+    pol = BallbotPolicy().load_sb3_state({k: z[k] for k in z.files if not k.startswith(("eval_", "train_"))}).eval().cuda()
     ref_ret, ref_len = float(z["eval_return"][0]), int(z["eval_length"][0])
     N = 4
     venv = BallbotVecEnv(N, terrain_config={"type": "flat", "config": {}}, reward_config=REWARD, env_config=ENV_CFG, precision=64)
@@ -265,3 +265,25 @@ def test_bb_step_is_cuda_graph_capturable():
     assert torch.equal(q1, q2) and torch.equal(v1, v2) and torch.equal(e1.obs["rgbd_1"], e2.obs["rgbd_1"])
     assert int(e1.episode_length.max()) > 0            # resets happened inside the replayed graph
     e1.close(); e2.close()
+
+
+def test_stochastic_policy_statistics_vs_reference_training_buffer():
+    """Closed loop under the archived policy's own action noise: the reference's Monitor buffer at the 10 M-step checkpoint
+    (last 100 training episodes, flat terrain: return 8.005 +- 0.712, length 318.7 +- 36.0; tests/golden/make_policy_fixture.py)
+    against first episodes of 512 engine envs driven by the same Gaussian policy.  Not like for like to the last digit -- the
+    buffer spans the final policy updates -- so the stated bound is 10 % on the means and 35 % on the spreads (measured:
+    339 +- 32 steps, 8.42 +- 0.63 return, i.e. +6 % / +5 %, the same sign and size as the deterministic episode's +2.4 % / +1.3 %)."""
+    import os
+    from openballbot_rl_b200.envs import BallbotVecEnv
+    from openballbot_rl_b200.training.evaluate import evaluate_policy
+    from openballbot_rl_b200.training.policy import BallbotPolicy
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policy_flat_10M.npz"))
+    pol = BallbotPolicy().load_sb3_state({k: z[k] for k in z.files if not k.startswith(("eval_", "train_"))}).eval().cuda()
+    ref_l, ref_r = z["train_ep_lengths"].astype(np.float64), z["train_ep_returns"]
+    venv = BallbotVecEnv(512, terrain_config={"type": "flat", "config": {}}, reward_config=REWARD, env_config=ENV_CFG, precision=64)
+    torch.manual_seed(0)
+    out = evaluate_policy(venv, pol, max_steps=700, deterministic=False)
+    L, G = out["lengths"].float().cpu().numpy(), out["returns"].cpu().numpy()
+    assert abs(L.mean() - ref_l.mean()) < 0.10 * ref_l.mean() and abs(G.mean() - ref_r.mean()) < 0.10 * ref_r.mean(), (L.mean(), G.mean())
+    assert abs(L.std() - ref_l.std()) < 0.35 * ref_l.std() and abs(G.std() - ref_r.std()) < 0.35 * ref_r.std(), (L.std(), G.std())
+    venv.close()

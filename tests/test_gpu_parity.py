@@ -180,3 +180,26 @@ def test_host_buffer_path_matches_device_path():
     np.testing.assert_array_equal(_obs16(e1), h["obs16"])
     np.testing.assert_array_equal(e1.reward.cpu().numpy(), h["reward"])
     e1.close(); e2.close()
+
+
+def test_depth_kernel_matches_reference_opengl_samples():
+    """The CUDA ray-cast against real depth images of the reference (see tests/test_oracle.py, same fixture and pose
+    reconstruction): median |depth difference| below 8 mm on every image."""
+    import os
+    from openballbot_rl_b200.engine import BallbotEngine
+    from tests.test_oracle import _reconstruct_poses
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_depth_samples.npz"))
+    n = len(z["orientation"])
+    eng = BallbotEngine(num_envs=n, precision=64, terrain="flat", cameras=True, auto_reset=False)
+    eng.reset()
+    for t in range(80):
+        eng.step(torch.zeros(n, 3, device="cuda"))
+    q_rest = eng.get_state()[0][0].cpu().numpy()
+    eng.set_state(qpos=np.stack(_reconstruct_poses(q_rest, z["orientation"])), qvel=np.zeros((n, 15)))
+    d0, d1 = eng.render_depth()
+    med = []
+    for i in range(n):
+        for img, key in ((d0, "rgbd_0"), (d1, "rgbd_1")):
+            med.append(float(np.median(np.abs(img[i, 0].cpu().numpy() - z[key][i].astype(np.float32)))))
+    assert max(med) < 0.008 and np.mean(med) < 0.005, med
+    eng.close()

@@ -150,7 +150,7 @@ def _policy():
     import torch
     from openballbot_rl_b200.training.policy import BallbotPolicy
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policy_flat_10M.npz"))
-    pol = BallbotPolicy().load_sb3_state({k: z[k] for k in z.files if not k.startswith("eval_")}).eval()
+    pol = BallbotPolicy().load_sb3_state({k: z[k] for k in z.files if not k.startswith(("eval_", "train_"))}).eval()
     return pol, float(z["eval_return"][0]), int(z["eval_length"][0])
 
 
@@ -177,3 +177,41 @@ def test_fixed_policy_episode_matches_reference_eval(oracle_mod):
     assert fail                                    # the recorded episode also ends by tilt, not by timeout
     assert abs(n - ref_len) <= 0.08 * ref_len, (n, ref_len)        # measured here: 387 vs 378
     assert abs(G - ref_ret) <= 0.06 * ref_ret, (G, ref_ret)        # measured here: 9.318 vs 9.1986
+
+
+def _reconstruct_poses(q_rest, rotvecs):
+    """Flat terrain: the base rotates about the ball body, which rests on the ground; pose from the recorded orientation."""
+    from scipy.spatial.transform import Rotation
+    pB, pL = q_rest[0:3].copy(), q_rest[10:13].copy()
+    out = []
+    for rv in rotvecs:
+        Rm = Rotation.from_rotvec(np.asarray(rv, np.float64))
+        q = np.array(q_rest, np.float64)
+        q[0:3] = pL + Rm.apply(pB - pL)
+        x, y, z, w = Rm.as_quat()
+        q[3:7] = [w, x, y, z]
+        out.append(q)
+    return out
+
+
+def test_depth_render_matches_reference_opengl_samples(oracle_mod):
+    """Golden vectors of the depth path: 4 x 2 real depth images of the reference (OpenGL renderer, flat terrain, archived
+    training checkpoints; tests/golden/make_depth_fixture.py) against the ray-cast at the pose reconstructed from the
+    recorded base orientation.  The reconstruction ignores the few millimetres the ball moves relative to the base while the
+    robot accelerates, so the bound is on the median: it pins camera placement, axes, fovy, planar-depth and clip conventions."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_depth_samples.npz"))
+    e = oracle_mod.OracleEnv(cameras=True)
+    e.reset()
+    for t in range(80):
+        e.step(np.zeros(3, np.float32))
+    q_rest = e.get_state()[0]
+    med = []
+    for i, q in enumerate(_reconstruct_poses(q_rest, z["orientation"])):
+        e.set_state(q, np.zeros(15)); e.forward()
+        for cam, key in ((0, "rgbd_0"), (1, "rgbd_1")):
+            ref = z[key][i].astype(np.float32)
+            d = e.render_depth(cam)
+            assert d.shape == ref.shape == (64, 64) and ref.max() <= 1.0 and d.max() <= 1.0
+            med.append(float(np.median(np.abs(d - ref))))
+    assert max(med) < 0.008 and np.mean(med) < 0.005, med          # metres
