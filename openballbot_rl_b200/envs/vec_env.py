@@ -77,6 +77,7 @@ class BallbotVecEnv:
         self.observation_space = create_observation_space({"h": im_h, "w": im_w}, 1, disable_cams)
         self.action_space = create_action_space()
         self._rng = np.random.default_rng(seed)       # terrain seeds of plugin terrains (ballbot_env.py:505-510)
+        self._terrain_cache = {}                      # host-generated plugin heightfields by seed
         self._actions = None
         self._t0 = time.time()
         self.last_terrain_seeds = np.zeros(self.num_envs, np.int64)
@@ -104,7 +105,11 @@ class BallbotVecEnv:
         for k, e in enumerate(env_ids):
             r_seed = cfg["seed"] if cfg.get("seed") is not None else int(self._rng.integers(0, 10000))
             self.last_terrain_seeds[e] = r_seed
-            fields[k] = np.asarray(self.terrain_gen(293, seed=r_seed), np.float32)
+            if r_seed not in self._terrain_cache:      # generators are pure functions of (config, seed)
+                if len(self._terrain_cache) >= 64:
+                    self._terrain_cache.clear()
+                self._terrain_cache[r_seed] = np.asarray(self.terrain_gen(293, seed=r_seed), np.float32).reshape(-1)
+            fields[k] = self._terrain_cache[r_seed]
         self.engine.set_hfield(env_ids.astype(np.int32), fields)
 
     # ------------------------------------------------------------------ VecEnv protocol
