@@ -376,6 +376,16 @@ k_stage(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io, in
   if (stage == 4) return;
   // ---- mj_forward up to the solver (CTA-synchronised phases)
   const float* hf = d.hfield + (p.hf_per_env ? (size_t)i * HF_CELLS : 0);
+  if (!skip && p.hf_per_env && L.gl < 8) {
+    // the ~7 x 7 heights under the ball are first touched by the collision phase, ~2 k instructions from here: start the
+    // DRAM/L2 fetch of the 8 row segments now (the ball moves less than a cell per stage, so the stage configuration is enough)
+    const T gsc = (T)(HN - 1) / ((T)2 * mc.hx);
+    int c0 = (int)((S.xq[10] - mc.ball_r + mc.hx) * gsc), r0 = (int)((S.xq[11] - mc.ball_r + mc.hx) * gsc) + L.gl;
+    c0 = c0 < 0 ? 0 : (c0 > HN - 8 ? HN - 8 : c0); r0 = r0 < 0 ? 0 : (r0 > HN - 1 ? HN - 1 : r0);
+    const float* row = hf + r0 * HN + c0;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 7));
+  }
   T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
   int nw; T qfs, qas;
   const int ncon = bbg::gForwardPre(mc, S, hf, (T)p.zscale, gs, L, stage == 3, nw, qfs, qas, skip, BB_WPB_STAGE > 1);
