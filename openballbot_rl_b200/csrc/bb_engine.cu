@@ -721,7 +721,7 @@ __device__ float hitHfield(F3 o, F3 dir, const float* __restrict__ hf, float sx,
         const float a = h10 - h00, b = h11 - h10;
         const float den = dz - a * dgx - b * dgy, num = c0 + a * u0 + b * v0;
         if (fabsf(den) > 1e-18f) {
-          const float t = num / den, u = u0 + t * dgx, v = v0 + t * dgy;
+          const float t = __fdividef(num, den), u = u0 + t * dgx, v = v0 + t * dgy;   // 2-ulp division: depth tolerance is 1e-3
           if (t > 0.f && v >= -e && u <= 1.f + e && u >= v - e) best = t;
         }
       }
@@ -729,14 +729,16 @@ __device__ float hitHfield(F3 o, F3 dir, const float* __restrict__ hf, float sx,
         const float a = h11 - h01, b = h01 - h00;
         const float den = dz - a * dgx - b * dgy, num = c0 + a * u0 + b * v0;
         if (fabsf(den) > 1e-18f) {
-          const float t = num / den, u = u0 + t * dgx, v = v0 + t * dgy;
+          const float t = __fdividef(num, den), u = u0 + t * dgx, v = v0 + t * dgy;   // 2-ulp division: depth tolerance is 1e-3
           if (t > 0.f && u >= -e && v <= 1.f + e && v >= u - e && (best < 0.f || t < best)) best = t;
         }
       }
       if (best > 0.f && best <= tmax) return best;
     }
     // next cell (indices are clamped: beyond the field edge tcur exceeds t1 and the loop ends)
-    if (xs) { cx = min(max(cx + stx, 0), n - 2); tmx += tdx; } else { cy = min(max(cy + sty, 0), n - 2); tmy += tdy; }
+    // (branch-free: neighbouring rays step along different axes)
+    cx = min(max(cx + (xs ? stx : 0), 0), n - 2); cy = min(max(cy + (xs ? 0 : sty), 0), n - 2);
+    tmx += xs ? tdx : 0.f; tmy += xs ? 0.f : tdy;
     tcur = tn;
   }
   return -1.f;
