@@ -652,7 +652,7 @@ struct Scene { F3 cam_o[2]; F3 cam_x[2], cam_y[2], cam_z[2]; Prim prim[7]; float
 __device__ __forceinline__ float hitSphere(F3 o, F3 dir, F3 c, float rad) {
   const F3 oc = o - c; const float a = fdot(dir, dir), b = fdot(oc, dir), cc = fdot(oc, oc) - rad * rad;
   const float disc = b * b - a * cc; if (disc < 0.f) return -1.f;
-  return (-b - sqrtf(disc)) / a;   // entry point only (back faces are culled by the rasteriser)
+  return __fdividef(-b - sqrtf(disc), a);   // entry point only (back faces are culled by the rasteriser); 2-ulp division, depth tolerance 1e-3
 }
 __device__ __forceinline__ float hitSide(F3 o, F3 dir, const Prim& p) {
   const F3 oc = o - p.c; const float od = fdot(oc, p.u), dd = fdot(dir, p.u);
@@ -660,7 +660,7 @@ __device__ __forceinline__ float hitSide(F3 o, F3 dir, const Prim& p) {
   const float a = fdot(dp, dp), b = fdot(op, dp), cc = fdot(op, op) - p.r * p.r;
   if (a < 1e-18f) return -1.f;
   const float disc = b * b - a * cc; if (disc < 0.f) return -1.f;
-  const float t = (-b - sqrtf(disc)) / a; const float zz = od + t * dd;
+  const float t = __fdividef(-b - sqrtf(disc), a); const float zz = od + t * dd;
   return (zz < -p.hl || zz > p.hl) ? -1.f : t;
 }
 __device__ float hitPrim(F3 o, F3 dir, const Prim& p) {
@@ -675,7 +675,7 @@ __device__ float hitPrim(F3 o, F3 dir, const Prim& p) {
     } else {
       const float od = fdot(oc, p.u), dd = fdot(dir, p.u);
       if (fabsf(dd) < 1e-18f || (float)s * dd >= 0.f) continue;
-      t = ((float)s * p.hl - od) / dd; if (t <= 0.f) continue;
+      t = __fdividef((float)s * p.hl - od, dd); if (t <= 0.f) continue;
       const F3 hp = oc + dir * t - p.u * ((float)s * p.hl);
       if (fdot(hp, hp) <= p.r * p.r && (best < 0.f || t < best)) best = t;
     }
