@@ -212,8 +212,13 @@ template <typename T>
 __device__ __forceinline__ void stepFinish(const EnvParams& p, const DevState& d, const float* __restrict__ actions, const bb_io& io, int i, bbg::GS<T>& S,
                                            const bbg::Ln& L, T warm, bool bad, int ncmax, int nit) {
   KinOut<T> kin;
+  const int nev = nit >> 12; nit &= 0xfff;
   int status = (ncmax << 8) | (nit << 16);   // bit 0: numerical failure, bits 8-15: max contacts of the stages, bits 16+: Newton iterations
-  const int key = bad ? 0 : (nit < WORK_BINS ? nit : WORK_BINS - 1);
+#ifndef BB_KEY_DIV
+#define BB_KEY_DIV 16
+#endif
+  const int kv = nev ? (nev + BB_KEY_DIV - 1) / BB_KEY_DIV : nit;            // split-phase path: line-search evaluations; fused path: iterations
+  const int key = bad ? 0 : (kv < WORK_BINS ? kv : WORK_BINS - 1);
   if (!bad) {
     bool b2 = (L.gl < NV && !(babs(S.xv[L.gl]) < (T)1e10));
     for (int k = L.gl; k < NQ; k += bbg::G) b2 |= !(babs(S.xq[k]) < (T)1e10);
@@ -443,7 +448,7 @@ __global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCK
     rk[bbg::RK_QACC + L.gl] = qacc;
     if (p.solver_mode != 0 && stage < 3) rk[bbg::RK_WARM + L.gl] = qacc;
   }
-  if (L.gl == 0) meta[bbg::META_NIT] += niter;
+  if (L.gl == 0) meta[bbg::META_NIT] += niter + (nwt.nevals << 12);   // low 12 bits: Newton iterations, above: line-search evaluations
 }
 // forward-dynamics probe through the group path (same outputs as k_probe)
 template <typename T> __global__ void k_probe_warp(EnvParams p, DevState d, int env, const double* ctrl3, double* out) {

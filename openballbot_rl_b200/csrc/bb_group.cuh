@@ -356,6 +356,7 @@ template <typename T, bool U = false> struct GNewton {
   T qfs, qas;        // dof-lane registers
   T qacc, Ma, grad, search, Mv;
   T cost, gauss, gnorm2;
+  int nevals = 0;    // line-search evaluations of this solve (work key of the scheduler)
   T* rec0;           // record of the contact this lane owns in every per-contact loop (c = gl; loop-invariant for the whole solve)
   __device__ GNewton(const ModelConst<T>& m, GS<T>& s, T* g, const Ln l, int n, int w, bool f, T qf, T qa)
       : mc(m), S(s), gs(g), L(l), ncon(n), nw(w), fast(f), qfs(qf), qas(qa) { rec0 = crec(S, gs, L.gl, nw); }
@@ -450,6 +451,7 @@ template <typename T, bool U = false> struct GNewton {
       if (U && !__any_sync(0xffffffffu, on)) break;      // both searches of the warp have finished
       const LsPt<T> p = lsEval(mc, S, gs, ncon, nw, q, a, dst, L, rec0);
       if (U && !on) continue;                             // passenger: state frozen
+      nevals++;
       bool done = false;
       int src = -1;          // slot whose Newton step is evaluated next (-1: `a` has been set explicitly)
       if (st == 0) {
