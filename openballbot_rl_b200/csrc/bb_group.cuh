@@ -579,9 +579,7 @@ template <typename T, bool U = false> struct GNewton {
         if (step) iter++;
         on = step && iter < mc.iterations && !(scale * (old - cost) < mc.tolerance || scale * bsqrt(gnorm2) < mc.tolerance);
       }
-      niter = iter;
-      return qacc;
-    }
+    } else {
 #pragma unroll 1
     while (iter < mc.iterations) {
       search = -gHessSolve(S, gs, ncon, nw, grad, L);
@@ -597,6 +595,7 @@ template <typename T, bool U = false> struct GNewton {
       costGrad();
       iter++;
       if (scale * (old - cost) < mc.tolerance || scale * bsqrt(gnorm2) < mc.tolerance) break;
+    }
     }
     niter = iter;
     return qacc;
