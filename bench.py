@@ -91,31 +91,64 @@ def cpu_arm(workload, seconds, procs):
 
 # ----------------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region.  NVML in-process (a query costs microseconds); spawning
+    `nvidia-smi` five times a second measurably perturbs the run, so it is only the fallback."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
     def __init__(self, gpu):
         super().__init__(daemon=True)
-        self.gpu, self.stop_flag, self.samples = gpu, False, []
+        self.gpu, self.stop_flag, self.samples = gpu, False, []     # samples: (sm_mhz, sm_max_mhz, reason bitmask)
+        self.recording = False                                      # samples are kept only inside the timed region
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[gpu]) if vis and vis.split(",")[gpu].isdigit() else gpu
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        return sm, mx, int(mask)
+
+    def _sample_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        f = [x.strip() for x in out.split(",")]
+        mask = sum(bit for (name, bit), v in zip(self.REASONS, f[2:6]) if v.lower().startswith("active"))
+        return int(f[0]), int(f[1]), mask
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                smp = self._sample_nvml() if self.nvml else self._sample_smi()
+                if self.recording:
+                    self.samples.append(smp)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1 if self.nvml else 1.0)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+        sm = sorted(s[0] for s in self.samples)
+        mask = 0
+        for s in self.samples:
+            mask |= s[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples),
+                "reasons": [name for name, bit in self.REASONS if mask & bit], "samples": len(self.samples),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------------- main
@@ -186,6 +219,11 @@ def main():
         torch.cuda.synchronize(dev)
 
     perlin = args.workload == "perlin"
+    # the sampler (NVML initialisation included) starts before the untimed pre-roll so that none of its start-up cost can fall
+    # into the timed region; it records only between the two timing events
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     eng = BallbotEngine(num_envs=envs, device=local_rank, precision=args.precision, terrain="perlin" if perlin else "flat",
                         cameras=perlin, auto_reset=True, seed=0, env_offset=rank * envs, solver=args.solver)
     gen = torch.Generator(device=dev); gen.manual_seed(rank)
@@ -198,19 +236,20 @@ def main():
     for t in range(warmup):
         eng.step(act[t % n_act])
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
     done_count = torch.zeros((), dtype=torch.int64, device=dev)
     launches0 = eng.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.recording = True
     ev0.record()
     for t in range(steps):
         eng.step(act[t % n_act])
         done_count += eng.terminated.sum()
     ev1.record()
     barrier()
+    if sampler:
+        sampler.recording = False
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count - launches0 + steps   # + the torch reduction kernel counting the resets
     # per-kernel breakdown (roofline): a second pass with CUDA events between the kernels of every step.  It is kept out of

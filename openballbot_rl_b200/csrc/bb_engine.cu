@@ -790,7 +790,10 @@ __device__ void buildScene(const ModelConst<float>& mc, const T* __restrict__ cq
 // builds the scene in its own shared-memory slot (9 lanes, one item each) and renders the unit's 8 x 4-pixel tiles
 // (neighbouring rays traverse similar cells => less divergence than row segments).  Consecutive units belong to the same
 // env, so the warps of a CTA share heightfield lines in L1/L2.
-constexpr int DEPTH_PARTS = 4;
+#ifndef BB_DEPTH_PARTS
+#define BB_DEPTH_PARTS 8
+#endif
+constexpr int DEPTH_PARTS = BB_DEPTH_PARTS;
 template <typename T>
 __global__ void __launch_bounds__(256) k_depth(EnvParams p, DevState d, const int* __restrict__ list, const int* __restrict__ count,
                                                int fixed_count, const T* __restrict__ cfgq, int cfg_stride, float* __restrict__ img0, float* __restrict__ img1) {
