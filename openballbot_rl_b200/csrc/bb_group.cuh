@@ -228,6 +228,60 @@ __device__ __forceinline__ T gHessSolve(GS<T>& S, const T* gs, int ncon, int nw,
   return x;
 }
 
+// x = M^-1 b for the block-diagonal mass matrix (qacc_smooth): the 9 x 9 base/wheel block on lanes 0..8 and the 6 x 6 ball
+// block on lanes 9..14 are factorised side by side with the same shifting-column scheme as gHessSolve, so the sequential
+// chain is 9 pivots instead of 15.  The arithmetic inside each block is the one the dense 15 x 15 factorisation performs
+// (its cross-block updates are exact zeros), so the result is bit-identical to gHessSolve(ncon = 0).
+template <typename T>
+__device__ __forceinline__ T gMassSolve(GS<T>& S, T b, const Ln L) {
+  const int gi = L.gi;
+  const bool top = gi < 9;
+  const int blk = top ? 0 : 9, nb = top ? 9 : 6, li = gi - blk;
+  T h[9];
+  {
+    const T* ma = S.M + (top ? gi : 0);
+    const T* mb = S.M + 81 + (top ? 0 : gi - 9);
+#pragma unroll
+    for (int k = 0; k < 6; k++) { const T va = ma[k * 9], vb = mb[k * 6]; h[k] = top ? va : vb; }
+#pragma unroll
+    for (int k = 6; k < 9; k++) { const T va = ma[k * 9]; h[k] = top ? va : (T)0; }
+  }
+  T myinv = 0, y = b;
+  T* Lf = S.Lf;
+#pragma unroll 1
+  for (int j = 0; j < 9; j++) {
+    const bool actv = j < nb;
+    const int src = actv ? blk + j : L.gl;
+    T piv = gget(h[0], src, L.mask);
+    piv = piv < (T)1e-15 ? (T)1e-15 : piv;
+    const T inv = brsqrt(piv);
+    const T l = h[0] * inv;
+    const bool mine = actv && li == j;
+    if (mine) myinv = inv;
+    const T yj = gget(y, src, L.mask) * inv;
+    if (mine) y = yj;
+    const bool below = actv && li > j;
+    const T lz = below ? l : (T)0;
+    if (below) y -= l * yj;                       // (predicated: a finished block's lanes see non-finite garbage pivots)
+    Lf[j * LS_ + L.gl] = lz;
+    __syncwarp(L.mask);
+    const T* cj = Lf + j * LS_ + blk + j + 1;
+#pragma unroll
+    for (int k = 0; k < 8; k++) h[k] = h[k + 1] - lz * cj[k];
+  }
+  T x = 0, s = 0;
+  const T* lrow = Lf + li * LS_ + blk;
+#pragma unroll 1
+  for (int i = 8; i >= 0; i--) {
+    const bool actv = i < nb;
+    const T cand = (y - s) * myinv;               // valid on the lane with local index i
+    const T xi = gget(cand, actv ? blk + i : L.gl, L.mask);
+    if (actv && li == i) x = xi;
+    if (actv) s += lrow[i] * xi;                  // L(blk + i, gi) for li < i, zero otherwise
+  }
+  return x;
+}
+
 // r[gi] = sum_k M(gi,k) v[k] for a published vector v (shared, 16 entries, v[15] finite)
 template <typename T> __device__ __forceinline__ T gSymv(const GS<T>& S, const T* v, int gi) {
   const bool top = gi < 9;
@@ -775,7 +829,7 @@ __device__ __forceinline__ int gForwardPre(const ModelConst<T>& mc, GS<T>& S, co
   if (cta_sync) __syncthreads();
   if (!skip) ncon = gCollide(mc, S, hf, zscale, gs, L, nw);   // consumes S.geo, which shares storage with the Cholesky factor
   if (cta_sync) __syncthreads();
-  if (!skip) qas = gHessSolve(S, gs, 0, 0, qfs, L);           // qacc_smooth = M^-1 qfrc_smooth
+  if (!skip) qas = gMassSolve(S, qfs, L);                     // qacc_smooth = M^-1 qfrc_smooth
   return ncon;
 }
 // in: S.xq, S.xv, S.ctrl, warm (dof-lane register)   out: returns qacc of this dof lane (and S.xq normalised).
