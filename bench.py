@@ -290,7 +290,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * envs * e2e_steps / float(te.item())
     h2d = envs * 3 * 4
-    d2h = envs * (16 * 4 + 4 + 1 + 1 + 8)
+    d2h = envs * (16 * 4 + 4 + 1 + 1 + 8 + 16 * 4 + 4 + 4)   # obs16, reward, terminated, failure, pos2d, terminal_obs, episode return / length
 
     if rank == 0:
         peak, peak_src = load_peaks()
