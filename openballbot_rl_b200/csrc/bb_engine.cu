@@ -316,8 +316,11 @@ __global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCK
 // k_stage<T>(stage): stage 0 loads the state; stages 1..3 fold the previous stage into the RK4 sums and advance the
 // stage state; every stage < 4 then runs mj_forward up to the solver and parks the solver input; stage 4 applies the RK4
 // update and finishes the step (observation, reward, termination, work lists).
+#ifndef BB_STAGE_MINBLOCKS
+#define BB_STAGE_MINBLOCKS (BB_WARP_MINBLOCKS * BB_WPB / BB_WPB_STAGE)
+#endif
 template <typename T>
-__global__ void __launch_bounds__(32 * BB_WPB_STAGE, (sizeof(T) == 4 ? BB_WARP_MINBLOCKS32 : BB_WARP_MINBLOCKS) * BB_WPB / BB_WPB_STAGE)
+__global__ void __launch_bounds__(32 * BB_WPB_STAGE, sizeof(T) == 4 ? BB_WARP_MINBLOCKS32 * BB_WPB / BB_WPB_STAGE : BB_STAGE_MINBLOCKS)
 k_stage(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io, int stage) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const bbg::Ln L = bbg::makeLn();

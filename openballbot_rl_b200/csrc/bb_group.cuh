@@ -40,7 +40,10 @@ constexpr int LS_ = 17;                     // row stride of the Cholesky factor
 constexpr int CRW = 74, CRH = 50;           // strides == 10 (mod 16): one-record-per-lane access is bank-conflict-free
 constexpr int OSW = 48, OSH = 24;
 constexpr int O_W = 0, O_FRC = 6, O_D0 = 9, O_JAR = 10, O_JV = 13, O_LS = 16;
-constexpr int NHS = 8;                      // terrain records resident in shared memory
+#ifndef BB_NHS
+#define BB_NHS 8
+#endif
+constexpr int NHS = BB_NHS;                 // terrain records resident in shared memory
 constexpr int GSCR = (MAXH - NHS) * CRH;    // per-env global overflow scratch (in T)
 // geometry block published by the smooth-dynamics pass
 constexpr int LSP_SLOTS = 8, LSP_W = 4, LSP_ALPHA = 0, LSP_COST = 1, LSP_D1 = 2, LSP_NXT = 3;   // line-search point slots
