@@ -49,3 +49,17 @@ def test_ppo_iteration_on_engine_with_embedding_cache():
     after = torch.cat([p.detach().reshape(-1) for p in L.params])
     assert info["n_updates"] > 0 and np.isfinite(info["value_loss"]) and not torch.equal(before, after)
     venv.close()
+
+
+def test_depth_frame_collection(tmp_path):
+    """Encoder pre-training data: fresh frames only (one in six steps per env + the reset frames), both cameras, sharded."""
+    from openballbot_rl_b200.training.collect import collect_depth_frames
+    from openballbot_rl_b200.training.utils import make_ballbot_vec_env
+    venv = make_ballbot_vec_env(32, terrain_config={"type": "perlin", "config": {}}, seed=1)
+    n = collect_depth_frames(venv, None, n_steps=24, out_dir=str(tmp_path), shard_frames=100)
+    files = sorted(p.name for p in tmp_path.iterdir())
+    frames = np.concatenate([np.load(tmp_path / f) for f in files])
+    assert n == frames.shape[0] == 2 * 32 * (1 + 24 // 6) and frames.shape[1:] == (64, 64) and frames.dtype == np.float16
+    assert files[0] == "depth_0000.npy" and len(files) == (n + 99) // 100
+    assert 0.0 < frames.min() and frames.max() <= 1.0
+    venv.close()
