@@ -29,7 +29,10 @@ typedef enum bb_status {
   BB_ERR_STATE = -4
 } bb_status;
 
-typedef enum bb_terrain { BB_TERRAIN_FLAT = 0, BB_TERRAIN_PERLIN = 1, BB_TERRAIN_EXTERNAL = 2 } bb_terrain;
+/* BB_TERRAIN_SHARED: one caller-provided heightfield for all envs (plugin terrains that do not depend on the per-reset seed,
+ * e.g. ramp / stairs / bowl with a fixed config): uploaded once with bb_set_hfield(env_ids = {0}, n = 1), auto-reset stays on
+ * the device like for BB_TERRAIN_FLAT. */
+typedef enum bb_terrain { BB_TERRAIN_FLAT = 0, BB_TERRAIN_PERLIN = 1, BB_TERRAIN_EXTERNAL = 2, BB_TERRAIN_SHARED = 3 } bb_terrain;
 typedef enum bb_reward { BB_REWARD_DIRECTIONAL = 0, BB_REWARD_DISTANCE = 1, BB_REWARD_EXTERNAL = 2 } bb_reward;
 
 /* Replaces the constructor arguments / YAML knobs of BBotSimulation.__init__ (ballbot_gym/envs/ballbot_env.py:157-231)
@@ -113,7 +116,8 @@ int bb_set_state(bb_engine* e, const double* qpos, const double* qvel, const dou
 int bb_get_state(bb_engine* e, double* qpos, double* qvel, double* warm, void* cuda_stream);
 
 /* replaces `model.hfield_data = terrain_gen(nrows, seed=r_seed)` (ballbot_env.py:513) for host-generated plugin
- * terrains: env_ids int32[n] (device), hfield float[n,293*293] (device). Only for BB_TERRAIN_EXTERNAL. */
+ * terrains: env_ids int32[n] (device), hfield float[n,293*293] (device). BB_TERRAIN_EXTERNAL (per env) or
+ * BB_TERRAIN_SHARED (n = 1, the single field every env uses). */
 int bb_set_hfield(bb_engine* e, const int32_t* env_ids_dev, int32_t n, const float* hfield_dev, void* cuda_stream);
 /* copies the heightfield of one env to a device buffer float[293*293] */
 int bb_get_hfield(bb_engine* e, int32_t env, float* hfield_dev, void* cuda_stream);

@@ -1018,7 +1018,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   if (!cfg || !out) { snprintf(g_create_error, sizeof(g_create_error), "bb_create: NULL argument"); return BB_ERR_INVALID; }
   *out = nullptr;
   if (cfg->abi_version != BB_ABI_VERSION || cfg->num_envs < 1 || (cfg->precision != 32 && cfg->precision != 64) || cfg->im_h < 1 || cfg->im_w < 1 ||
-      cfg->terrain_type < 0 || cfg->terrain_type > 2 || cfg->reward_type < 0 || cfg->reward_type > 2 || cfg->camera_frame_rate <= 0.f) {
+      cfg->terrain_type < 0 || cfg->terrain_type > 3 || cfg->reward_type < 0 || cfg->reward_type > 2 || cfg->camera_frame_rate <= 0.f) {
     snprintf(g_create_error, sizeof(g_create_error), "bb_create: invalid config (abi %d, num_envs %d, precision %d)", cfg->abi_version, cfg->num_envs, cfg->precision);
     return BB_ERR_INVALID;
   }
@@ -1054,7 +1054,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   p.reward_type = cfg->reward_type; p.reward_scale = cfg->reward_scale; p.action_reg = cfg->action_reg_coef; p.survival = cfg->survival_bonus;
   p.tdir[0] = cfg->target_direction[0]; p.tdir[1] = cfg->target_direction[1]; p.goal[0] = cfg->goal_position[0]; p.goal[1] = cfg->goal_position[1];
   p.dist_scale = cfg->distance_scale; p.zscale = cfg->hfield_zscale; p.terrain_type = cfg->terrain_type; p.terrain_seed = cfg->terrain_seed;
-  p.seed = cfg->seed; p.auto_reset = cfg->auto_reset; p.solver_mode = cfg->solver_mode; p.hf_per_env = cfg->terrain_type != BB_TERRAIN_FLAT;
+  p.seed = cfg->seed; p.auto_reset = cfg->auto_reset; p.solver_mode = cfg->solver_mode; p.hf_per_env = cfg->terrain_type == BB_TERRAIN_PERLIN || cfg->terrain_type == BB_TERRAIN_EXTERNAL;
   p.pscale = cfg->perlin_scale; p.ppers = cfg->perlin_persistence; p.plac = cfg->perlin_lacunarity; p.pamp = cfg->perlin_amplitude; p.poct = cfg->perlin_octaves;
   e->tsize = cfg->precision == 64 ? 8 : 4;
   DevState& d = e->d;
@@ -1202,6 +1202,12 @@ int bb_get_state(bb_engine* e, double* qpos, double* qvel, double* warm, void* s
 }
 int bb_set_hfield(bb_engine* e, const int32_t* ids, int32_t n, const float* hf, void* stream) {
   if (!e || !ids || !hf || n < 0) return BB_ERR_INVALID;
+  if (e->cfg.terrain_type == BB_TERRAIN_SHARED) {   // the one field shared by every env
+    if (n != 1) return fail(e, BB_ERR_INVALID, "bb_set_hfield: a shared-terrain engine takes exactly one heightfield");
+    BB_CUDA(cudaMemcpyAsync(e->d.hfield, hf, sizeof(float) * HF_CELLS, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    e->launches++;
+    return BB_OK;
+  }
   if (!e->p.hf_per_env) return fail(e, BB_ERR_INVALID, "bb_set_hfield: engine was created with flat terrain (no per-env heightfields)");
   if (n == 0) return BB_OK;
   const size_t tot = (size_t)n * HF_CELLS;

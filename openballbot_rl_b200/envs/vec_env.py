@@ -58,13 +58,23 @@ class BallbotVecEnv:
         self.terrain_gen = create_terrain(terrain_config)
         self._terrain_plugin = ttype not in BUILTIN_TERRAINS
         self._reward_plugin = rtype not in BUILTIN_REWARDS
-        self._manual_reset = self._terrain_plugin or self._reward_plugin
+        # A plugin terrain that does not depend on the per-reset seed (fixed `seed` in its config, or a generator that ignores
+        # it: ramp, stairs, bowl, ...) is the same heightfield at every reset of every env (ballbot_env.py:505-513 would
+        # regenerate an identical array): upload it once, share it, and keep auto-reset on the device.
+        self._terrain_shared = False
+        if self._terrain_plugin:
+            if tcfg.get("seed") is not None:
+                self._terrain_shared = True
+            else:
+                a, b = (np.asarray(self.terrain_gen(293, seed=sd), np.float32) for sd in (0, 1))
+                self._terrain_shared = bool(np.array_equal(a, b))
+        self._manual_reset = (self._terrain_plugin and not self._terrain_shared) or self._reward_plugin
         im_h, im_w = int(cam_s.get("height", 64)), int(cam_s.get("width", 64))
         if not cam_s.get("disable_rgb", True) and not disable_cams:
             raise NotImplementedError("RGB channels need the OpenGL rasteriser; the B200 engine provides depth only (camera.disable_rgb: true)")
         self.engine = BallbotEngine(
             num_envs=self.num_envs, device=device, precision=precision,
-            terrain="external" if self._terrain_plugin else ttype, terrain_seed=tcfg.get("seed"),
+            terrain=("shared" if self._terrain_shared else "external") if self._terrain_plugin else ttype, terrain_seed=tcfg.get("seed"),
             perlin={k: tcfg[k] for k in ("scale", "octaves", "persistence", "lacunarity", "amplitude") if k in tcfg},
             hfield_zscale=resolve_zscale(terrain_config), cameras=not disable_cams, im_h=im_h, im_w=im_w,
             camera_frame_rate=cam_s.get("frame_rate", 90), max_ep_steps=self.max_ep_steps,
@@ -114,7 +124,14 @@ class BallbotVecEnv:
 
     # ------------------------------------------------------------------ VecEnv protocol
     def reset(self):
-        if self._terrain_plugin:
+        if self._terrain_shared:
+            if not getattr(self, "_shared_uploaded", False):
+                cfg = self.terrain_config.get("config", {}) or {}
+                r_seed = cfg["seed"] if cfg.get("seed") is not None else 0
+                self.last_terrain_seeds[:] = r_seed
+                self.engine.set_hfield(np.zeros(1, np.int32), np.asarray(self.terrain_gen(293, seed=r_seed), np.float32).reshape(1, -1))
+                self._shared_uploaded = True
+        elif self._terrain_plugin:
             self._upload_plugin_terrain(np.arange(self.num_envs))
         self.engine.reset()
         return self._obs_view()
@@ -137,7 +154,7 @@ class BallbotVecEnv:
             done_mask = eng.terminated.clone()
             if bool(done_mask.any()):
                 term_obs = eng.terminal_obs.clone()
-                if self._terrain_plugin:
+                if self._terrain_plugin and not self._terrain_shared:
                     self._upload_plugin_terrain(torch.nonzero(done_mask).flatten().cpu().numpy())
                 rew, term, fail, pos = eng.reward.clone(), eng.terminated.clone(), eng.failure.clone(), eng.pos2d.clone()
                 eng.reset(done_mask)

@@ -287,3 +287,29 @@ def test_stochastic_policy_statistics_vs_reference_training_buffer():
     assert abs(L.mean() - ref_l.mean()) < 0.10 * ref_l.mean() and abs(G.mean() - ref_r.mean()) < 0.10 * ref_r.mean(), (L.mean(), G.mean())
     assert abs(L.std() - ref_l.std()) < 0.35 * ref_l.std() and abs(G.std() - ref_r.std()) < 0.35 * ref_r.std(), (L.std(), G.std())
     venv.close()
+
+
+def test_seed_independent_plugin_terrain_is_shared_and_auto_resets_on_device():
+    """Plugin terrains that ignore the per-reset seed (ramp, stairs, bowl, ... or any terrain with a fixed `seed`) are uploaded
+    once and shared by all envs (BB_TERRAIN_SHARED): same physics as the per-env upload path, resets handled by the engine."""
+    from openballbot_rl_b200.envs import BallbotVecEnv
+    from openballbot_rl_b200.terrain import shapes
+    cfg = {**ENV_CFG, "env": {**ENV_CFG["env"], "max_ep_steps": 30}}
+    tcfg = {"type": "ramp", "config": {"ramp_angle": 6.0}}
+    venv = BallbotVecEnv(6, terrain_config=tcfg, reward_config=REWARD, env_config=cfg, disable_cams=True, precision=64)
+    assert venv._terrain_shared and not venv._manual_reset
+    venv.reset()
+    hf = shapes.generate_ramp_terrain(293, ramp_angle=6.0).astype(np.float32)
+    np.testing.assert_array_equal(venv.engine.get_hfield(3).cpu().numpy(), hf.ravel())
+    rng = np.random.default_rng(0)
+    n_done = 0
+    for t in range(65):
+        a = rng.uniform(-1, 1, (6, 3)).astype(np.float32)
+        obs, rew, dones, info = venv.step(torch.from_numpy(a).cuda())
+        n_done += int(dones.sum())
+    assert n_done >= 12 and float(obs["orientation"].abs().max()) < 1.0        # two rounds of device-side auto-resets, envs alive
+    venv.close()
+    # hills draws its hill centres from the seed: per-env upload path, host-side resets
+    venv = BallbotVecEnv(2, terrain_config={"type": "hills", "config": {"num_hills": 3}}, reward_config=REWARD, env_config=cfg, disable_cams=True)
+    assert not venv._terrain_shared and venv._manual_reset
+    venv.close()
