@@ -524,15 +524,12 @@ __device__ __forceinline__ int dperm(const int* __restrict__ perm, int i) { retu
 #define FA(a, b) __fadd_rn((a), (b))
 #define FS(a, b) __fsub_rn((a), (b))
 __device__ __forceinline__ float grad4(int gi, float x, float y, float z, float w) {
-  // 32 gradient directions of 4-D simplex noise: one zero component (gi>>3 selects which), signs from the low bits
+  // 32 gradient directions of 4-D simplex noise: one zero component (gi>>3 selects which), signs from the low bits.
+  // Branch-free selection of the three participating coordinates (gi differs from lane to lane; a switch serialises).
   const int zc = gi >> 3;
   const float s0 = (gi & 4) ? -1.f : 1.f, s1 = (gi & 2) ? -1.f : 1.f, s2 = (gi & 1) ? -1.f : 1.f;
-  switch (zc) {
-    case 0: return FA(FA(FM(s0, y), FM(s1, z)), FM(s2, w));
-    case 1: return FA(FA(FM(s0, x), FM(s1, z)), FM(s2, w));
-    case 2: return FA(FA(FM(s0, x), FM(s1, y)), FM(s2, w));
-    default: return FA(FA(FM(s0, x), FM(s1, y)), FM(s2, z));
-  }
+  const float a = zc == 0 ? y : x, b = zc <= 1 ? z : y, c = zc <= 2 ? w : z;
+  return FA(FA(FM(s0, a), FM(s1, b)), FM(s2, c));
 }
 __device__ float simplex4(const int* __restrict__ perm, float x, float y, float z, float w) {
   const float F4 = 0.309016994f, G4 = 0.138196601f;
