@@ -193,10 +193,21 @@ __device__ __forceinline__ T gHessSolve(GS<T>& S, const T* gs, int ncon, int nw,
   // The trailing update touches the 14 - j live rows only up to the granularity of three loop bodies (14 / 9 / 4 rows).
   T myinv = 0, y = b;
   T* Lf = S.Lf;
+  // Pivot floor.  fp64: MuJoCo's absolute mjMINVAL.  fp32: the Hessian spans ~10 orders of magnitude (contact stiffness vs
+  // wheel inertia), so cancellation can leave a pivot tiny or negative; it is floored relative to the dof's own assembled
+  // diagonal entry (travels with the pivot in a second broadcast) instead of letting 1 / sqrt(pivot) explode.
+  T dfloor = (T)1e-15;
+  if (sizeof(T) == 4) {
+    T d0 = h[0];
+#pragma unroll
+    for (int k = 1; k < NV; k++) d0 = gi == k ? h[k] : d0;
+    dfloor = (T)1e-6 * d0;
+  }
 #define BB_PIVOT_STEP(NUPD)                                                                                               \
   {                                                                                                                       \
     T piv = gget(h[0], j, L.mask);                                                                                        \
-    piv = piv < (T)1e-15 ? (T)1e-15 : piv;                                                                                \
+    const T pfl = sizeof(T) == 4 ? gget(dfloor, j, L.mask) : (T)1e-15;                                                    \
+    piv = piv < pfl ? pfl : piv;                                                                                          \
     const T inv = brsqrt(piv);                                                                                            \
     const T l = h[0] * inv;                       /* lanes i >= j: L(i,j)  (lane j: sqrt(pivot)) */                      \
     if (gi == j) myinv = inv;                                                                                             \
