@@ -5,7 +5,9 @@ from openballbot_rl_b200.engine import BallbotEngine
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 3000
 prec = int(sys.argv[3]) if len(sys.argv) > 3 else 64
-eng = BallbotEngine(num_envs=N, precision=prec, terrain="perlin", cameras=True, seed=0)
+terrain = sys.argv[4] if len(sys.argv) > 4 else "perlin"
+solver = sys.argv[5] if len(sys.argv) > 5 else "exact"
+eng = BallbotEngine(num_envs=N, precision=prec, terrain=terrain, cameras=True, seed=0, solver=solver)
 eng.reset()
 g = torch.Generator(device="cuda"); g.manual_seed(0)
 act = torch.rand(64, N, 3, device="cuda", generator=g) * 2 - 1
