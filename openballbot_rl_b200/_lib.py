@@ -84,8 +84,11 @@ def lib():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise EngineError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                          "(nvcc, sm_100a). The ballbot engine has no CPU fallback.")
+        try:                                   # a fresh checkout: compile once if the toolchain is here, else fail loudly
+            build(force=True)
+        except Exception as exc:
+            raise EngineError(f"{LIB_PATH} not found and could not be built ({exc}): run `python -c 'import __graft_entry__ "
+                              "as g; g.build()'` (nvcc, sm_100a). The ballbot engine has no CPU fallback.") from exc
     L = C.CDLL(LIB_PATH)
     vp = C.c_void_p
     L.bb_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
