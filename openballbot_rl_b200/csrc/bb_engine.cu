@@ -1,13 +1,18 @@
 // bb_engine.cu -- CUDA kernels (sm_100a) and the C ABI (include/ballbot_b200.h) of the batched ballbot engine.
 //
-// Kernels (all fixed-grid, device-side work lists => no host sync inside bb_step, CUDA-graph capturable):
-//   k_step<T>      one thread per env: action map, RK4 mj_step equivalent (4 x forward dynamics with contact
-//                  generation and the elliptic-cone Newton solve), proprio obs, reward, termination, episode
-//                  statistics, work-list append for auto-reset and camera refresh        (ballbot_env.py:854-1036)
-//   k_terrain      simplex-fBm heightfield regeneration for the envs in the reset list    (terrain/perlin.py:8-74)
-//   k_reset<T>     spawn-height window max, state reset, reset observation                (ballbot_env.py:528-565,612-634)
-//   k_depth<T>     2 x HxW depth ray-cast per refreshing env (hfield DDA + analytic prims) (sensors/rgbd.py:46-82)
-// State is structure-of-arrays [field][env] so that a warp's loads/stores are fully coalesced.
+// Kernels (all fixed-grid, device-side work lists => no host sync or allocation inside bb_step, CUDA-graph capturable):
+//   k_begin_step, k_order   counting sort of the envs by the solver work of their previous step (scheduling only)
+//   k_stage<T>(s) x5        split-phase step, one 16-lane group per env: fold RK stage s-1, advance the stage state, smooth
+//                           dynamics, contact generation + constraint rows, qacc_smooth; s = 0 loads the state and maps the
+//                           action, s = 4 applies the RK4 update and writes proprio obs, reward, termination, episode
+//                           statistics and the reset / refresh work lists                  (ballbot_env.py:854-1036)
+//   k_newton<T>(s) x4       elliptic-cone Newton solve of RK stage s for the envs that have contacts (mj_fwdConstraint)
+//   k_step_warp<T>          the same arithmetic fused into one launch (step_kernel = 2, cross-check)
+//   k_step<T>               one thread per env (step_kernel = 1, cross-check; shares bb_core.cuh with the CPU test harness)
+//   k_terrain               simplex-fBm heightfield regeneration for the envs in the reset list    (terrain/perlin.py:8-74)
+//   k_reset<T>              spawn-height window max, state reset, reset observation       (ballbot_env.py:528-565,612-634)
+//   k_depth<T>              2 x HxW depth ray-cast per refreshing env (hfield DDA + analytic prims) (sensors/rgbd.py:46-82)
+// State is one record per env (qpos17 qvel15 qacc_warmstart15, stride 48) that a 16-lane group loads / stores coalesced.
 #include <cuda_runtime.h>
 
 #include <cstdio>
