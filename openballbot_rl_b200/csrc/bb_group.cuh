@@ -9,16 +9,19 @@
 // Layout of the solver (mj_fwdConstraint / mj_solNewton semantics, reference call ballbot_env.py:912):
 //   * lane i < 15 of a group owns dof i: qfrc_smooth, qacc_smooth, qacc, M qacc, gradient, search direction and the
 //     RK4 accumulators are ONE register each per lane;
-//   * the mass matrix is a full symmetric 15 x 16 array in shared memory (lane i reads column i with unit stride);
+//   * the block-diagonal mass matrix (9 x 9 base/wheels + 6 x 6 ball) sits in shared memory, both triangles stored;
 //   * the Hessian H = M + sum_c J_c' W_c J_c is assembled with column i in the registers of lane i and factorised in
-//     place (right-looking Cholesky: per column one shuffle for the pivot, one rsqrt, the scaled column is exchanged
-//     through a 16-word shared buffer); forward substitution is fused into the factorisation, the backward
-//     substitution needs one shuffle per dof;
+//     place by a rolled right-looking Cholesky: per pivot one broadcast, one rsqrt, the scaled column goes to the
+//     shared factor array (row stride 17), and every lane shifts its column up by one inside the update FMA so that the
+//     pivot row is always register 0; forward substitution is fused, backward substitution reads the lane's own row;
 //   * contact c is owned by lane c % G for the per-contact scalar work (cone zones, line-search coefficients);
 //     its record (3 Jacobian rows + 24 scalars) lives in shared memory (3 wheel + 9 terrain records) and spills to a
 //     global scratch beyond that (deep impacts only);
 //   * the exact line search is a state machine around ONE evaluation call site, so two environments that are in
-//     different phases of their searches still share every evaluation instruction.
+//     different phases of their searches still share every evaluation instruction; evaluated points live in
+//     shared-memory slots and the brackets are slot indices;
+//   * GNewton<T, true> (k_newton) is the uniform-warp variant: both groups run every loop together, a finished group
+//     rides along with its state frozen, and all collectives use the compile-time full-warp mask.
 // The arithmetic restates the same algorithm as bb_core.cuh (thread-per-env cross-check and CPU test harness); only
 // summation orders and the rsqrt-based square roots differ.
 #pragma once
