@@ -15,7 +15,7 @@
 //     shared factor array (row stride 17), and every lane shifts its column up by one inside the update FMA so that the
 //     pivot row is always register 0; forward substitution is fused, backward substitution reads the lane's own row;
 //   * contact c is owned by lane c % G for the per-contact scalar work (cone zones, line-search coefficients);
-//     its record (3 Jacobian rows + 24 scalars) lives in shared memory (3 wheel + 9 terrain records) and spills to a
+//     its record (3 Jacobian rows + 24 scalars) lives in shared memory (3 wheel + 8 terrain records) and spills to a
 //     global scratch beyond that (deep impacts only);
 //   * the exact line search is a state machine around ONE evaluation call site, so two environments that are in
 //     different phases of their searches still share every evaluation instruction; evaluated points live in
