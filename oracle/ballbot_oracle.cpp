@@ -499,6 +499,119 @@ int spherePrism(const R* c, R r, const R* a, const R* b, const R* c3, R* dist, R
   return 1;
 }
 
+
+// ---- additional geom pairs (ballbot.xml:41-69: every geom but `ballast` has contype = conaffinity = 1)
+// closest points of segments p1-q1 and p2-q2 (Ericson, Real-Time Collision Detection 5.1.9)
+R closestSegSeg(const R* p1, const R* q1, const R* p2, const R* q2, R* c1, R* c2) {
+  R d1[3], d2[3], r[3];
+  for (int k = 0; k < 3; k++) { d1[k] = q1[k] - p1[k]; d2[k] = q2[k] - p2[k]; r[k] = p1[k] - p2[k]; }
+  R a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r), s, t;
+  if (a <= MINVAL && e <= MINVAL) { s = t = 0; }
+  else if (a <= MINVAL) { s = 0; t = f / e; t = t < 0 ? 0 : (t > 1 ? 1 : t); }
+  else {
+    R c = dot3(d1, r);
+    if (e <= MINVAL) { t = 0; s = -c / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+    else {
+      R b = dot3(d1, d2), den = a * e - b * b;
+      s = den > MINVAL ? (b * f - c * e) / den : 0; s = s < 0 ? 0 : (s > 1 ? 1 : s);
+      t = (b * s + f) / e;
+      if (t < 0) { t = 0; s = -c / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+      else if (t > 1) { t = 1; s = (b - c) / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+    }
+  }
+  for (int k = 0; k < 3; k++) { c1[k] = p1[k] + d1[k] * s; c2[k] = p2[k] + d2[k] * t; }
+  R dv[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
+  return dot3(dv, dv);
+}
+// closest points between the segment p0-p1 and the triangle abc: ps on the segment, pt on the triangle; returns squared distance.
+// Candidates in a fixed order (segment end points vs the triangle, then the segment vs the three edges); first minimum wins.
+R closestSegTriangle(const R* p0, const R* p1, const R* a, const R* b, const R* c, R* ps, R* pt) {
+  R best = 1e300, q[3], s1[3], s2[3];
+  const R* ends[2] = {p0, p1};
+  for (int i = 0; i < 2; i++) {
+    closestPtTriangle(q, ends[i], a, b, c);
+    R dv[3] = {ends[i][0] - q[0], ends[i][1] - q[1], ends[i][2] - q[2]}, d2 = dot3(dv, dv);
+    if (d2 < best) { best = d2; v3cp(ps, ends[i]); v3cp(pt, q); }
+  }
+  const R* ed[3][2] = {{a, b}, {b, c}, {c, a}};
+  for (int i = 0; i < 3; i++) {
+    R d2 = closestSegSeg(p0, p1, ed[i][0], ed[i][1], s1, s2);
+    if (d2 < best) { best = d2; v3cp(ps, s1); v3cp(pt, s2); }
+  }
+  return best;
+}
+// capsule (segment p0-p1, radius r) against the prism under the top triangle (a,b,c3); same conventions as spherePrism:
+// exact closest feature of the top surface patch; a segment point under the top plane only counts inside the prism's column.
+int capsulePrism(const R* p0, const R* p1, R r, const R* a, const R* b, const R* c3, R* dist, R* nrm, R* pos) {
+  R e1[3], e2[3], n[3];
+  for (int k = 0; k < 3; k++) { e1[k] = b[k] - a[k]; e2[k] = c3[k] - a[k]; }
+  cross3(n, e1, e2); if (n[2] < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+  normalize3(n);
+  R ps[3], pt[3];
+  closestSegTriangle(p0, p1, a, b, c3, ps, pt);
+  // lowest segment point relative to the top plane
+  R h0 = (p0[0] - a[0]) * n[0] + (p0[1] - a[1]) * n[1] + (p0[2] - a[2]) * n[2];
+  R h1 = (p1[0] - a[0]) * n[0] + (p1[1] - a[1]) * n[1] + (p1[2] - a[2]) * n[2];
+  const R* pl = h0 <= h1 ? p0 : p1; R hl = h0 <= h1 ? h0 : h1;
+  if (hl < 0) {   // the segment dips under the top plane: deep contact at its lowest end, only inside this prism's column
+    R ap[3] = {pl[0] - a[0], pl[1] - a[1], pl[2] - a[2]};
+    R u = (e1[0] * e2[1] - e1[1] * e2[0]);
+    R s = (ap[0] * e2[1] - ap[1] * e2[0]) / u, t = (e1[0] * ap[1] - e1[1] * ap[0]) / u;
+    if (!(s < 0 || t < 0 || s + t > 1)) {
+      *dist = hl - r; v3cp(nrm, n);
+      for (int k = 0; k < 3; k++) pos[k] = pl[k] - n[k] * (r + 0.5 * (*dist));
+      return 1;
+    }
+    R hs = (ps[0] - a[0]) * n[0] + (ps[1] - a[1]) * n[1] + (ps[2] - a[2]) * n[2];
+    if (hs < 0) return 0;   // closest feature reached from below the plane: handled by the neighbouring prism
+  }
+  R dv[3] = {ps[0] - pt[0], ps[1] - pt[1], ps[2] - pt[2]}, dl = norm3(dv);
+  if (dl >= r || dl < MINVAL) return 0;
+  *dist = dl - r;
+  for (int k = 0; k < 3; k++) nrm[k] = dv[k] / dl;
+  for (int k = 0; k < 3; k++) pos[k] = pt[k] + nrm[k] * 0.5 * (*dist);
+  return 1;
+}
+void geomWorld(const Data& d, const Geom& g, R* c, R* axis) {
+  R t[3], gm[9];
+  mulMatVec3(t, d.xmat[g.body], g.pos); for (int k = 0; k < 3; k++) c[k] = d.xpos[g.body][k] + t[k];
+  mulMat3(gm, d.xmat[g.body], g.mat); v3set(axis, gm[2], gm[5], gm[8]);
+}
+// capsule geom vs the heightfield: sub-grid of the capsule's AABB, prisms in the scan order of the ball pair
+void capsuleHfield(const Model& m, Data& d, const Geom& g, int pairId) {
+  const R sx = m.hf_size[0], sy = m.hf_size[1], sz = m.hf_size[2], sb = m.hf_size[3];
+  const int nrow = HN, ncol = HN; const float* data = d.hfield.data();
+  R cc[3], ax[3]; geomWorld(d, g, cc, ax);
+  const R rad = g.size[0], len = g.size[1];
+  R p0[3], p1[3]; for (int k = 0; k < 3; k++) { p0[k] = cc[k] - ax[k] * len; p1[k] = cc[k] + ax[k] * len; }
+  R lo[3], hi[3]; for (int k = 0; k < 3; k++) { lo[k] = std::fmin(p0[k], p1[k]) - rad; hi[k] = std::fmax(p0[k], p1[k]) + rad; }
+  if (sx < lo[0] || -sx > hi[0] || sy < lo[1] || -sy > hi[1] || sz < lo[2] || -sb > hi[2]) return;
+  int cmin = (int)std::floor((lo[0] + sx) / (2 * sx) * (ncol - 1)), cmax = (int)std::ceil((hi[0] + sx) / (2 * sx) * (ncol - 1));
+  int rmin = (int)std::floor((lo[1] + sy) / (2 * sy) * (nrow - 1)), rmax = (int)std::ceil((hi[1] + sy) / (2 * sy) * (nrow - 1));
+  if (cmin < 0) cmin = 0; if (rmin < 0) rmin = 0; if (cmax > ncol - 1) cmax = ncol - 1; if (rmax > nrow - 1) rmax = nrow - 1;
+  const R dx = 2 * sx / (ncol - 1), dy = 2 * sy / (nrow - 1), zmin = lo[2];
+  int cnt = 0; const int dr[2] = {1, 0};
+  for (int r = rmin; r < rmax && cnt < 50; r++) {
+    R v[3][3] = {{0}}; int nvert = 0;
+    for (int c = cmin; c <= cmax && cnt < 50; c++)
+      for (int k = 0; k < 2 && cnt < 50; k++) {
+        v3cp(v[0], v[1]); v3cp(v[1], v[2]);
+        v3set(v[2], dx * c - sx, dy * (r + dr[k]) - sy, (R)data[(r + dr[k]) * ncol + c] * sz);
+        if (++nvert < 3) continue;
+        if (v[0][2] < zmin && v[1][2] < zmin && v[2][2] < zmin) continue;
+        R dist, nrm[3], pos[3];
+        if (!capsulePrism(p0, p1, rad, v[0], v[1], v[2], &dist, nrm, pos)) continue;
+        if (d.ncon >= MAXCON) continue;
+        Contact& cn = d.con[d.ncon++];
+        memset(&cn, 0, sizeof(cn));
+        cn.dist = dist; v3cp(cn.pos, pos); v3cp(cn.frame, nrm); makeFrame(cn.frame);
+        cn.body1 = 0; cn.body2 = g.body; cn.pair = pairId; v3cp(cn.friction, m.fric_hfield);
+        cnt++;
+      }
+  }
+}
+
+int g_extra_pairs = 1;
 void collision(const Model& m, Data& d) {
   d.ncon = 0;
   // ball sphere world pose
@@ -562,6 +675,61 @@ void collision(const Model& m, Data& d) {
             cnt++;
           }
       }
+    }
+  }
+  if (!g_extra_pairs) return;
+  // --- dynamic pairs of the other colliding geoms (friction = element-wise max of the geom defaults, condim 3):
+  // world heightfield x {wheel capsules, camera-stick capsules}; ball x {camera sticks (patched sphere-capsule), tower cylinder}.
+  // Filtered by MuJoCo: same weld body (base/cam geoms among themselves), parent-child (base/cam x wheels). Wheel x wheel
+  // capsules are ~0.09 m apart for every hinge angle; tower x heightfield and the cone meshes are not modelled (ORACLE_ASSUMPTIONS).
+  for (int i = 0; i < 2; i++) capsuleHfield(m, d, m.stick[i], 5 + i);
+  for (int i = 0; i < 3; i++) capsuleHfield(m, d, m.wheel[i], 7 + i);
+  for (int i = 0; i < 2; i++) {   // ball x stick: mjraw_SphereCapsule with the patched frame
+    const Geom& g = m.stick[i]; R cc[3], axis[3]; geomWorld(d, g, cc, axis);
+    R vec[3] = {bc[0] - cc[0], bc[1] - cc[1], bc[2] - cc[2]};
+    R x = dot3(axis, vec), len = g.size[1];
+    if (x > len) x = len; if (x < -len) x = -len;
+    R dif[3] = {cc[0] + axis[0] * x - bc[0], cc[1] + axis[1] * x - bc[1], cc[2] + axis[2] * x - bc[2]};
+    R cd = norm3(dif), mind = br + g.size[0];
+    if (cd > mind || d.ncon >= MAXCON) continue;
+    Contact& c = d.con[d.ncon++];
+    memset(&c, 0, sizeof(c));
+    for (int k = 0; k < 3; k++) c.frame[k] = dif[k] / cd;
+    c.dist = cd - mind;
+    for (int k = 0; k < 3; k++) c.pos[k] = bc[k] + c.frame[k] * (br + 0.5 * c.dist);
+    v3cp(c.frame + 3, axis); makeFrame(c.frame);
+    c.body1 = 7; c.body2 = g.body; c.pair = 11 + i; v3cp(c.friction, m.fric_hfield);
+  }
+  {   // ball x tower: mjraw_SphereCylinder (side / cap / corner)
+    const Geom& g = m.tower; R cc[3], axis[3]; geomWorld(d, g, cc, axis);
+    R vec[3] = {bc[0] - cc[0], bc[1] - cc[1], bc[2] - cc[2]};
+    R x = dot3(vec, axis), pp[3] = {vec[0] - axis[0] * x, vec[1] - axis[1] * x, vec[2] - axis[2] * x}, pp2 = dot3(pp, pp);
+    R rad = g.size[0], hgt = g.size[1];
+    bool side = std::fabs(x) < hgt, cap = pp2 < rad * rad;
+    if (side && cap) { if (hgt - std::fabs(x) < rad - std::sqrt(pp2)) side = false; else cap = false; }
+    R tgt[3], trad; bool hit = false; R nrm[3], dist = 0;
+    if (side) { for (int k = 0; k < 3; k++) tgt[k] = cc[k] + axis[k] * x; trad = rad; }
+    else if (cap) {   // plane of the nearer cap against the sphere
+      R sg = x > 0 ? 1 : -1, pc[3]; for (int k = 0; k < 3; k++) pc[k] = cc[k] + sg * hgt * axis[k];
+      R dd = sg * ((bc[0] - pc[0]) * axis[0] + (bc[1] - pc[1]) * axis[1] + (bc[2] - pc[2]) * axis[2]) - br;
+      if (dd < 0 && d.ncon < MAXCON) { hit = true; dist = dd; for (int k = 0; k < 3; k++) nrm[k] = -sg * axis[k]; }
+      trad = -1;
+    } else {
+      R pn = std::sqrt(pp2), sg = x > 0 ? 1 : -1;
+      for (int k = 0; k < 3; k++) tgt[k] = cc[k] + pp[k] / pn * rad + sg * hgt * axis[k];
+      trad = 0;
+    }
+    if (trad >= 0) {
+      R dif[3] = {tgt[0] - bc[0], tgt[1] - bc[1], tgt[2] - bc[2]}, cd = norm3(dif);
+      if (cd < br + trad && cd > MINVAL && d.ncon < MAXCON) { hit = true; dist = cd - br - trad; for (int k = 0; k < 3; k++) nrm[k] = dif[k] / cd; }
+    }
+    if (hit) {
+      Contact& c = d.con[d.ncon++];
+      memset(&c, 0, sizeof(c));
+      c.dist = dist; v3cp(c.frame, nrm);
+      for (int k = 0; k < 3; k++) c.pos[k] = bc[k] + nrm[k] * (br + 0.5 * dist);
+      makeFrame(c.frame);
+      c.body1 = 7; c.body2 = g.body; c.pair = 10; v3cp(c.friction, m.fric_hfield);
     }
   }
 }
@@ -945,6 +1113,25 @@ float noise4(float x, float y, float z, float w) {
   }
   return 27.0f * total;
 }
+
+// 2-D simplex noise of noise._simplex (untiled branch of snoise2: terrain/gradient.py:74-80)  [3P-memory]
+const float GRAD3[12][3] = {{1, 1, 0}, {-1, 1, 0}, {1, -1, 0}, {-1, -1, 0}, {1, 0, 1}, {-1, 0, 1}, {1, 0, -1}, {-1, 0, -1}, {0, 1, 1}, {0, -1, 1}, {0, 1, -1}, {0, -1, -1}};
+float noise2(float x, float y) {
+  const float F2 = 0.3660254037844386f, G2 = 0.21132486540518713f;
+  float s = (x + y) * F2, i = floorf(x + s), j = floorf(y + s), t = (i + j) * G2;
+  float xx[3], yy[3], n[3] = {0.f, 0.f, 0.f};
+  xx[0] = x - (i - t); yy[0] = y - (j - t);
+  int i1 = xx[0] > yy[0], j1 = xx[0] <= yy[0];
+  xx[2] = xx[0] + G2 * 2.0f - 1.0f; yy[2] = yy[0] + G2 * 2.0f - 1.0f;
+  xx[1] = xx[0] - i1 + G2; yy[1] = yy[0] - j1 + G2;
+  int I = (int)i & 255, J = (int)j & 255;
+  int g[3] = {perm(I + perm(J)) % 12, perm(I + i1 + perm(J + j1)) % 12, perm(I + 1 + perm(J + 1)) % 12};
+  for (int c = 0; c < 3; c++) {
+    float f = 0.5f - xx[c] * xx[c] - yy[c] * yy[c];
+    if (f > 0) n[c] = f * f * f * f * (GRAD3[g[c]][0] * xx[c] + GRAD3[g[c]][1] * yy[c]);
+  }
+  return (n[0] + n[1] + n[2]) * 70.0f;
+}
 float fbm4(float x, float y, float z, float w, int octaves, float persistence, float lacunarity) {
   float freq = 1.0f, amp = 1.0f, mx = 1.0f, total = noise4(x, y, z, w);
   for (int i = 1; i < octaves; i++) {
@@ -1132,9 +1319,11 @@ void bbo_default_config(bbo_config* c) {
   c->max_ep_steps = 4000; c->max_allowed_tilt = 20.0; c->max_wheel_velocity = 10.0; c->camera_frame_rate = 90.0;
   c->reward_scale = 0.01; c->action_reg_coef = -0.0001; c->survival_bonus = 0.02; c->target_dir[0] = 0; c->target_dir[1] = 1;
   c->hfield_zscale = 2.0; c->cameras = 0; c->im_h = 64; c->im_w = 64;
+  c->reward_type = 0; c->goal[0] = 0; c->goal[1] = 0; c->distance_scale = 1.0;
 }
 bbo_env* bbo_create(const bbo_config* cfg) {
   bbo_env* e = new bbo_env();
+  { const char* x = getenv("BBO_EXTRA"); if (x) g_extra_pairs = x[0] != '0'; }
   e->cfg = *cfg; buildModel(e->m); e->m.hf_size[2] = cfg->hfield_zscale;
   memset(e->d.qpos, 0, sizeof(R) * NQ);
   e->d.hfield.assign(HN * HN, 0.f);
@@ -1181,7 +1370,11 @@ int bbo_step(bbo_env* e, const float* a, float* obs, float* reward, uint8_t* ter
   mjStep(e->m, d);
   getObs(e, a, obs);
   // reward, float32 arithmetic as NumPy>=2 does (ballbot_env.py:929-937)
-  float r = (obs[6] * (float)c.target_dir[0] + obs[7] * (float)c.target_dir[1]) * (float)c.reward_scale;
+  float r;
+  if (c.reward_type == 1) {   // DistanceReward on pos2d (rewards/distance.py:33-50): float32 norm of (goal - pos2d)
+    const float dx = (float)c.goal[0] - (float)d.xpos[1][0], dy = (float)c.goal[1] - (float)d.xpos[1][1];
+    r = (-(float)c.distance_scale * sqrtf(dx * dx + dy * dy)) * (float)c.reward_scale;
+  } else r = (obs[6] * (float)c.target_dir[0] + obs[7] * (float)c.target_dir[1]) * (float)c.reward_scale;
   float nrm = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
   r += (float)c.action_reg_coef * (nrm * nrm);
   e->step_counter++;
@@ -1248,16 +1441,36 @@ int bbo_get_kin(bbo_env* e, double* xpos, double* xquat, double* cvel) {
   return 0;
 }
 
+static int g_trig = -1;   // 1: fast_sin / fast_cos of noise/_noise.h (default), 0: libm sinf / cosf (BBO_TRIG=l, experiment record)
+static inline float fast_sin_(float x) {
+  volatile float z = (x + 25165824.0f);
+  x = x - (z - 25165824.0f);
+  float y = x - x * fabsf(x);
+  return y * (3.1f + 3.6f * fabsf(y));
+}
+static inline float tsin(float x) { return g_trig ? fast_sin_(x) : sinf(x); }
+static inline float tcos(float x) { return g_trig ? fast_sin_(x + 0.5f) : cosf(x); }
 float bbo_snoise2_tiled(float x, float y, int octaves, float persistence, float lacunarity, float repeatx, float repeaty, int base) {
   // noise._simplex py_noise2, tiled branch (both repeats given) [3P-memory]
+  if (g_trig < 0) { const char* e = getenv("BBO_TRIG"); g_trig = !(e && e[0] == 'l'); }
   float z = (float)base, w = z;
   float yf = (float)(y * 2.0 / repeaty), yr = (float)(repeaty * M_1_PI * 0.5);
-  float vy = sinf(yf), vyz = cosf(yf);
+  float vy = tsin(yf), vyz = tcos(yf);
   y = vy * yr; w += vyz * yr;
   float xf = (float)(x * 2.0 / repeatx), xr = (float)(repeatx * M_1_PI * 0.5);
-  float vx = sinf(xf), vxz = cosf(xf);
+  float vx = tsin(xf), vxz = tcos(xf);
   x = vx * xr; z += vxz * xr;
   return fbm4(x, y, z, w, octaves, persistence, lacunarity);
+}
+float bbo_snoise2(float x, float y, int octaves, float persistence, float lacunarity, int base) {
+  // untiled branch of py_noise2: `base` is added to both coordinates of every octave
+  const float z = (float)base;
+  float freq = 1.0f, amp = 1.0f, mx = 1.0f, total = noise2(x + z, y + z);
+  for (int i = 1; i < octaves; i++) {
+    freq *= lacunarity; amp *= persistence; mx += amp;
+    total += noise2(x * freq + z, y * freq + z) * amp;
+  }
+  return total / mx;
 }
 int bbo_perlin_terrain(int n, double scale, int octaves, double persistence, double lacunarity, double amplitude, int seed, float* out) {
   // terrain/perlin.py:51-74

@@ -40,6 +40,9 @@ typedef struct bbo_config {
   double hfield_zscale;      /* ballbot.xml:23 size[2] (2.0); ramp/gradient mutate it, ballbot_env.py:486-495 */
   int cameras;               /* 0: disable_cameras=True */
   int im_h, im_w;            /* 64 x 64 */
+  int reward_type;           /* 0 directional (rewards/directional.py:33-54), 1 distance (rewards/distance.py:33-50 on info pos2d) */
+  double goal[2];            /* distance reward: goal_position */
+  double distance_scale;     /* distance reward: scale */
 } bbo_config;
 
 void bbo_default_config(bbo_config* cfg);
@@ -78,6 +81,8 @@ int bbo_get_kin(bbo_env* e, double* xpos_base3, double* xquat_base4, double* cve
  * restated (terrain/perlin.py:56-65), and the full terrain/perlin.py:8-74 generator */
 float bbo_snoise2_tiled(float x, float y, int octaves, float persistence, float lacunarity,
                         float repeatx, float repeaty, int base);
+/* noise.snoise2(x, y, octaves, persistence, lacunarity, base=seed) without repeats (terrain/gradient.py:74-80) */
+float bbo_snoise2(float x, float y, int octaves, float persistence, float lacunarity, int base);
 int bbo_perlin_terrain(int n, double scale, int octaves, double persistence, double lacunarity,
                        double amplitude, int seed, float* out);
 /* spawn offset of ballbot_env.py:528-565 for a given hfield */

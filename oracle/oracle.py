@@ -19,7 +19,8 @@ class Config(C.Structure):
     _fields_ = [("max_ep_steps", C.c_int), ("max_allowed_tilt", C.c_double), ("max_wheel_velocity", C.c_double),
                 ("camera_frame_rate", C.c_double), ("reward_scale", C.c_double), ("action_reg_coef", C.c_double),
                 ("survival_bonus", C.c_double), ("target_dir", C.c_double * 2), ("hfield_zscale", C.c_double),
-                ("cameras", C.c_int), ("im_h", C.c_int), ("im_w", C.c_int)]
+                ("cameras", C.c_int), ("im_h", C.c_int), ("im_w", C.c_int),
+                ("reward_type", C.c_int), ("goal", C.c_double * 2), ("distance_scale", C.c_double)]
 
 
 def build(force=False):
@@ -56,6 +57,8 @@ def lib():
         L.bbo_get_kin.argtypes = [C.c_void_p, dp, dp, dp]
         L.bbo_snoise2_tiled.restype = C.c_float
         L.bbo_snoise2_tiled.argtypes = [C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int]
+        L.bbo_snoise2.restype = C.c_float
+        L.bbo_snoise2.argtypes = [C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int]
         L.bbo_perlin_terrain.argtypes = [C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, fp]
         L.bbo_spawn_offset.restype = C.c_double
         L.bbo_spawn_offset.argtypes = [fp, C.c_double]
@@ -97,8 +100,8 @@ class OracleEnv:
         lib().bbo_default_config(C.byref(cfg))
         cfg.cameras = int(cameras); cfg.im_h = cfg.im_w = im
         for k, v in kw.items():
-            if k == "target_dir":
-                cfg.target_dir[0], cfg.target_dir[1] = v
+            if k in ("target_dir", "goal"):
+                getattr(cfg, k)[0], getattr(cfg, k)[1] = v
             else:
                 setattr(cfg, k, v)
         self.cfg = cfg
