@@ -89,6 +89,12 @@ def cpu_arm(workload, seconds, procs):
     return steps / wall, steps, wall
 
 
+def cpu_single_thread(seconds=6.0):
+    """BASELINE.json configs[0] (C1): ONE flat-terrain env, fixed-seed random actions, one thread, episodes restarted on tilt."""
+    n, wall = _cpu_worker((0, seconds, "flat"))
+    return n / wall, n, wall
+
+
 # ----------------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler(threading.Thread):
     """SM clock and throttle reasons during the timed region.  NVML in-process (a query costs microseconds); spawning
@@ -175,9 +181,12 @@ def main():
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     workload_name = ("perlin uneven terrain + ball-hfield contacts + depth raycast 2x64x64 every 6th step, terrain regen on reset"
                      if args.workload == "perlin" else "flat terrain, proprioceptive obs only")
+    # identical in both arms (the driver compares them); run-specific details go to the line's "run" object
     config = {"workload": f"{workload_name}; {envs} envs/GPU (BASELINE.json configs[{2 if args.workload == 'perlin' else 1}])",
-              "envs_per_gpu": envs, "physics": f"fp{args.precision}", "solver": args.solver, "integrator": "RK4 dt=0.002", "actions": "U(-1,1)^3 device RNG seed 0",
-              "parallelism": f"env-sharded x{world}, no collective on the step path"}
+              "envs_per_gpu": envs, "physics": f"fp{args.precision}", "solver": args.solver, "integrator": "RK4 dt=0.002",
+              "actions": "U(-1,1)^3, fresh draw every step (device RNG on the GPU arm, numpy on the CPU arm)",
+              "collision_pairs": "ball x wheels, ball x terrain, wheels / sticks x terrain, ball x sticks / tower",
+              "parallelism": f"env-sharded x{args.gpus}, no collective on the step path"}
     cores = os.cpu_count() or 1
 
     # ------------------------------------------------------------------ reference arm: CPU oracle on all host cores
@@ -194,10 +203,13 @@ def main():
                 total_steps += st; total_wall += wall
         value = total_steps / max(total_wall, 1e-9)
         sample = f"{cores} worker processes x 1 oracle env each (SubprocVecEnv shape), {per_step_seconds:.0f} s of stepping per timed round, {n_rounds} rounds"
+        st_rate, st_n, st_wall = cpu_single_thread(6.0)
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
                           "warmup": warmup, "ms_per_step": 1e3 * total_wall / max(1, n_rounds), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                           "single_thread_flat": {"value": st_rate, "unit": UNIT, "cores": 1, "sample": f"BASELINE configs[0]: one flat env, one thread, {st_n} env-steps in {st_wall:.1f} s"},
+                                           "note": "unoptimised -O2 fp64 restatement incl. a CPU ray-cast every 6th step and ctypes overhead per step; a real mj_step of this 15-dof model is O(10 k) steps/s/core"},
                           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "wall_s": time.perf_counter() - t0}))
         return
@@ -227,15 +239,25 @@ def main():
     eng = BallbotEngine(num_envs=envs, device=local_rank, precision=args.precision, terrain="perlin" if perlin else "flat",
                         cameras=perlin, auto_reset=True, seed=0, env_offset=rank * envs, solver=args.solver)
     gen = torch.Generator(device=dev); gen.manual_seed(rank)
-    n_act = 64
-    act = (torch.rand(n_act, envs, 3, device=dev, generator=gen) * 2 - 1).contiguous()   # U(-1,1)^3, pre-generated on device
+    act = torch.empty(envs, 3, device=dev)
+
+    def draw():                    # U(-1,1)^3, a fresh device-side draw for every step
+        return act.uniform_(-1.0, 1.0, generator=gen)
     eng.reset()
-    preroll = args.preroll if args.preroll >= 0 else (300 if perlin else 0)
+    # Untimed pre-roll.  All envs start their first episode together; to make ANY timed window representative the episode phases
+    # are randomised first: during the first `stagger` steps every env is force-reset once at its own step (a fixed pseudo-random
+    # schedule), then the rest of the pre-roll lets the reset waves mix (episodes last ~160 +- 50 steps on this workload).
+    preroll = args.preroll if args.preroll >= 0 else (600 if perlin else 0)
+    stagger = min(320, preroll // 2)
+    if stagger:
+        when = (torch.arange(envs, device=dev, dtype=torch.int64) * 7919 + 13 * rank) % stagger
     for t in range(preroll):
-        eng.step(act[t % n_act])
+        if t < stagger:
+            eng.reset((when == t).to(torch.uint8))
+        eng.step(draw())
     done_count = torch.zeros((), dtype=torch.int64, device=dev)
     for t in range(warmup):        # same ops as the timed loop, so that lazily loaded kernels and allocator growth happen here
-        eng.step(act[t % n_act])
+        eng.step(draw())
         done_count += eng.terminated.sum()
     barrier()
     done_count.zero_()
@@ -246,21 +268,21 @@ def main():
         sampler.recording = True
     ev0.record()
     for t in range(steps):
-        eng.step(act[t % n_act])
+        eng.step(draw())
         done_count += eng.terminated.sum()
     ev1.record()
     barrier()
     if sampler:
         sampler.recording = False
     ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count - launches0 + steps   # + the torch reduction kernel counting the resets
+    launches = eng.launch_count - launches0             # this repo's own kernels only (torch's RNG / reduction kernels are not counted)
     # per-kernel breakdown (roofline): a second pass with CUDA events between the kernels of every step.  It is kept out of
     # the headline loop because the 5 event records per step cost a few per cent; same engine, same env population.
     prof_steps = 0 if args.no_kernel_profile else max(10, min(steps, 60))
     if prof_steps:
         eng.profile_begin(prof_steps)
         for t in range(prof_steps):
-            eng.step(act[(steps + t) % n_act])
+            eng.step(draw())
         torch.cuda.synchronize(dev)
         prof = eng.profile_end()
     else:
@@ -277,20 +299,28 @@ def main():
 
     # ---- e2e: the same step through the host-buffer C-ABI call (numpy actions in, numpy obs/reward/done out)
     e2e_steps = max(3, min(steps, 100))
-    act_host = act[:n_act].cpu().numpy()
-    eng.step_host(act_host[0], images=False)
-    barrier()
-    t0 = time.perf_counter()
-    for t in range(e2e_steps):
-        eng.step_host(act_host[t % n_act], images=False)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * envs * e2e_steps / float(te.item())
+    rng_host = np.random.default_rng(rank)
+    act_host = rng_host.uniform(-1, 1, (64, envs, 3)).astype(np.float32)
+
+    def e2e_run(images, n):
+        eng.step_host(act_host[0], images=images)
+        barrier()
+        t0 = time.perf_counter()
+        for t in range(n):
+            eng.step_host(act_host[t % 64], images=images)
+        torch.cuda.synchronize(dev)
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return world * envs * n / float(te.item())
+    e2e_value = e2e_run(False, e2e_steps)
     h2d = envs * 3 * 4
     d2h = envs * (16 * 4 + 4 + 1 + 1 + 8 + 16 * 4 + 4 + 4)   # obs16, reward, terminated, failure, pos2d, terminal_obs, episode return / length
+    # the same call with both depth images copied to host numpy arrays every step (what a numpy / SB3 caller of the VecEnv pays;
+    # the reference's pipes carry the same 32 KB per env): bounded to a few steps, 2.1 GB cross PCIe per step at 65,536 envs
+    e2e_img_steps = max(3, min(steps, 12)) if perlin else 0
+    e2e_img_value = e2e_run(True, e2e_img_steps) if e2e_img_steps else None
+    d2h_img = d2h + envs * 2 * 64 * 64 * 4
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -298,8 +328,9 @@ def main():
         kern = {"step": prof["step_ms"] / nsteps, "terrain": prof["terrain_ms"] / nsteps, "reset": prof["reset_ms"] / nsteps, "depth": prof["depth_ms"] / nsteps}
         resets_per_step_gpu = total_resets / world / steps
         refresh_per_step = envs / 6.0 if perlin else 0.0
+        table = perlin and eng.cfg.perlin_table != 0 and envs >= 2048   # all 10,000 Perlin fields precomputed at bb_create: a reset selects one
         alg = {"step": envs * (BYTES_STATE[args.precision] + (BYTES_HF_FOOTPRINT if perlin else 0.0)),
-               "terrain": resets_per_step_gpu * BYTES_TERRAIN if perlin else 0.0,
+               "terrain": resets_per_step_gpu * BYTES_TERRAIN if perlin and not table else 0.0,
                "depth": (refresh_per_step + resets_per_step_gpu) * BYTES_DEPTH_REFRESH, "reset": resets_per_step_gpu * 600.0}
         dom = max(kern, key=lambda k: kern[k])
         achieved = alg[dom] / max(kern[dom] * 1e-3, 1e-12) / 1e9
@@ -307,8 +338,10 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": f"f{args.precision}", "data": "synthetic",
-                "config": dict(config, preroll_steps=preroll, l2="working set (state + per-env heightfields + images) exceeds the 126 MB L2; no flush needed",
-                               resets_in_timed_region=total_resets, mean_episode_len=(world * envs * steps / total_resets) if total_resets else None),
+                "config": config,
+                "run": dict(preroll_steps=preroll, phase_stagger_steps=stagger, terrain_storage="table of 10,000 Perlin fields (3.4 GB)" if table else "per-env fields",
+                            l2="working set (state + split-phase context + heightfields + images) exceeds the 126 MB L2; no flush needed",
+                            resets_in_timed_region=total_resets, mean_episode_len=(world * envs * steps / total_resets) if total_resets else None),
                 "roofline": {"bound": "hbm", "kernel": "k_stage x5 + k_newton x4 (one step)" if dom == "step" else f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (NCU_TRAFFIC[dom] * (envs if dom == "step" else refresh_per_step + resets_per_step_gpu)
                                          if perlin and args.precision == 64 and dom in NCU_TRAFFIC else None),
@@ -319,12 +352,18 @@ def main():
                              "note": "not HBM-bound: the constraint solver (k_newton, 64 % of the step) is bound by the latency of its dependent chain (ncu: wait 2.6 cycles per issue, IPC 1.6 of 4, FP64 pipe 16 %, DRAM 1 %); depth ray-cast and terrain noise are instruction-issue bound (IPC 3.0 / 3.5); see profiles/README.md"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "bb_step_host (C ABI, host buffers); depth images stay device-resident for the policy encoder"},
+                "e2e_images": ({"value": e2e_img_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_img, "steps": e2e_img_steps,
+                                "api": "bb_step_host with img_0 / img_1: both 64x64 depth images of every env copied to host numpy arrays every step"}
+                               if e2e_img_value else None),
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary() if sampler else None}
         if not args.no_cpu_baseline and world == 1:
             rate, st, wall = cpu_arm(args.workload, args.cpu_seconds, cores)
+            st_rate, st_n, st_wall = cpu_single_thread(5.0)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"fp64 oracle, {cores} processes x 1 env (SubprocVecEnv shape), same workload, {wall:.1f} s wall, {st} env-steps"}
+                                    "sample": f"fp64 oracle, {cores} processes x 1 env (SubprocVecEnv shape), same workload, {wall:.1f} s wall, {st} env-steps",
+                                    "single_thread_flat": {"value": st_rate, "unit": UNIT, "cores": 1, "sample": f"BASELINE configs[0]: one flat env, one thread, {st_n} env-steps in {st_wall:.1f} s"},
+                                    "note": "unoptimised -O2 fp64 restatement incl. a CPU ray-cast every 6th step and ctypes overhead per step; a real mj_step of this 15-dof model is O(10 k) steps/s/core"}
         print(json.dumps(line))
     eng.close()
     if world > 1:

@@ -16,10 +16,13 @@
 extern "C" {
 #endif
 
-#define BB_ABI_VERSION 1
+#define BB_ABI_VERSION 2
 #define BB_HFIELD_N 293 /* ballbot_gym/models/ballbot.xml:23 (nrow = ncol = 293) */
 #define BB_NQ 17
 #define BB_NV 15
+#define BB_PERLIN_SEEDS 10000   /* ballbot_env.py:506: r_seed = integers(0, 10000) => only this many distinct Perlin fields exist */
+#define BB_PROBE_MAXCON 80      /* rows of the contact array written by bb_probe_forward / bb_get_contacts */
+#define BB_CONTACT_STRIDE 14    /* one contact row: type, dist, pos[3], frame[9] (mjContact.dist / pos / frame) */
 
 typedef enum bb_status {
   BB_OK = 0,
@@ -66,6 +69,12 @@ typedef struct bb_config {
   int32_t step_kernel;       /* 0: lane-group kernels, split-phase (default); 1: thread-per-env reference mapping (cross-check); 2: lane-group kernel, fused RK4 step (cross-check) */
   int32_t solver_mode;       /* 0: MuJoCo-faithful iteration path (every RK4 stage warm-starts from qacc_warmstart);
                                 1: fast -- stages 2..4 warm-start from the previous stage (same minimiser within tolerance) */
+  int32_t perlin_table;      /* BB_TERRAIN_PERLIN storage: 1 = all BB_PERLIN_SEEDS possible fields are generated once at bb_create
+                                (3.4 GB, independent of num_envs) and a reset only selects one; 0 = one regenerated field per env
+                                (343 KB per env, any seed value); -1 = auto (table from 2048 envs up) */
+  int32_t seed_stream;       /* terrain-seed draws at (auto-)reset: 0 = counter-based hash of (seed, env, episode) with the law
+                                U{0..9999}; 1 = numpy PCG64 per env, bit-compatible with self._np_random.integers(0, 10000)
+                                (ballbot_env.py:506); states are uploaded with bb_set_rng_state */
 } bb_config;
 
 /* Caller-owned device buffers written by bb_step / bb_reset.  Layouts follow the observation dict of
@@ -99,8 +108,13 @@ const char* bb_last_error(const bb_engine* e); /* e may be NULL: error of the la
 int bb_num_envs(const bb_engine* e);
 
 /* replaces VecEnv.reset() / BBotSimulation.reset (ballbot_env.py:567-671) for the envs selected by mask
- * (device uint8[N], NULL = all). Writes the reset observation into io. */
-int bb_reset(bb_engine* e, const uint8_t* mask_dev, const bb_io* io, void* cuda_stream);
+ * (device uint8[N], NULL = all). seeds_dev (device int32[N], NULL = draw from the engine's seed stream) fixes the terrain seed
+ * r_seed of every selected env (ballbot_env.py:505-510) -- replay of recorded episodes. Writes the reset observation into io. */
+int bb_reset(bb_engine* e, const uint8_t* mask_dev, const int32_t* seeds_dev, const bb_io* io, void* cuda_stream);
+/* numpy-compatible terrain-seed stream (seed_stream = 1): per-env PCG64 state as np.random.PCG64(seed).state gives it,
+ * device uint64[N][5] = {state_hi, state_lo, inc_hi, inc_lo, has_uint32 | uinteger << 32}; replaces gymnasium's
+ * seeding.np_random(seed) behind reset(seed=...) / eval_env=[True, seed] (ballbot_env.py:378-384,596-599) */
+int bb_set_rng_state(bb_engine* e, const uint64_t* state_dev, void* cuda_stream);
 
 /* replaces VecEnv.step_async+step_wait / BBotSimulation.step (ballbot_env.py:854-1036): one patched-MuJoCo
  * mj_step (RK4, 2 ms) per env + observation + reward + termination (+ auto-reset). actions_dev: float[N,3]. */
@@ -134,10 +148,14 @@ int bb_perlin_grid(int32_t device, int32_t n, float scale, int32_t octaves, floa
 int bb_render_depth(bb_engine* e, float* rgbd_0, float* rgbd_1, void* cuda_stream);
 
 /* parity probe == inspecting mjData.qacc / qacc_smooth / qfrc_smooth / ncon / solver_niter / contact[] after one
- * mj_forward (reference call sites ballbot_env.py:525,620): out_dev double[64] = qacc[0:15], qacc_smooth[15:30],
- * qfrc_smooth[30:45], ncon[45], niter[46], then model constants; contact dist[53], pos[53*3], frame[53*9]. */
-int bb_probe_forward(bb_engine* e, int32_t env, const double* ctrl3_dev, double* out_dev, double* cdist_dev, double* cpos_dev,
-                     double* cframe_dev, void* cuda_stream);
+ * mj_forward (reference call sites ballbot_env.py:525,620) through the SAME device code the step kernels run:
+ * out_dev double[64] = qacc[0:15], qacc_smooth[15:30], qfrc_smooth[30:45], ncon[45], niter[46], then model constants;
+ * contacts_dev double[BB_PROBE_MAXCON][BB_CONTACT_STRIDE], row = {type, dist, pos[3], frame[9]} with type
+ * 0..2 ball x wheel_i, 3 heightfield x ball, 4/5 heightfield x camera stick, 6..8 heightfield x wheel_i, 9 ball x tower,
+ * 10/11 ball x camera stick (order: robot pairs first, then the ball x heightfield prisms in MuJoCo's scan order). */
+int bb_probe_forward(bb_engine* e, int32_t env, const double* ctrl3_dev, double* out_dev, double* contacts_dev, void* cuda_stream);
+/* mjData.contact[] / ncon of env `env` at its current state (contact-set parity): contacts_dev as above, ncon_dev int32[1] */
+int bb_get_contacts(bb_engine* e, int32_t env, double* contacts_dev, int32_t* ncon_dev, void* cuda_stream);
 
 /* Host-buffer convenience path == what SubprocVecEnv.step does for numpy callers: H2D copy of actions, bb_step,
  * D2H copy of the proprio observation block [N,16] (orientation, angular_vel, vel, motor_state, actions, rel ts),
@@ -176,8 +194,10 @@ int bb_gae(const float* rewards_dev, const float* values_dev, const uint8_t* don
 
 /* number of kernel launches issued by this engine so far (bench.py's gpu_launches claim) */
 int64_t bb_launch_count(const bb_engine* e);
-/* engine model constants for tests: dA[4], meaninertia, masses (m0, mw, mL) */
-int bb_model_constants(double* dA4, double* meaninertia, double* masses3);
+/* engine model constants for tests: dA[12] (diagApprox per contact type), meaninertia, masses (m0, mw, mL) */
+int bb_model_constants(double* dA12, double* meaninertia, double* masses3);
+/* "libballbot_b200 abi <n> built <date> <time> src <hash of the translation unit's sources>": lets a test log tell a stale .so from a fresh one */
+const char* bb_build_info(void);
 
 #ifdef __cplusplus
 }

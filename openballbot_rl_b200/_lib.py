@@ -17,6 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 HFIELD_N = 293
 NQ, NV = 17, 15
+PROBE_MAXCON, CONTACT_STRIDE = 80, 14      # BB_PROBE_MAXCON, BB_CONTACT_STRIDE
 
 
 class EngineError(RuntimeError):
@@ -35,6 +36,7 @@ class Config(C.Structure):
         ("reward_type", C.c_int32), ("reward_scale", C.c_float), ("action_reg_coef", C.c_float),
         ("survival_bonus", C.c_float), ("target_direction", C.c_float * 2), ("goal_position", C.c_float * 2),
         ("distance_scale", C.c_float), ("seed", C.c_uint64), ("auto_reset", C.c_int32), ("step_kernel", C.c_int32), ("solver_mode", C.c_int32),
+        ("perlin_table", C.c_int32), ("seed_stream", C.c_int32),
     ]
 
 
@@ -55,7 +57,8 @@ class HostIO(C.Structure):
 EXPORTED = ["bb_create", "bb_destroy", "bb_default_config", "bb_last_error", "bb_num_envs", "bb_reset", "bb_step",
             "bb_add_reward", "bb_set_state", "bb_get_state", "bb_set_hfield", "bb_get_hfield", "bb_get_terrain_seeds",
             "bb_perlin_terrain", "bb_render_depth", "bb_step_host", "bb_reset_host", "bb_launch_count",
-            "bb_model_constants", "bb_probe_forward", "bb_profile_begin", "bb_profile_end", "bb_perlin_grid", "bb_gae", "bb_host_buffers"]
+            "bb_model_constants", "bb_probe_forward", "bb_profile_begin", "bb_profile_end", "bb_perlin_grid", "bb_gae", "bb_host_buffers",
+            "bb_set_rng_state", "bb_get_contacts", "bb_build_info"]
 
 
 def needs_build():
@@ -66,11 +69,21 @@ def needs_build():
     return any(os.path.exists(s) and os.path.getmtime(s) > t for s in srcs)
 
 
+def source_hash():
+    """Short hash of every source of the library (what bb_build_info() reports: tells a stale .so from a fresh one)."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in [os.path.join(_CSRC, s) for s in _SOURCES] + [os.path.join(_PKG, "..", "include", "ballbot_b200.h")]:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:12]
+
+
 def build(force=False, verbose=False):
     """Compile csrc/bb_engine.cu for sm_100a into libballbot_b200.so (nvcc cross-compiles without a GPU)."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + [os.path.join(_CSRC, u) for u in _UNITS]
+    cmd = ["nvcc"] + NVCC_FLAGS + [f'-DBB_SRC_HASH="{source_hash()}"'] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + [os.path.join(_CSRC, u) for u in _UNITS]
     subprocess.check_call(cmd)
     return LIB_PATH
 
@@ -98,7 +111,11 @@ def lib():
     L.bb_last_error.argtypes = [vp]
     L.bb_last_error.restype = C.c_char_p
     L.bb_num_envs.argtypes = [vp]
-    L.bb_reset.argtypes = [vp, vp, C.POINTER(IO), vp]
+    L.bb_reset.argtypes = [vp, vp, vp, C.POINTER(IO), vp]
+    L.bb_set_rng_state.argtypes = [vp, vp, vp]
+    L.bb_get_contacts.argtypes = [vp, C.c_int32, vp, vp, vp]
+    L.bb_build_info.argtypes = []
+    L.bb_build_info.restype = C.c_char_p
     L.bb_step.argtypes = [vp, vp, C.POINTER(IO), vp]
     L.bb_add_reward.argtypes = [vp, vp, C.POINTER(IO), vp]
     L.bb_set_state.argtypes = [vp, vp, vp, vp, vp]
@@ -117,7 +134,7 @@ def lib():
     L.bb_gae.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_float, C.c_float, vp, vp, vp]
     L.bb_profile_begin.argtypes = [vp, C.c_int32]
     L.bb_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
-    L.bb_probe_forward.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.bb_probe_forward.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
     L.bb_model_constants.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L

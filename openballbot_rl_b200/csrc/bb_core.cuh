@@ -33,7 +33,16 @@ namespace bb {
 
 constexpr int NQ = 17, NV = 15, HN = 293;
 constexpr int MAXH = 50;          // mjMAXCONPAIR: max ball-hfield contacts per forward pass
-constexpr int NC = 3 + MAXH;      // 3 wheel contacts + hfield contacts
+constexpr int NC = 64;            // contact capacity of one forward pass (3 wheel pairs + <= 50 ball-terrain prisms + the other pairs)
+// contact types (index of ModelConst::dA):
+//   0..2  ball x wheel_i (explicit pairs, anisotropic friction, ballbot.xml:89-93)     3      heightfield x ball
+//   4,5   heightfield x camera stick i (cam bodies are welded to the base)              6..8   heightfield x wheel_i capsule
+//   9     ball x tower cylinder                                                         10,11  ball x camera stick i
+constexpr int NCT = 12;
+BB_HD bool ctHasBase(int ty) { return ty != 3; }
+BB_HD bool ctHasBall(int ty) { return ty <= 3 || ty >= 9; }
+BB_HD int ctWheel(int ty) { return ty <= 2 ? ty : ((ty >= 6 && ty <= 8) ? ty - 6 : -1); }
+BB_HD int ctFric(int ty) { return ty <= 2 ? 0 : 1; }
 constexpr int NTRI = NV * (NV + 1) / 2;
 
 // ---------------------------------------------------------------------------------------------- math
@@ -108,7 +117,7 @@ template <typename T> struct ModelConst {
   // ball
   T mL, IL, dz, ball_r;
   // contact model
-  T dA[4];         // diagApprox: wheel0..2 pairs, hfield pair
+  T dA[NCT];       // diagApprox (sum of the two bodies' invweight0) per contact type
   T K, B;          // solref -> stiffness / damping of aref
   T solimp[5];
   T mu[2], f1[2], f2[2], d1r[2], d2r[2];   // [0] wheel pairs, [1] hfield pair
@@ -350,6 +359,123 @@ template <typename T> BB_HD V3<T> closestOnTriangle(const V3<T>& p, const V3<T>&
   return a + ab * (vb * den) + ac * (vc * den);
 }
 
+// closest points of the segments p1-q1 and p2-q2 (returns the squared distance)
+template <typename T> BB_HD T closestSegSeg(const V3<T>& p1, const V3<T>& q1, const V3<T>& p2, const V3<T>& q2, V3<T>& c1, V3<T>& c2) {
+  const V3<T> d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+  const T a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), tiny = (T)1e-15;
+  T s, t;
+  if (a <= tiny && e <= tiny) { s = 0; t = 0; }
+  else if (a <= tiny) { s = 0; t = f / e; t = t < 0 ? (T)0 : (t > 1 ? (T)1 : t); }
+  else {
+    const T c = dot(d1, r);
+    if (e <= tiny) { t = 0; s = -c / a; s = s < 0 ? (T)0 : (s > 1 ? (T)1 : s); }
+    else {
+      const T b = dot(d1, d2), den = a * e - b * b;
+      s = den > tiny ? (b * f - c * e) / den : (T)0; s = s < 0 ? (T)0 : (s > 1 ? (T)1 : s);
+      t = (b * s + f) / e;
+      if (t < 0) { t = 0; s = -c / a; s = s < 0 ? (T)0 : (s > 1 ? (T)1 : s); }
+      else if (t > 1) { t = 1; s = (b - c) / a; s = s < 0 ? (T)0 : (s > 1 ? (T)1 : s); }
+    }
+  }
+  c1 = p1 + d1 * s; c2 = p2 + d2 * t;
+  const V3<T> dv = c1 - c2;
+  return dot(dv, dv);
+}
+// closest points between the segment p0-p1 (ps) and the triangle abc (pt): segment end points against the triangle, then the
+// segment against the three edges; the first minimum in that order wins
+template <typename T>
+BB_HD void closestSegTriangle(const V3<T>& p0, const V3<T>& p1, const V3<T>& a, const V3<T>& b, const V3<T>& c, V3<T>& ps, V3<T>& pt) {
+  T best = (T)1e30;
+#pragma unroll 1
+  for (int i = 0; i < 2; i++) {
+    const V3<T> e = i ? p1 : p0;
+    const V3<T> q = closestOnTriangle(e, a, b, c);
+    const V3<T> dv = e - q; const T d2 = dot(dv, dv);
+    if (d2 < best) { best = d2; ps = e; pt = q; }
+  }
+#pragma unroll 1
+  for (int i = 0; i < 3; i++) {
+    const V3<T> e0 = i == 0 ? a : (i == 1 ? b : c), e1 = i == 0 ? b : (i == 1 ? c : a);
+    V3<T> s1, s2;
+    const T d2 = closestSegSeg(p0, p1, e0, e1, s1, s2);
+    if (d2 < best) { best = d2; ps = s1; pt = s2; }
+  }
+}
+// capsule (segment p0-p1, radius r) against the prism under the top triangle (ta, tb, tc): closest feature of the top surface
+// patch; a segment point under the top plane only counts inside the prism's column (same conventions as the ball pair)
+template <typename T>
+BB_HD bool capsulePrism(const V3<T>& p0, const V3<T>& p1, T r, const V3<T>& ta, const V3<T>& tb, const V3<T>& tc, T& dist, V3<T>& n, V3<T>& pos) {
+  const V3<T> e1 = tb - ta, e2 = tc - ta;
+  V3<T> nn = cross(e1, e2); if (nn.z < 0) nn = -nn;
+  nn = nn * ((T)1 / bsqrt(dot(nn, nn)));
+  V3<T> ps = p0, pt = ta;
+  closestSegTriangle(p0, p1, ta, tb, tc, ps, pt);
+  const T h0 = dot(p0 - ta, nn), h1 = dot(p1 - ta, nn);
+  const V3<T> pl = h0 <= h1 ? p0 : p1; const T hl = h0 <= h1 ? h0 : h1;
+  if (hl < 0) {
+    const V3<T> ap = pl - ta;
+    const T u = e1.x * e2.y - e1.y * e2.x;
+    const T sa = (ap.x * e2.y - ap.y * e2.x) / u, tt = (e1.x * ap.y - e1.y * ap.x) / u;
+    if (!(sa < 0 || tt < 0 || sa + tt > 1)) { dist = hl - r; n = nn; pos = pl - nn * (r + (T)0.5 * dist); return true; }
+    if (dot(ps - ta, nn) < 0) return false;
+  }
+  const V3<T> dv = ps - pt; const T dl = bsqrt(dot(dv, dv));
+  if (dl >= r || dl < (T)1e-15) return false;
+  dist = dl - r; n = dv * ((T)1 / dl); pos = pt + n * ((T)0.5 * dist);
+  return true;
+}
+// heightfield sub-grid of an axis-aligned box [lo, hi] (mjc_ConvexHField): false = the box misses the field
+template <typename T> struct HfGrid { int cmin, cmax, rmin, rmax; T dx, zmin; };
+template <typename T> BB_HD bool hfieldSubgrid(T sx, T hbase, T zscale, const V3<T>& lo, const V3<T>& hi, HfGrid<T>& gr) {
+  if ((sx < lo.x) || (-sx > hi.x) || (sx < lo.y) || (-sx > hi.y) || (zscale < lo.z) || (-hbase > hi.z)) return false;
+  const T gs = (T)(HN - 1) / ((T)2 * sx);
+  int cmin = (int)bfloor((lo.x + sx) * gs), cmax = (int)bceil((hi.x + sx) * gs);
+  int rmin = (int)bfloor((lo.y + sx) * gs), rmax = (int)bceil((hi.y + sx) * gs);
+  gr.cmin = cmin < 0 ? 0 : cmin; gr.rmin = rmin < 0 ? 0 : rmin; gr.cmax = cmax > HN - 1 ? HN - 1 : cmax; gr.rmax = rmax > HN - 1 ? HN - 1 : rmax;
+  gr.dx = (T)2 * sx / (T)(HN - 1); gr.zmin = lo.z;
+  return true;
+}
+// top triangle k (0 / 1) of heightfield cell (r, c) in the triangle-strip order of mjc_ConvexHField
+template <typename T> BB_HD void hfieldTriangle(const float* hf, T zscale, T sx, T dx, int r, int c, int k, V3<T>& ta, V3<T>& tb, V3<T>& tc) {
+  const T x0 = dx * (T)c - sx, x1 = dx * (T)(c + 1) - sx, y0 = dx * (T)r - sx, y1 = dx * (T)(r + 1) - sx;
+  const V3<T> v00 = mk(x0, y0, (T)hf[r * HN + c] * zscale), v11 = mk(x1, y1, (T)hf[(r + 1) * HN + c + 1] * zscale);
+  if (k == 0) { ta = mk(x0, y1, (T)hf[(r + 1) * HN + c] * zscale); tb = v00; tc = v11; }
+  else { ta = v00; tb = v11; tc = mk(x1, y0, (T)hf[r * HN + c + 1] * zscale); }
+}
+// sphere (centre bc, radius br) against a capsule (centre cc, axis cu, radius r, half length hl): nearest point on the segment,
+// then sphere-sphere (mjraw_SphereCapsule); normal points from the sphere to the capsule
+template <typename T> BB_HD bool sphereCapsule(const V3<T>& bc, T br, const V3<T>& cc, const V3<T>& cu, T r, T hl, T& dist, V3<T>& n, V3<T>& pos) {
+  T x = dot(cu, bc - cc);
+  x = x > hl ? hl : (x < -hl ? -hl : x);
+  const V3<T> dif = cc + cu * x - bc;
+  const T cd = bsqrt(dot(dif, dif)), mind = br + r;
+  if (cd >= mind) return false;
+  n = dif * ((T)1 / cd); dist = cd - mind; pos = bc + n * (br + (T)0.5 * dist);
+  return true;
+}
+// sphere against a cylinder (mjraw_SphereCylinder: side / cap / corner); normal points from the sphere to the cylinder
+template <typename T> BB_HD bool sphereCylinder(const V3<T>& bc, T br, const V3<T>& cc, const V3<T>& ax, T rad, T hgt, T& dist, V3<T>& n, V3<T>& pos) {
+  const V3<T> vec = bc - cc;
+  const T x = dot(vec, ax);
+  const V3<T> pp = vec - ax * x; const T pp2 = dot(pp, pp);
+  bool side = babs(x) < hgt, cap = pp2 < rad * rad;
+  if (side && cap) { if (hgt - babs(x) < rad - bsqrt(pp2)) side = false; else cap = false; }
+  const T sg = x > 0 ? (T)1 : (T)-1;
+  V3<T> tgt; T trad;
+  if (side) { tgt = cc + ax * x; trad = rad; }
+  else if (cap) {
+    const V3<T> pc = cc + ax * (sg * hgt);
+    const T dd = sg * dot(bc - pc, ax) - br;
+    if (!(dd < 0)) return false;
+    dist = dd; n = ax * (-sg); pos = bc + n * (br + (T)0.5 * dist);
+    return true;
+  } else { tgt = cc + pp * (rad / bsqrt(pp2)) + ax * (sg * hgt); trad = 0; }
+  const V3<T> dif = tgt - bc; const T cd = bsqrt(dot(dif, dif));
+  if (!(cd < br + trad) || !(cd > (T)1e-15)) return false;
+  dist = cd - br - trad; n = dif * ((T)1 / cd); pos = bc + n * (br + (T)0.5 * dist);
+  return true;
+}
+
 // Contact generation: 3 patched sphere-capsule pairs (tools/mujoco_fix.patch:9-18) + ball vs heightfield prisms.
 // Only penetrating contacts (dist < 0) are recorded since margin = gap = 0.
 template <typename T>
@@ -433,6 +559,44 @@ BB_HD void collide(const ModelConst<T>& mc, const Geo<T>& g, const V3<T>* capC, 
       }
     }
   }
+  // ---- the other colliding geoms (ballbot.xml:41-69): camera sticks and wheel capsules against the heightfield, then the ball
+  // against the sticks (patched sphere-capsule) and the tower cylinder.  Order = the oracle's.
+#pragma unroll 1
+  for (int gi = 0; gi < 5; gi++) {
+    V3<T> cc, cu; T rad, hl; int ty;
+    if (gi < 2) { cc = g.pB + rot(g.RB, ld3(mc.stick_c[gi])); cu = rot(g.RB, ld3(mc.stick_u[gi])); rad = mc.stick_r; hl = mc.stick_hl; ty = 4 + gi; }
+    else { cc = capC[gi - 2]; cu = capU[gi - 2]; rad = mc.wheel_r; hl = mc.wheel_hl; ty = 6 + gi - 2; }
+    const V3<T> p0 = cc - cu * hl, p1 = cc + cu * hl;
+    const V3<T> lo = mk(bmin(p0.x, p1.x) - rad, bmin(p0.y, p1.y) - rad, bmin(p0.z, p1.z) - rad);
+    const V3<T> hi = mk(bmax(p0.x, p1.x) + rad, bmax(p0.y, p1.y) + rad, bmax(p0.z, p1.z) + rad);
+    HfGrid<T> gr;
+    if (!hfieldSubgrid(mc.hx, mc.hbase, zscale, lo, hi, gr)) continue;
+    int cnt = 0;
+    for (int r = gr.rmin; r < gr.rmax && cnt < MAXH; r++)
+      for (int c = gr.cmin; c < gr.cmax && cnt < MAXH; c++)
+        for (int k = 0; k < 2 && cnt < MAXH; k++) {
+          V3<T> ta, tb, tc; hfieldTriangle(hf, zscale, mc.hx, gr.dx, r, c, k, ta, tb, tc);
+          if (ta.z < gr.zmin && tb.z < gr.zmin && tc.z < gr.zmin) continue;
+          T dist; V3<T> n, pos;
+          if (!capsulePrism(p0, p1, rad, ta, tb, tc, dist, n, pos)) continue;
+          if (nc < NC) { st3(s.cF[nc], n); makeFrame(s.cF[nc], false); st3(s.cP[nc], pos); s.cDist[nc] = dist; s.ctype[nc] = (unsigned char)ty; nc++; }
+          cnt++;
+        }
+  }
+  for (int i = 0; i < 2; i++) {
+    const V3<T> cc = g.pB + rot(g.RB, ld3(mc.stick_c[i])), cu = rot(g.RB, ld3(mc.stick_u[i]));
+    T dist; V3<T> n, pos;
+    if (sphereCapsule(bc, br, cc, cu, mc.stick_r, mc.stick_hl, dist, n, pos) && nc < NC) {
+      st3(s.cF[nc], n); st3(s.cF[nc] + 3, cu); makeFrame(s.cF[nc], true);
+      st3(s.cP[nc], pos); s.cDist[nc] = dist; s.ctype[nc] = (unsigned char)(10 + i); nc++;
+    }
+  }
+  {
+    T dist; V3<T> n, pos;
+    if (sphereCylinder(bc, br, g.pB + rot(g.RB, ld3(mc.tower_c)), g.RB.c2, mc.tower_r, mc.tower_hl, dist, n, pos) && nc < NC) {
+      st3(s.cF[nc], n); makeFrame(s.cF[nc], false); st3(s.cP[nc], pos); s.cDist[nc] = dist; s.ctype[nc] = 9; nc++;
+    }
+  }
   s.nc = nc;
 }
 
@@ -444,11 +608,17 @@ template <typename T> BB_HD VelCtx<T> velCtx(const Geo<T>& g, const T* v) {
 }
 template <typename T> BB_HD void contactVel(const Geo<T>& g, const Scratch<T>& s, int c, const VelCtx<T>& vc, T* out) {
   const V3<T> P = ld3(s.cP[c]);
-  const V3<T> vball = vc.vL + cross(vc.wL, P - g.pL);
-  V3<T> rel;
-  const int ty = s.ctype[c];
-  if (ty == 3) rel = vball;
-  else rel = vc.vB + cross(vc.wB, P - g.pB) + cross(g.aw[ty], P - g.hw[ty]) * vc.v[6 + ty] - vball;
+  // relative velocity body2 - body1: the ball is body 2 against the heightfield and body 1 against every robot geom
+  const int ty = s.ctype[c], wi = ctWheel(ty);
+  V3<T> rel = mk((T)0, (T)0, (T)0);
+  if (ctHasBase(ty)) {
+    rel = vc.vB + cross(vc.wB, P - g.pB);
+    if (wi >= 0) rel = rel + cross(g.aw[wi], P - g.hw[wi]) * vc.v[6 + wi];
+  }
+  if (ctHasBall(ty)) {
+    const V3<T> vball = vc.vL + cross(vc.wL, P - g.pL);
+    rel = ty == 3 ? vball : rel - vball;
+  }
   const T* f = s.cF[c];
   out[0] = f[0] * rel.x + f[1] * rel.y + f[2] * rel.z;
   out[1] = f[3] * rel.x + f[4] * rel.y + f[5] * rel.z;
@@ -463,11 +633,14 @@ template <typename T> BB_HD void subJtF(const Geo<T>& g, const Scratch<T>& s, T*
     const V3<T> Fw = mk(f[0] * fc[0] + f[3] * fc[1] + f[6] * fc[2], f[1] * fc[0] + f[4] * fc[1] + f[7] * fc[2],
                         f[2] * fc[0] + f[5] * fc[1] + f[8] * fc[2]);
     const V3<T> P = ld3(s.cP[c]);
-    const int ty = s.ctype[c];
-    if (ty == 3) { FLs = FLs + Fw; TLs = TLs + cross(P - g.pL, Fw); }
-    else {
-      FB = FB + Fw; TB = TB + cross(P - g.pB, Fw); tq[ty] += dot(g.aw[ty], cross(P - g.hw[ty], Fw));
-      FLs = FLs - Fw; TLs = TLs - cross(P - g.pL, Fw);
+    const int ty = s.ctype[c], wi = ctWheel(ty);
+    if (ctHasBase(ty)) {
+      FB = FB + Fw; TB = TB + cross(P - g.pB, Fw);
+      if (wi >= 0) tq[wi] += dot(g.aw[wi], cross(P - g.hw[wi], Fw));
+    }
+    if (ctHasBall(ty)) {
+      if (ty == 3) { FLs = FLs + Fw; TLs = TLs + cross(P - g.pL, Fw); }
+      else { FLs = FLs - Fw; TLs = TLs - cross(P - g.pL, Fw); }
     }
   }
   const V3<T> tb = rotT(g.RB, TB), tl = rotT(g.RL, TLs);
@@ -479,7 +652,7 @@ template <typename T> BB_HD void subJtF(const Geo<T>& g, const Scratch<T>& s, T*
 // elliptic-cone zone logic of mj_constraintUpdate for one contact; returns cost, fills force/state/(cone Hessian)
 template <typename T>
 BB_HD T coneUpdate(const ModelConst<T>& mc, Scratch<T>& s, int c, const T* jar, bool wantH) {
-  const int k = s.ctype[c] == 3 ? 1 : 0;
+  const int k = ctFric(s.ctype[c]);
   const T mu = mc.mu[k], f1 = mc.f1[k], f2 = mc.f2[k];
   const T D0 = s.cD[c], D1 = D0 * mc.d1r[k], D2 = D0 * mc.d2r[k];
   const T U0 = jar[0] * mu, U1 = jar[1] * f1, U2 = jar[2] * f2;
@@ -527,16 +700,18 @@ template <typename T> BB_HD void addContactHessian(const Geo<T>& g, Scratch<T>& 
       for (int j = 0; j < 3; j++) Ww[3 * i + j] = f[i] * WF[j] + f[3 + i] * WF[3 + j] + f[6 + i] * WF[6 + j];
   }
   const V3<T> P = ld3(s.cP[c]);
-  const int ty = s.ctype[c];
+  const int ty = s.ctype[c], wi = ctWheel(ty);
   V3<T> gcol[13]; int idx[13]; int n = 0;
   const V3<T> rL = P - g.pL;
-  if (ty != 3) {
+  if (ctHasBase(ty)) {
     const V3<T> rB = P - g.pB;
     gcol[n] = mk((T)1, (T)0, (T)0); idx[n++] = 0; gcol[n] = mk((T)0, (T)1, (T)0); idx[n++] = 1; gcol[n] = mk((T)0, (T)0, (T)1); idx[n++] = 2;
     gcol[n] = cross(g.RB.c0, rB); idx[n++] = 3; gcol[n] = cross(g.RB.c1, rB); idx[n++] = 4; gcol[n] = cross(g.RB.c2, rB); idx[n++] = 5;
-    gcol[n] = cross(g.aw[ty], P - g.hw[ty]); idx[n++] = 6 + ty;
-    gcol[n] = mk((T)-1, (T)0, (T)0); idx[n++] = 9; gcol[n] = mk((T)0, (T)-1, (T)0); idx[n++] = 10; gcol[n] = mk((T)0, (T)0, (T)-1); idx[n++] = 11;
-    gcol[n] = cross(rL, g.RL.c0); idx[n++] = 12; gcol[n] = cross(rL, g.RL.c1); idx[n++] = 13; gcol[n] = cross(rL, g.RL.c2); idx[n++] = 14;
+    if (wi >= 0) { gcol[n] = cross(g.aw[wi], P - g.hw[wi]); idx[n++] = 6 + wi; }
+    if (ctHasBall(ty)) {
+      gcol[n] = mk((T)-1, (T)0, (T)0); idx[n++] = 9; gcol[n] = mk((T)0, (T)-1, (T)0); idx[n++] = 10; gcol[n] = mk((T)0, (T)0, (T)-1); idx[n++] = 11;
+      gcol[n] = cross(rL, g.RL.c0); idx[n++] = 12; gcol[n] = cross(rL, g.RL.c1); idx[n++] = 13; gcol[n] = cross(rL, g.RL.c2); idx[n++] = 14;
+    }
   } else {
     gcol[n] = mk((T)1, (T)0, (T)0); idx[n++] = 9; gcol[n] = mk((T)0, (T)1, (T)0); idx[n++] = 10; gcol[n] = mk((T)0, (T)0, (T)1); idx[n++] = 11;
     gcol[n] = cross(g.RL.c0, rL); idx[n++] = 12; gcol[n] = cross(g.RL.c1, rL); idx[n++] = 13; gcol[n] = cross(g.RL.c2, rL); idx[n++] = 14;
@@ -578,7 +753,7 @@ template <typename T> struct Newton {
     for (int c = 0; c < s.nc; c++) {
       cs += coneUpdate(mc, s, c, s.cJar[c], true);
       if (s.cstate[c] == 1) {
-        const int k = s.ctype[c] == 3 ? 1 : 0; const T D0 = s.cD[c];
+        const int k = ctFric(s.ctype[c]); const T D0 = s.cD[c];
         const T W[6] = {D0, D0 * mc.d1r[k], D0 * mc.d2r[k], 0, 0, 0};
         addContactHessian(g, s, c, W);
       } else if (s.cstate[c] == 2) addContactHessian(g, s, c, s.cHc[c]);
@@ -597,7 +772,7 @@ template <typename T> struct Newton {
     LsPt<T> p; p.alpha = alpha;
     p.cost = qG0 + alpha * (qG1 + alpha * qG2); p.d1 = qG1 + (T)2 * alpha * qG2; p.d2 = (T)2 * qG2;
     for (int c = 0; c < s.nc; c++) {
-      const int k = s.ctype[c] == 3 ? 1 : 0;
+      const int k = ctFric(s.ctype[c]);
       const T mu = mc.mu[k], f1 = mc.f1[k], f2 = mc.f2[k];
       const T* jr = s.cJar[c]; const T* jv = s.cJv[c];
       const T D0 = s.cD[c], D1 = D0 * mc.d1r[k], D2 = D0 * mc.d2r[k];

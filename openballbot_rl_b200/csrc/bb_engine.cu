@@ -56,9 +56,10 @@ struct EnvParams {
   int max_ep_steps; float max_tilt, max_wheel_vel;
   int reward_type; float reward_scale, action_reg, survival, tdir[2], goal[2], dist_scale;
   float zscale; int terrain_type, terrain_seed; unsigned long long seed;
-  int auto_reset, hf_per_env, solver_mode;
+  int auto_reset, hf_mode, solver_mode, seed_stream;   // hf_mode: 0 one shared field, 1 one field per env, 2 table of Perlin fields indexed by seed
   float pscale, ppers, plac, pamp; int poct;
 };
+enum { HF_SHARED = 0, HF_PER_ENV = 1, HF_TABLE = 2 };
 struct DevState {
   void* st;        // T[N][SST]
   void* camq;      // T[N][CST]  configuration the cameras see (last RK stage / reset state)
@@ -67,7 +68,8 @@ struct DevState {
   void* ctx;       // T[N][bbg::CTXN] split-phase step: solver input (M, qfrc_smooth, qacc_smooth, contact records)
   int* meta;       // int[N][4]       split-phase step: ncon, nw, Newton iterations, flags
   int* step_count; int* cam_steps; unsigned* episode; int* tseed;
-  float* hfield;   // [N][HF_CELLS] (hf_per_env) or [HF_CELLS]
+  float* hfield;   // [N][HF_CELLS] (HF_PER_ENV), [HF_CELLS] (HF_SHARED) or [table_n][HF_CELLS] (HF_TABLE)
+  unsigned long long* rng;   // [N][5] numpy PCG64 state per env (seed_stream = 1): state hi/lo, inc hi/lo, has_uint32 | uinteger << 32
   float* ptab;     // [2][293] circle coordinates of the tiled simplex noise (sin, cos) per grid index
   float* ep_ret; int* ep_len;
   int* counters;   // [0] reset-list length, [1] refresh-list length, [2] depth work-unit cursor
@@ -82,11 +84,45 @@ constexpr int WORK_BINS = 64;
 __device__ __forceinline__ unsigned long long splitmix(unsigned long long x) {
   x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31);
 }
-// counter-based replacement of self._np_random.integers(0, 10000) (ballbot_env.py:506): U{0..9999} per (env, episode)
-__device__ __forceinline__ int drawTerrainSeed(const EnvParams& p, int env, unsigned episode) {
+// numpy's PCG64 (XSL-RR 128/64) + Generator.integers(0, 10000): 32-bit halves of the 64-bit outputs are consumed low half first
+// (has_uint32 / uinteger buffering of pcg64_next32), bounded by Lemire's multiply-and-reject (buffered_bounded_lemire_uint32)
+__device__ __forceinline__ unsigned pcg64Next32(unsigned long long* st) {
+  const unsigned long long buf = st[4];
+  if (buf & 1ull) { st[4] = 0; return (unsigned)(buf >> 32); }
+  const unsigned __int128 mult = ((unsigned __int128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+  unsigned __int128 state = ((unsigned __int128)st[0] << 64) | st[1];
+  const unsigned __int128 inc = ((unsigned __int128)st[2] << 64) | st[3];
+  state = state * mult + inc;
+  const unsigned long long hi = (unsigned long long)(state >> 64), lo = (unsigned long long)state;
+  st[0] = hi; st[1] = lo;
+  const unsigned long long x = hi ^ lo; const unsigned r = (unsigned)(hi >> 58);
+  const unsigned long long out = (x >> r) | (x << ((64u - r) & 63u));
+  st[4] = 1ull | ((out >> 32) << 32);
+  return (unsigned)out;
+}
+__device__ __forceinline__ int pcg64Integers10000(unsigned long long* st) {
+  const unsigned rng = 9999u, excl = 10000u;
+  unsigned long long m = (unsigned long long)pcg64Next32(st) * excl;
+  unsigned left = (unsigned)m;
+  if (left < excl) {
+    const unsigned thr = (0xFFFFFFFFu - rng) % excl;
+    while (left < thr) { m = (unsigned long long)pcg64Next32(st) * excl; left = (unsigned)m; }
+  }
+  return (int)(m >> 32);
+}
+// r_seed = self._np_random.integers(0, 10000) (ballbot_env.py:506): either the numpy-compatible per-env stream or a counter-based
+// hash with the same U{0..9999} law per (env, episode)
+__device__ __forceinline__ int drawTerrainSeed(const EnvParams& p, const DevState& d, int env, unsigned episode) {
   if (p.terrain_seed >= 0) return p.terrain_seed;
+  if (p.seed_stream == 1) return pcg64Integers10000(d.rng + 5 * (size_t)env);
   unsigned long long h = splitmix(p.seed ^ splitmix((unsigned long long)(p.env_offset + env) * 0x100000001B3ull + episode));
   return (int)(h % 10000ull);
+}
+// heightfield of env i
+__device__ __forceinline__ const float* hfOf(const EnvParams& p, const DevState& d, int i) {
+  if (p.hf_mode == HF_PER_ENV) return d.hfield + (size_t)i * HF_CELLS;
+  if (p.hf_mode == HF_TABLE) return d.hfield + (size_t)(p.terrain_seed >= 0 ? 0 : d.tseed[i]) * HF_CELLS;
+  return d.hfield;
 }
 
 // --------------------------------------------------------------------------------------------- step
@@ -114,7 +150,7 @@ __global__ void __launch_bounds__(64) k_step(EnvParams p, DevState d, const floa
   int status = 0;
   if (!bad) {
     Scratch<T> s;
-    const float* hf = d.hfield + (p.hf_per_env ? (size_t)i * HF_CELLS : 0);
+    const float* hf = hfOf(p, d, i);
     rk4Step(cmc<T>(), qpos, qvel, warm, ctrl, hf, (T)p.zscale, s, &kin, qlast);
     for (int k = 0; k < NQ; k++) bad |= !(babs(qpos[k]) < (T)1e10);
     for (int k = 0; k < NV; k++) bad |= !(babs(qvel[k]) < (T)1e10);
@@ -171,7 +207,7 @@ __global__ void __launch_bounds__(64) k_step(EnvParams p, DevState d, const floa
   d.step_count[i] = sc; d.cam_steps[i] = cs; d.ep_ret[i] = eret; d.ep_len[i] = elen;
   if (term && p.auto_reset) {
     const unsigned ep = d.episode[i] + 1; d.episode[i] = ep;
-    d.tseed[i] = drawTerrainSeed(p, i, ep);
+    d.tseed[i] = drawTerrainSeed(p, d, i, ep);
     d.reset_list[atomicAdd(&d.counters[0], 1)] = i;
   } else if (refresh) {
     T* cq = (T*)d.camq;
@@ -288,7 +324,7 @@ __device__ __forceinline__ void stepFinish(const EnvParams& p, const DevState& d
     d.step_count[i] = sc; d.cam_steps[i] = cs; d.ep_ret[i] = eret; d.ep_len[i] = elen;
     if (term && p.auto_reset) {
       const unsigned ep = d.episode[i] + 1; d.episode[i] = ep;
-      d.tseed[i] = drawTerrainSeed(p, i, ep);
+      d.tseed[i] = drawTerrainSeed(p, d, i, ep);
       d.reset_list[atomicAdd(&d.counters[0], 1)] = i;
     } else if (refresh) d.refresh_list[atomicAdd(&d.counters[1], 1)] = i;
   }
@@ -309,7 +345,7 @@ __global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCK
   int ncmax = 0, nit = 0;
   if (!bad) {
     int cs; const bool refresh = cameraRefresh(p, d, i, cs);
-    const float* hf = d.hfield + (p.hf_per_env ? (size_t)i * HF_CELLS : 0);
+    const float* hf = hfOf(p, d, i);
     T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
     T* cq = refresh ? (T*)d.camq + (size_t)i * CST : nullptr;
     bbg::gRk4(cmc<T>(), S, hf, (T)p.zscale, gs, cq, L, warm, p.solver_mode != 0, ncmax, nit);
@@ -388,8 +424,8 @@ k_stage(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io, in
   }
   if (stage == 4) return;
   // ---- mj_forward up to the solver (CTA-synchronised phases)
-  const float* hf = d.hfield + (p.hf_per_env ? (size_t)i * HF_CELLS : 0);
-  if (!skip && p.hf_per_env && L.gl < 8) {
+  const float* hf = hfOf(p, d, i);
+  if (!skip && p.hf_mode != HF_SHARED && L.gl < 8) {
     // the ~7 x 7 heights under the ball are first touched by the collision phase, ~2 k instructions from here: start the
     // DRAM/L2 fetch of the 8 row segments now (the ball moves less than a cell per stage, so the stage configuration is enough)
     const T gsc = (T)(HN - 1) / ((T)2 * mc.hx);
@@ -400,8 +436,8 @@ k_stage(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io, in
     asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 7));
   }
   T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
-  int nw; T qfs, qas;
-  const int ncon = bbg::gForwardPre(mc, S, hf, (T)p.zscale, gs, L, stage == 3, nw, qfs, qas, skip, BB_WPB_STAGE > 1);
+  int nw, nd; T qfs, qas;
+  const int ncon = bbg::gForwardPre(mc, S, hf, (T)p.zscale, gs, L, stage == 3, nw, nd, qfs, qas, skip, BB_WPB_STAGE > 1);
   if (skip) return;
   if (dof) {
     rk[bbg::RK_XV + L.gl] = xv;
@@ -417,10 +453,10 @@ k_stage(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io, in
     if (cameraRefresh(p, d, i, cs)) { T* cq = (T*)d.camq + (size_t)i * CST; for (int k = L.gl; k < NQ; k += bbg::G) cq[k] = S.xq[k]; }
   }
   if (L.gl == 0) {
-    meta[bbg::META_NCON] = ncon; meta[bbg::META_NW] = nw;
+    meta[bbg::META_NCON] = ncon; meta[bbg::META_NW] = nw | (nd << 8);
     if (ncon > ncmax) meta[bbg::META_FLAGS] = ncon << 8;
   }
-  if (ncon > 0) bbg::ctxSave((T*)d.ctx + (size_t)i * bbg::CTXN, S, ncon, nw, qfs, qas, L);
+  if (ncon > 0) bbg::ctxSave((T*)d.ctx + (size_t)i * bbg::CTXN, S, ncon, nd, qfs, qas, L);
 }
 // k_newton<T>: constraint solve of one RK stage for the envs that have contacts, in work-sorted order.  Uniform-warp
 // solver (GNewton<T, true>): a warp leaves only when neither of its envs has contacts; otherwise both groups run the solver
@@ -434,21 +470,21 @@ __global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCK
   const bool live = slot < p.N;
   const int i = d.order[live ? slot : p.N - 1];
   int* meta = d.meta + 4 * (size_t)i;
-  int ncon = meta[bbg::META_NCON], nw = meta[bbg::META_NW];
+  int ncon = meta[bbg::META_NCON], nw = meta[bbg::META_NW] & 0xff, nd = meta[bbg::META_NW] >> 8;
   const bool act = live && ncon > 0 && !(meta[bbg::META_FLAGS] & 1);
   if (!__any_sync(0xffffffffu, act)) return;
-  if (!act) { ncon = 0; nw = 0; }                      // passenger group: empty contact loops, results discarded
+  if (!act) { ncon = 0; nw = 0; nd = 0; }              // passenger group: empty contact loops, results discarded
   bbg::GS<T>& S = reinterpret_cast<bbg::GS<T>*>(smem_raw)[warp * bbg::EPW + grp];
   T* rk = (T*)d.rk + (size_t)i * bbg::RKN;
   T qfs = 0, qas = 0, warm = 0;
   if (act) {
-    bbg::ctxLoad((const T*)d.ctx + (size_t)i * bbg::CTXN, S, ncon, nw, qfs, qas, L);
+    bbg::ctxLoad((const T*)d.ctx + (size_t)i * bbg::CTXN, S, ncon, nd, qfs, qas, L);
     warm = L.gl < NV ? rk[bbg::RK_WARM + L.gl] : (T)0;
   }
   __syncwarp();
   T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
   bbg::Ln LU = L; LU.mask = 0xffffffffu;               // compile-time constant member mask for everything inlined below
-  bbg::GNewton<T, true> nwt(cmc<T>(), S, gs, LU, ncon, nw, p.solver_mode != 0, qfs, qas);
+  bbg::GNewton<T, true> nwt(cmc<T>(), S, gs, LU, ncon, nw, nd, p.solver_mode != 0, qfs, qas);
   int niter;
   const T qacc = nwt.run(warm, niter, act);
   if (!act) return;
@@ -459,7 +495,7 @@ __global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCK
   if (L.gl == 0) meta[bbg::META_NIT] += niter + (nwt.nevals << 12);   // low 12 bits: Newton iterations, above: line-search evaluations
 }
 // forward-dynamics probe through the group path (same outputs as k_probe)
-template <typename T> __global__ void k_probe_warp(EnvParams p, DevState d, int env, const double* ctrl3, double* out) {
+template <typename T> __global__ void k_probe_warp(EnvParams p, DevState d, int env, const double* ctrl3, double* out, double* dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   if ((threadIdx.x & 31) >= bbg::G) return;
   const bbg::Ln L = bbg::makeLn();
@@ -471,20 +507,23 @@ template <typename T> __global__ void k_probe_warp(EnvParams p, DevState d, int 
   for (int k = L.gl; k < bbg::MSZ; k += bbg::G) S.M[k] = 0;
   if (L.gl < 3) S.ctrl[L.gl] = (T)ctrl3[L.gl];
   __syncwarp(L.mask);
-  const float* hf = d.hfield + (p.hf_per_env ? (size_t)env * HF_CELLS : 0);
+  const float* hf = hfOf(p, d, env);
   int ncon, niter; T qas, qfs;
-  const T qacc = bbg::gForward(cmc<T>(), S, hf, (T)p.zscale, (T*)d.gscr + (size_t)env * bbg::GSCR, L, warm, p.solver_mode != 0, true, ncon, niter, &qas, &qfs);
+  const T qacc = bbg::gForward<T, true>(cmc<T>(), S, hf, (T)p.zscale, (T*)d.gscr + (size_t)env * bbg::GSCR, L, warm, p.solver_mode != 0, true, ncon, niter, &qas, &qfs, dbg);
   if (L.gl < NV) { out[L.gl] = (double)qacc; out[15 + L.gl] = (double)qas; out[30 + L.gl] = (double)qfs; }
   if (L.gl == 0) { out[45] = ncon; out[46] = niter; }
 }
 
 // explicit reset: mask -> reset list (+ new terrain seed)
-__global__ void k_mask_to_list(EnvParams p, DevState d, const uint8_t* __restrict__ mask) {
+__global__ void k_mask_to_list(EnvParams p, DevState d, const uint8_t* __restrict__ mask, const int* __restrict__ seeds) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.N) return;
   if (mask && !mask[i]) return;
   const unsigned ep = d.episode[i] + 1; d.episode[i] = ep;
-  d.tseed[i] = drawTerrainSeed(p, i, ep);
+  if (seeds) {   // caller-fixed r_seed (replay); the table only holds seeds 0 .. BB_PERLIN_SEEDS - 1
+    const int sd = seeds[i];
+    d.tseed[i] = p.hf_mode == HF_TABLE ? (int)((unsigned)sd % (unsigned)BB_PERLIN_SEEDS) : sd;
+  } else d.tseed[i] = drawTerrainSeed(p, d, i, ep);
   d.reset_list[atomicAdd(&d.counters[0], 1)] = i;
 }
 // k_begin_step, one block of WORK_BINS threads: clears the work-list counters and turns the key histogram of the previous step into
@@ -565,11 +604,18 @@ __device__ float simplex4(const int* __restrict__ perm, float x, float y, float 
 }
 // snoise2(x, y, octaves, persistence, lacunarity, repeatx=1024, repeaty=1024, base=seed): tiled branch = 4-D fBm on two circles.
 // The circle coordinates depend on the grid index only (not on the seed): perlinCircle(idx) = (sin, cos) * R of one axis.
+// fast_sin / fast_cos of noise/_noise.h: argument in half-turns, wrapped to [-1, 1] by the 1.5 * 2^24 float trick, parabola + correction
+__device__ __forceinline__ float noiseFastSin(float x) {
+  const float z = FA(x, 25165824.0f);
+  x = FS(x, FS(z, 25165824.0f));
+  const float y = FS(x, FM(x, fabsf(x)));
+  return FM(y, FA(3.1f, FM(3.6f, fabsf(y))));
+}
 __device__ __forceinline__ void perlinCircle(int idx, float scale, float& s, float& c) {
   const float x = (float)((double)idx / (double)scale);
   const float rr = (float)(1024.0 * 0.3183098861837907 * 0.5);
   const float xf = (float)((double)x * 2.0 / 1024.0);
-  s = FM(sinf(xf), rr); c = FM(cosf(xf), rr);
+  s = FM(noiseFastSin(xf), rr); c = FM(noiseFastSin(FA(xf, 0.5f)), rr);
 }
 __device__ float perlinFbm(const int* __restrict__ perm, float si, float ci, float sj, float cj, int seed, int oct, float pers, float lac, float amp) {
   const float x = si, y = sj, z = FA((float)seed, ci), w = FA((float)seed, cj);
@@ -590,6 +636,7 @@ __device__ float perlinHeight(const int* __restrict__ perm, int i, int j, int se
 #undef FA
 #undef FS
 // circle coordinates of the 293 grid indices (engine constant: depends on perlin_scale only)
+__global__ void k_iota(int n, int first, int* __restrict__ out) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = first + i; }
 __global__ void k_perlin_table(float scale, float* __restrict__ tab) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < HN) perlinCircle(i, scale, tab[i], tab[HN + i]);
@@ -632,7 +679,7 @@ __global__ void k_reset(EnvParams p, DevState d, bb_io io) {
   if (k >= d.counters[0]) return;
   const int i = d.reset_list[k];
   // spawn height: max of hfield rows/cols 140..151 (ballbot_env.py:546-563, cell_size = 5/293 quirk)
-  const float* hf = d.hfield + (p.hf_per_env ? (size_t)i * HF_CELLS : 0);
+  const float* hf = hfOf(p, d, i);
   float mx = -1e30f;
   for (int r = 140; r < 152; r++) for (int c = 140; c < 152; c++) mx = fmaxf(mx, hf[r * HN + c]);
   const double off = (double)mx * (double)p.zscale + 0.01;
@@ -820,7 +867,7 @@ __global__ void __launch_bounds__(256) k_depth(EnvParams p, DevState d, const in
     __syncwarp();
     if (lane < 9) buildScene(c_mc32, cfgq, cfg_stride, env, sc, lane);
     __syncwarp();
-    const float* hf = d.hfield + (p.hf_per_env ? (size_t)env * HF_CELLS : 0);
+    const float* hf = hfOf(p, d, env);
     float* out = (cam ? img1 : img0) + (size_t)env * npix;
     const F3 o = sc.cam_o[cam];
     const int tend = min(tiles, (part + 1) * chunk);
@@ -870,6 +917,10 @@ __global__ void k_scatter_hfield(const int* __restrict__ ids, int n, const float
   const int k = (int)(t / HF_CELLS); const int cell = (int)(t - (size_t)k * HF_CELLS);
   dst[(size_t)ids[k] * HF_CELLS + cell] = src[t];
 }
+__global__ void k_get_hfield(EnvParams p, DevState d, int env, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < HF_CELLS) out[c] = hfOf(p, d, env)[c];
+}
 __global__ void k_add_reward(int N, float scale, const float* __restrict__ term, bb_io io, float* ep_ret) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= N) return;
   const float add = term[i] * scale;
@@ -886,7 +937,7 @@ __global__ void k_pack_obs16(int N, bb_io io, float* __restrict__ obs16) {
 }
 
 // single forward-dynamics evaluation at the current state of one env: solver / contact probe for parity tests
-template <typename T> __global__ void k_probe(EnvParams p, DevState d, int env, const double* ctrl3, double* out, double* cdist, double* cpos, double* cframe) {
+template <typename T> __global__ void k_probe(EnvParams p, DevState d, int env, const double* ctrl3, double* out, double* crows) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const T* st = (const T*)d.st;
   T qpos[NQ], qvel[NV], warm[NV], ctrl[3], qacc[NV];
@@ -894,17 +945,19 @@ template <typename T> __global__ void k_probe(EnvParams p, DevState d, int env, 
   for (int k = 0; k < NV; k++) { qvel[k] = st[(size_t)env * SST + NQ + k]; warm[k] = st[(size_t)env * SST + NQ + NV + k]; }
   for (int k = 0; k < 3; k++) ctrl[k] = (T)ctrl3[k];
   Scratch<T> s; KinOut<T> kin;
-  const float* hf = d.hfield + (p.hf_per_env ? (size_t)env * HF_CELLS : 0);
+  const float* hf = hfOf(p, d, env);
   forwardDynamics(cmc<T>(), qpos, qvel, ctrl, warm, hf, (T)p.zscale, s, qacc, &kin);
   for (int k = 0; k < NV; k++) { out[k] = (double)qacc[k]; out[15 + k] = (double)s.qas[k]; out[30 + k] = (double)s.qfs[k]; }
   out[45] = kin.ncon; out[46] = kin.niter; out[47] = (double)cmc<T>().timestep; out[48] = cmc<T>().iterations; out[49] = cmc<T>().ls_iterations;
   out[50] = (double)cmc<T>().meaninertia; out[51] = (double)cmc<T>().K; out[52] = (double)cmc<T>().B; out[53] = (double)cmc<T>().dA[3];
   for (int c = 0; c < s.nc; c++) {
-    cdist[c] = (double)s.cDist[c];
-    for (int j = 0; j < 3; j++) cpos[3 * c + j] = (double)s.cP[c][j];
-    for (int j = 0; j < 9; j++) cframe[9 * c + j] = (double)s.cF[c][j];
+    double* o = crows + BB_CONTACT_STRIDE * c;
+    o[0] = s.ctype[c]; o[1] = (double)s.cDist[c];
+    for (int j = 0; j < 3; j++) o[2 + j] = (double)s.cP[c][j];
+    for (int j = 0; j < 9; j++) o[5 + j] = (double)s.cF[c][j];
   }
 }
+__global__ void k_probe_count(const double* out, int* ncon) { *ncon = (int)out[45]; }
 
 const unsigned char h_perm[256] = {
     151, 160, 137, 91, 90, 15, 131, 13, 201, 95, 96, 53, 194, 233, 7, 225, 140, 36, 103, 30, 69, 142, 8, 99, 37, 240, 21, 10, 23,
@@ -928,6 +981,8 @@ struct bb_engine {
   EnvParams p;
   DevState d;
   int N;
+  int table_n;                     // fields in the Perlin table (HF_TABLE)
+  double* probe_out;               // scratch of bb_get_contacts
   size_t tsize;
   int64_t launches;
   char err[256];
@@ -953,6 +1008,13 @@ struct bb_engine {
   } while (0)
 
 static int fail(bb_engine* e, int code, const char* msg) { snprintf(e->err, sizeof(e->err), "%s", msg); return code; }
+// Every entry point runs on the engine's own device whatever the caller's current device is, and leaves the caller's
+// current device untouched (two engines on different GPUs in one process; torch's current device != cfg.device).
+struct DevGuard {
+  int prev; bool sw;
+  explicit DevGuard(int dev) : prev(-1), sw(false) { if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) { cudaSetDevice(dev); sw = true; } }
+  ~DevGuard() { if (sw) cudaSetDevice(prev); }
+};
 static inline int blocksFor(int n, int b) { return (n + b - 1) / b; }
 
 static int checkIo(bb_engine* e, const bb_io* io) {
@@ -969,7 +1031,7 @@ static inline int depthGrid(int N) { const int need = (N * 2 * DEPTH_PARTS + 7) 
 static int launchResetAndRender(bb_engine* e, const bb_io* io, cudaStream_t s, bool do_reset, cudaEvent_t* ev = nullptr) {
   const int N = e->N;
   if (do_reset) {
-    if (e->cfg.terrain_type == BB_TERRAIN_PERLIN) {
+    if (e->cfg.terrain_type == BB_TERRAIN_PERLIN && e->p.hf_mode == HF_PER_ENV) {
       dim3 grid(blocksFor(HF_CELLS, 256), N < 128 ? N : 128);
       k_terrain<<<grid, 256, 0, s>>>(e->p, e->d, e->d.reset_list, e->d.counters, 0, nullptr, nullptr);
       e->launches++;
@@ -1001,16 +1063,22 @@ void bb_default_config(bb_config* c) {
   c->max_ep_steps = 4000; c->max_allowed_tilt = 20.f; c->max_wheel_velocity = 10.f;
   c->reward_type = BB_REWARD_DIRECTIONAL; c->reward_scale = 0.01f; c->action_reg_coef = -0.0001f; c->survival_bonus = 0.02f;
   c->target_direction[0] = 0.f; c->target_direction[1] = 1.f; c->goal_position[0] = 0.f; c->goal_position[1] = 0.f; c->distance_scale = 1.f;
-  c->seed = 0; c->auto_reset = 1; c->step_kernel = 0; c->solver_mode = 0;
+  c->seed = 0; c->auto_reset = 1; c->step_kernel = 0; c->solver_mode = 0; c->perlin_table = -1; c->seed_stream = 0;
 }
 
 const char* bb_last_error(const bb_engine* e) { return e ? e->err : g_create_error; }
 int bb_num_envs(const bb_engine* e) { return e ? e->N : 0; }
 int64_t bb_launch_count(const bb_engine* e) { return e ? e->launches : 0; }
 
-int bb_model_constants(double* dA4, double* meaninertia, double* masses3) {
+const char* bb_build_info(void) {
+#ifndef BB_SRC_HASH
+#define BB_SRC_HASH "unknown"
+#endif
+  return "libballbot_b200 abi 2 built " __DATE__ " " __TIME__ " src " BB_SRC_HASH;
+}
+int bb_model_constants(double* dA12, double* meaninertia, double* masses3) {
   ModelConst<double> m; buildModelConst(m);
-  if (dA4) for (int i = 0; i < 4; i++) dA4[i] = m.dA[i];
+  if (dA12) for (int i = 0; i < NCT; i++) dA12[i] = m.dA[i];
   if (meaninertia) *meaninertia = m.meaninertia;
   if (masses3) { masses3[0] = m.m0; masses3[1] = m.mw; masses3[2] = m.mL; }
   return BB_OK;
@@ -1020,7 +1088,8 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   if (!cfg || !out) { snprintf(g_create_error, sizeof(g_create_error), "bb_create: NULL argument"); return BB_ERR_INVALID; }
   *out = nullptr;
   if (cfg->abi_version != BB_ABI_VERSION || cfg->num_envs < 1 || (cfg->precision != 32 && cfg->precision != 64) || cfg->im_h < 1 || cfg->im_w < 1 ||
-      cfg->terrain_type < 0 || cfg->terrain_type > 3 || cfg->reward_type < 0 || cfg->reward_type > 2 || cfg->camera_frame_rate <= 0.f) {
+      cfg->terrain_type < 0 || cfg->terrain_type > 3 || cfg->reward_type < 0 || cfg->reward_type > 2 || cfg->camera_frame_rate <= 0.f ||
+      cfg->perlin_table < -1 || cfg->perlin_table > 1 || cfg->seed_stream < 0 || cfg->seed_stream > 1 || cfg->perlin_octaves < 1) {
     snprintf(g_create_error, sizeof(g_create_error), "bb_create: invalid config (abi %d, num_envs %d, precision %d)", cfg->abi_version, cfg->num_envs, cfg->precision);
     return BB_ERR_INVALID;
   }
@@ -1036,7 +1105,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   const int N = e->N;
   auto bail = [&](int code) { snprintf(g_create_error, sizeof(g_create_error), "%s", e->err); bb_destroy(e); return code; };
 #define BB_CUDA_C(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { snprintf(e->err, sizeof(e->err), "%s failed: %s", #call, cudaGetErrorString(_e)); return bail(BB_ERR_CUDA); } } while (0)
-  BB_CUDA_C(cudaSetDevice(cfg->device));
+  DevGuard guard(cfg->device);
   {
     ModelConst<double> m64; buildModelConst(m64);
     ModelConst<float> m32; narrowModel(m64, m32);
@@ -1056,7 +1125,14 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   p.reward_type = cfg->reward_type; p.reward_scale = cfg->reward_scale; p.action_reg = cfg->action_reg_coef; p.survival = cfg->survival_bonus;
   p.tdir[0] = cfg->target_direction[0]; p.tdir[1] = cfg->target_direction[1]; p.goal[0] = cfg->goal_position[0]; p.goal[1] = cfg->goal_position[1];
   p.dist_scale = cfg->distance_scale; p.zscale = cfg->hfield_zscale; p.terrain_type = cfg->terrain_type; p.terrain_seed = cfg->terrain_seed;
-  p.seed = cfg->seed; p.auto_reset = cfg->auto_reset; p.solver_mode = cfg->solver_mode; p.hf_per_env = cfg->terrain_type == BB_TERRAIN_PERLIN || cfg->terrain_type == BB_TERRAIN_EXTERNAL;
+  p.seed = cfg->seed; p.auto_reset = cfg->auto_reset; p.solver_mode = cfg->solver_mode; p.seed_stream = cfg->seed_stream;
+  p.hf_mode = cfg->terrain_type == BB_TERRAIN_EXTERNAL ? HF_PER_ENV : HF_SHARED;
+  if (cfg->terrain_type == BB_TERRAIN_PERLIN) {
+    // a fixed terrain seed means ONE field for every env and every episode; random seeds mean at most BB_PERLIN_SEEDS fields
+    const bool table = cfg->terrain_seed >= 0 || cfg->perlin_table == 1 || (cfg->perlin_table == -1 && N >= 2048);
+    p.hf_mode = table ? HF_TABLE : HF_PER_ENV;
+    e->table_n = table ? (cfg->terrain_seed >= 0 ? 1 : BB_PERLIN_SEEDS) : 0;
+  }
   p.pscale = cfg->perlin_scale; p.ppers = cfg->perlin_persistence; p.plac = cfg->perlin_lacunarity; p.pamp = cfg->perlin_amplitude; p.poct = cfg->perlin_octaves;
   e->tsize = cfg->precision == 64 ? 8 : 4;
   DevState& d = e->d;
@@ -1084,11 +1160,25 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   }
   k_init_order<<<blocksFor(N > 2 * WORK_BINS ? N : 2 * WORK_BINS, 256), 256>>>(N, d);
   BB_CUDA_C(cudaMalloc(&d.reset_list, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.refresh_list, sizeof(int) * N));
-  const size_t hfbytes = sizeof(float) * HF_CELLS * (p.hf_per_env ? (size_t)N : 1);
+  const size_t hfbytes = sizeof(float) * HF_CELLS * (p.hf_mode == HF_PER_ENV ? (size_t)N : (p.hf_mode == HF_TABLE ? (size_t)e->table_n : 1));
   BB_CUDA_C(cudaMalloc(&d.hfield, hfbytes));
-  BB_CUDA_C(cudaMemset(d.hfield, 0, hfbytes));
+  if (p.hf_mode != HF_TABLE) BB_CUDA_C(cudaMemset(d.hfield, 0, hfbytes));
   BB_CUDA_C(cudaMalloc(&d.ptab, sizeof(float) * 2 * HN));
   k_perlin_table<<<blocksFor(HN, 128), 128>>>(cfg->perlin_scale, d.ptab);
+  BB_CUDA_C(cudaMalloc(&d.rng, sizeof(unsigned long long) * 5 * (size_t)N));
+  BB_CUDA_C(cudaMemset(d.rng, 0, sizeof(unsigned long long) * 5 * (size_t)N));
+  BB_CUDA_C(cudaMalloc(&e->probe_out, sizeof(double) * 64));
+  if (p.hf_mode == HF_TABLE) {
+    // every Perlin field the reference can ever draw (r_seed in 0 .. 9999, ballbot_env.py:506), generated once by the same
+    // kernel that regenerates per-env fields: resets then only select a field, and HBM use no longer grows with num_envs
+    int* seeds = nullptr;
+    BB_CUDA_C(cudaMalloc(&seeds, sizeof(int) * e->table_n));
+    k_iota<<<blocksFor(e->table_n, 256), 256>>>(e->table_n, cfg->terrain_seed >= 0 ? cfg->terrain_seed : 0, seeds);
+    dim3 grid(blocksFor(HF_CELLS, 256), e->table_n < 592 ? e->table_n : 592);
+    k_terrain<<<grid, 256>>>(p, d, nullptr, nullptr, e->table_n, seeds, d.hfield);
+    BB_CUDA_C(cudaDeviceSynchronize());
+    cudaFree(seeds);
+  }
   BB_CUDA_C(cudaMemset(d.st, 0, e->tsize * SST * N)); BB_CUDA_C(cudaMemset(d.camq, 0, e->tsize * CST * N));
   BB_CUDA_C(cudaMemset(d.step_count, 0, sizeof(int) * N)); BB_CUDA_C(cudaMemset(d.cam_steps, 0, sizeof(int) * N));
   BB_CUDA_C(cudaMemset(d.episode, 0, sizeof(unsigned) * N)); BB_CUDA_C(cudaMemset(d.tseed, 0, sizeof(int) * N));
@@ -1102,10 +1192,11 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
 
 int bb_destroy(bb_engine* e) {
   if (!e) return BB_OK;
+  DevGuard guard(e->cfg.device);
   DevState& d = e->d;
   cudaFree(d.st); cudaFree(d.camq); cudaFree(d.gscr); cudaFree(d.rk); cudaFree(d.ctx); cudaFree(d.meta); cudaFree(d.step_count); cudaFree(d.cam_steps); cudaFree(d.episode); cudaFree(d.tseed);
   cudaFree(d.work); cudaFree(d.order); cudaFree(d.bins);
-  cudaFree(d.ep_ret); cudaFree(d.ep_len); cudaFree(d.counters); cudaFree(d.reset_list); cudaFree(d.refresh_list); cudaFree(d.hfield); cudaFree(d.ptab);
+  cudaFree(d.ep_ret); cudaFree(d.ep_len); cudaFree(d.counters); cudaFree(d.reset_list); cudaFree(d.refresh_list); cudaFree(d.hfield); cudaFree(d.ptab); cudaFree(d.rng); cudaFree(e->probe_out);
   if (e->prof_ev) { for (int i = 0; i < 5 * e->prof_cap; i++) cudaEventDestroy(e->prof_ev[i]); free(e->prof_ev); }
   if (e->host_ready) {
     cudaFreeHost(e->h_act); cudaFree(e->d_act); cudaFree(e->d_obs16); cudaFreeHost(e->h_obs16); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_pos2d);
@@ -1121,22 +1212,32 @@ int bb_destroy(bb_engine* e) {
   return BB_OK;
 }
 
-int bb_reset(bb_engine* e, const uint8_t* mask_dev, const bb_io* io, void* stream) {
+int bb_reset(bb_engine* e, const uint8_t* mask_dev, const int32_t* seeds_dev, const bb_io* io, void* stream) {
   if (!e) return BB_ERR_INVALID;
   int rc = checkIo(e, io); if (rc) return rc;
+  DevGuard guard(e->cfg.device);
   cudaStream_t s = (cudaStream_t)stream;
   const int N = e->N;
   k_clear_counters<<<1, 1, 0, s>>>(e->d);
-  k_mask_to_list<<<blocksFor(N, 256), 256, 0, s>>>(e->p, e->d, mask_dev);
+  k_mask_to_list<<<blocksFor(N, 256), 256, 0, s>>>(e->p, e->d, mask_dev, seeds_dev);
   e->launches += 2;
   rc = launchResetAndRender(e, io, s, true); if (rc) return rc;
   BB_CUDA(cudaGetLastError());
   return BB_OK;
 }
 
+int bb_set_rng_state(bb_engine* e, const uint64_t* state_dev, void* stream) {
+  if (!e || !state_dev) return BB_ERR_INVALID;
+  if (e->cfg.seed_stream != 1) return fail(e, BB_ERR_STATE, "bb_set_rng_state: engine was created with seed_stream = 0 (counter-based terrain seeds)");
+  DevGuard guard(e->cfg.device);
+  BB_CUDA(cudaMemcpyAsync(e->d.rng, state_dev, sizeof(unsigned long long) * 5 * (size_t)e->N, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return BB_OK;
+}
+
 int bb_step(bb_engine* e, const float* actions_dev, const bb_io* io, void* stream) {
   if (!e || !actions_dev) return e ? fail(e, BB_ERR_INVALID, "bb_step: actions is NULL") : BB_ERR_INVALID;
   int rc = checkIo(e, io); if (rc) return rc;
+  DevGuard guard(e->cfg.device);
   cudaStream_t s = (cudaStream_t)stream;
   const int N = e->N;
   const int bs = N >= 148 * 64 * 2 ? 64 : 32;
@@ -1177,6 +1278,7 @@ int bb_step(bb_engine* e, const float* actions_dev, const bb_io* io, void* strea
 
 int bb_add_reward(bb_engine* e, const float* term_dev, const bb_io* io, void* stream) {
   if (!e || !term_dev) return BB_ERR_INVALID;
+  DevGuard guard(e->cfg.device);
   int rc = checkIo(e, io); if (rc) return rc;
   k_add_reward<<<blocksFor(e->N, 256), 256, 0, (cudaStream_t)stream>>>(e->N, e->cfg.reward_scale, term_dev, *io, e->d.ep_ret);
   e->launches++;
@@ -1186,6 +1288,7 @@ int bb_add_reward(bb_engine* e, const float* term_dev, const bb_io* io, void* st
 
 int bb_set_state(bb_engine* e, const double* qpos, const double* qvel, const double* warm, void* stream) {
   if (!e) return BB_ERR_INVALID;
+  DevGuard guard(e->cfg.device);
   cudaStream_t s = (cudaStream_t)stream; const int N = e->N;
   if (e->cfg.precision == 64) { k_set_state<double><<<blocksFor(N, 128), 128, 0, s>>>(N, (double*)e->d.st, qpos, qvel, warm); k_copy_camq<double><<<blocksFor(N, 128), 128, 0, s>>>(N, (const double*)e->d.st, (double*)e->d.camq); }
   else { k_set_state<float><<<blocksFor(N, 128), 128, 0, s>>>(N, (float*)e->d.st, qpos, qvel, warm); k_copy_camq<float><<<blocksFor(N, 128), 128, 0, s>>>(N, (const float*)e->d.st, (float*)e->d.camq); }
@@ -1195,6 +1298,7 @@ int bb_set_state(bb_engine* e, const double* qpos, const double* qvel, const dou
 }
 int bb_get_state(bb_engine* e, double* qpos, double* qvel, double* warm, void* stream) {
   if (!e) return BB_ERR_INVALID;
+  DevGuard guard(e->cfg.device);
   cudaStream_t s = (cudaStream_t)stream; const int N = e->N;
   if (e->cfg.precision == 64) k_get_state<double><<<blocksFor(N, 128), 128, 0, s>>>(N, (const double*)e->d.st, qpos, qvel, warm);
   else k_get_state<float><<<blocksFor(N, 128), 128, 0, s>>>(N, (const float*)e->d.st, qpos, qvel, warm);
@@ -1204,13 +1308,14 @@ int bb_get_state(bb_engine* e, double* qpos, double* qvel, double* warm, void* s
 }
 int bb_set_hfield(bb_engine* e, const int32_t* ids, int32_t n, const float* hf, void* stream) {
   if (!e || !ids || !hf || n < 0) return BB_ERR_INVALID;
+  DevGuard guard(e->cfg.device);
   if (e->cfg.terrain_type == BB_TERRAIN_SHARED) {   // the one field shared by every env
     if (n != 1) return fail(e, BB_ERR_INVALID, "bb_set_hfield: a shared-terrain engine takes exactly one heightfield");
     BB_CUDA(cudaMemcpyAsync(e->d.hfield, hf, sizeof(float) * HF_CELLS, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     e->launches++;
     return BB_OK;
   }
-  if (!e->p.hf_per_env) return fail(e, BB_ERR_INVALID, "bb_set_hfield: engine was created with flat terrain (no per-env heightfields)");
+  if (e->p.hf_mode != HF_PER_ENV) return fail(e, BB_ERR_INVALID, "bb_set_hfield: engine has no per-env heightfields (flat terrain or Perlin table); create it with BB_TERRAIN_EXTERNAL");
   if (n == 0) return BB_OK;
   const size_t tot = (size_t)n * HF_CELLS;
   k_scatter_hfield<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids, n, hf, e->d.hfield);
@@ -1220,17 +1325,21 @@ int bb_set_hfield(bb_engine* e, const int32_t* ids, int32_t n, const float* hf, 
 }
 int bb_get_hfield(bb_engine* e, int32_t env, float* out, void* stream) {
   if (!e || !out || env < 0 || env >= e->N) return BB_ERR_INVALID;
-  const float* src = e->d.hfield + (e->p.hf_per_env ? (size_t)env * HF_CELLS : 0);
-  BB_CUDA(cudaMemcpyAsync(out, src, sizeof(float) * HF_CELLS, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  DevGuard guard(e->cfg.device);
+  k_get_hfield<<<blocksFor(HF_CELLS, 256), 256, 0, (cudaStream_t)stream>>>(e->p, e->d, env, out);   // the field index of table mode lives on the device
+  e->launches++;
+  BB_CUDA(cudaGetLastError());
   return BB_OK;
 }
 int bb_get_terrain_seeds(bb_engine* e, int32_t* seeds, void* stream) {
   if (!e || !seeds) return BB_ERR_INVALID;
+  DevGuard guard(e->cfg.device);
   BB_CUDA(cudaMemcpyAsync(seeds, e->d.tseed, sizeof(int) * e->N, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return BB_OK;
 }
 int bb_perlin_terrain(bb_engine* e, const int32_t* seeds, int32_t n, float* out, void* stream) {
   if (!e || !seeds || !out || n < 1) return BB_ERR_INVALID;
+  DevGuard guard(e->cfg.device);
   dim3 grid(blocksFor(HF_CELLS, 256), n < 128 ? n : 128);
   k_terrain<<<grid, 256, 0, (cudaStream_t)stream>>>(e->p, e->d, nullptr, nullptr, n, seeds, out);
   e->launches++;
@@ -1239,6 +1348,7 @@ int bb_perlin_terrain(bb_engine* e, const int32_t* seeds, int32_t n, float* out,
 }
 int bb_render_depth(bb_engine* e, float* img0, float* img1, void* stream) {
   if (!e || !img0 || !img1) return BB_ERR_INVALID;
+  DevGuard guard(e->cfg.device);
   const int N = e->N; cudaStream_t s = (cudaStream_t)stream;
   const int grid = depthGrid(N);
   BB_CUDA(cudaMemsetAsync(e->d.counters + 2, 0, sizeof(int), s));   // work-unit cursor of k_depth
@@ -1251,16 +1361,29 @@ int bb_render_depth(bb_engine* e, float* img0, float* img1, void* stream) {
 
 // replaces reading mjData.contact / qacc / solver_niter after mj_forward in a debugger (parity tests): one forward-dynamics
 // evaluation for env `env` at its current state; out_dev double[64], contact arrays double[53 | 159 | 477] (device)
-int bb_probe_forward(bb_engine* e, int32_t env, const double* ctrl3_dev, double* out_dev, double* cdist_dev, double* cpos_dev, double* cframe_dev, void* stream) {
-  if (!e || env < 0 || env >= e->N || !ctrl3_dev || !out_dev || !cdist_dev || !cpos_dev || !cframe_dev) return BB_ERR_INVALID;
+int bb_probe_forward(bb_engine* e, int32_t env, const double* ctrl3_dev, double* out_dev, double* contacts_dev, void* stream) {
+  if (!e || env < 0 || env >= e->N || !ctrl3_dev || !out_dev || !contacts_dev) return BB_ERR_INVALID;
+  DevGuard guard(e->cfg.device);
   if (e->cfg.step_kernel == 1) {
-    if (e->cfg.precision == 64) k_probe<double><<<1, 32, 0, (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev, cdist_dev, cpos_dev, cframe_dev);
-    else k_probe<float><<<1, 32, 0, (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev, cdist_dev, cpos_dev, cframe_dev);
-  } else {   // warp path: accelerations / counts only (contact arrays are left untouched)
-    if (e->cfg.precision == 64) k_probe_warp<double><<<1, 32, sizeof(bbg::GS<double>), (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev);
-    else k_probe_warp<float><<<1, 32, sizeof(bbg::GS<float>), (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev);
+    if (e->cfg.precision == 64) k_probe<double><<<1, 32, 0, (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev, contacts_dev);
+    else k_probe<float><<<1, 32, 0, (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev, contacts_dev);
+  } else {   // lane-group path: the production collision / solver code (gForward), contacts written by the lanes that found them
+    if (e->cfg.precision == 64) k_probe_warp<double><<<1, 32, sizeof(bbg::GS<double>), (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev, contacts_dev);
+    else k_probe_warp<float><<<1, 32, sizeof(bbg::GS<float>), (cudaStream_t)stream>>>(e->p, e->d, env, ctrl3_dev, out_dev, contacts_dev);
   }
   e->launches++;
+  BB_CUDA(cudaGetLastError());
+  return BB_OK;
+}
+__global__ void k_zero3(double* p) { if (threadIdx.x < 3) p[threadIdx.x] = 0.0; }
+int bb_get_contacts(bb_engine* e, int32_t env, double* contacts_dev, int32_t* ncon_dev, void* stream) {
+  if (!e || env < 0 || env >= e->N || !contacts_dev || !ncon_dev) return BB_ERR_INVALID;
+  DevGuard guard(e->cfg.device);
+  double* ctrl = e->probe_out + 56;    // three zeros behind the probe outputs
+  k_zero3<<<1, 32, 0, (cudaStream_t)stream>>>(ctrl);
+  int rc = bb_probe_forward(e, env, ctrl, e->probe_out, contacts_dev, stream); if (rc) return rc;
+  k_probe_count<<<1, 1, 0, (cudaStream_t)stream>>>(e->probe_out, ncon_dev);
+  e->launches += 2;
   BB_CUDA(cudaGetLastError());
   return BB_OK;
 }
@@ -1271,7 +1394,7 @@ int bb_perlin_grid(int32_t device, int32_t n, float scale, int32_t octaves, floa
   if (n < 1 || nseeds < 1 || !seeds_host || !out_host || octaves < 1) return BB_ERR_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) { snprintf(g_create_error, sizeof(g_create_error), "bb_perlin_grid: CUDA device %d not available; no CPU fallback", device); return BB_ERR_NO_DEVICE; }
-  if (cudaSetDevice(device) != cudaSuccess) return BB_ERR_CUDA;
+  DevGuard guard(device);
   if (cudaMemcpyToSymbol(c_perm, h_perm, sizeof(h_perm)) != cudaSuccess) return BB_ERR_CUDA;
   int* dseeds = nullptr; float* dout = nullptr; const size_t cells = (size_t)n * n;
   int rc = BB_OK;
@@ -1290,6 +1413,7 @@ int bb_perlin_grid(int32_t device, int32_t n, float scale, int32_t octaves, floa
 // per-kernel device timing of the next `max_steps` bb_step calls (CUDA events on the caller's stream)
 int bb_profile_begin(bb_engine* e, int32_t max_steps) {
   if (!e || max_steps < 1) return BB_ERR_INVALID;
+  DevGuard guard(e->cfg.device);
   if (e->prof_ev) { for (int i = 0; i < 5 * e->prof_cap; i++) cudaEventDestroy(e->prof_ev[i]); free(e->prof_ev); e->prof_ev = nullptr; }
   e->prof_ev = (cudaEvent_t*)malloc(sizeof(cudaEvent_t) * 5 * (size_t)max_steps);
   if (!e->prof_ev) return fail(e, BB_ERR_INVALID, "bb_profile_begin: out of host memory");
@@ -1300,6 +1424,7 @@ int bb_profile_begin(bb_engine* e, int32_t max_steps) {
 // ms4 = total milliseconds spent in {k_step, k_terrain, k_reset, k_depth} over the profiled steps; synchronises
 int bb_profile_end(bb_engine* e, double* ms4, int32_t* nsteps) {
   if (!e || !e->prof_ev || !ms4) return BB_ERR_INVALID;
+  DevGuard guard(e->cfg.device);
   double acc[4] = {0, 0, 0, 0};
   if (e->prof_n > 0) BB_CUDA(cudaEventSynchronize(e->prof_ev[5 * (size_t)(e->prof_n - 1) + 4]));
   for (int k = 0; k < e->prof_n; k++)
@@ -1363,6 +1488,7 @@ static int hostReadback(bb_engine* e, const bb_host_io* out) {
 }
 int bb_host_buffers(bb_engine* e, float** actions_host, bb_host_io* out) {
   if (!e || !out) return BB_ERR_INVALID;
+  DevGuard guard(e->cfg.device);
   int rc = hostInit(e); if (rc) return rc;
   if (actions_host) *actions_host = e->h_act;
   memset(out, 0, sizeof(*out));
@@ -1372,6 +1498,7 @@ int bb_host_buffers(bb_engine* e, float** actions_host, bb_host_io* out) {
 }
 int bb_step_host(bb_engine* e, const float* actions_host, const bb_host_io* out) {
   if (!e || !actions_host || !out) return BB_ERR_INVALID;
+  DevGuard guard(e->cfg.device);
   int rc = hostInit(e); if (rc) return rc;
   if (actions_host != e->h_act) memcpy(e->h_act, actions_host, sizeof(float) * 3 * e->N);
   BB_CUDA(cudaMemcpyAsync(e->d_act, e->h_act, sizeof(float) * 3 * e->N, cudaMemcpyHostToDevice, e->hstream));
@@ -1380,13 +1507,14 @@ int bb_step_host(bb_engine* e, const float* actions_host, const bb_host_io* out)
 }
 int bb_reset_host(bb_engine* e, const uint8_t* mask_host, const bb_host_io* out) {
   if (!e || !out) return BB_ERR_INVALID;
+  DevGuard guard(e->cfg.device);
   int rc = hostInit(e); if (rc) return rc;
   const uint8_t* dm = nullptr;
   if (mask_host) { memcpy(e->h_mask, mask_host, e->N); BB_CUDA(cudaMemcpyAsync(e->d_mask, e->h_mask, e->N, cudaMemcpyHostToDevice, e->hstream)); dm = e->d_mask; }
   BB_CUDA(cudaMemsetAsync(e->dio.reward, 0, sizeof(float) * e->N, e->hstream));
   BB_CUDA(cudaMemsetAsync(e->dio.terminated, 0, e->N, e->hstream)); BB_CUDA(cudaMemsetAsync(e->dio.failure, 0, e->N, e->hstream));
   BB_CUDA(cudaMemsetAsync(e->dio.pos2d, 0, sizeof(float) * 2 * e->N, e->hstream));
-  rc = bb_reset(e, dm, &e->dio, e->hstream); if (rc) return rc;
+  rc = bb_reset(e, dm, nullptr, &e->dio, e->hstream); if (rc) return rc;
   return hostReadback(e, out);
 }
 

@@ -15,8 +15,11 @@
 //     shared factor array (row stride 17), and every lane shifts its column up by one inside the update FMA so that the
 //     pivot row is always register 0; forward substitution is fused, backward substitution reads the lane's own row;
 //   * contact c is owned by lane c % G for the per-contact scalar work (cone zones, line-search coefficients);
-//     its record (3 Jacobian rows + 24 scalars) lives in shared memory (3 wheel + 8 terrain records) and spills to a
-//     global scratch beyond that (deep impacts only);
+//     its record (3 Jacobian rows + 24 scalars) lives in shared memory (3 dense + 8 terrain records) and spills to a
+//     global scratch beyond that (deep impacts, robot geoms touching the terrain);
+//   * contact order: [nw ball x wheel pairs (anisotropic friction)] [nd - nw other dense pairs: ball x stick / tower, stick /
+//     wheel capsule x heightfield] [ncon - nd ball x heightfield prisms]; "dense" = 16-column Jacobian rows (any dof), the
+//     ball x heightfield rows only hold the ball dofs;
 //   * the exact line search is a state machine around ONE evaluation call site, so two environments that are in
 //     different phases of their searches still share every evaluation instruction; evaluated points live in
 //     shared-memory slots and the brackets are slot indices;
@@ -47,7 +50,11 @@ constexpr int O_W = 0, O_FRC = 6, O_D0 = 9, O_JAR = 10, O_JV = 13, O_LS = 16;
 #define BB_NHS 8
 #endif
 constexpr int NHS = BB_NHS;                 // terrain records resident in shared memory
-constexpr int GSCR = (MAXH - NHS) * CRH;    // per-env global overflow scratch (in T)
+constexpr int NDS = 3;                      // dense records resident in shared memory
+constexpr int NDMAX = 27;                   // dense contact capacity (3 wheel pairs + 24 others)
+constexpr int GSD = (NDMAX - NDS) * CRW;    // dense overflow records come first in the per-env global scratch
+constexpr int GSCR = GSD + (MAXH - NHS) * CRH;    // per-env global overflow scratch (in T)
+constexpr int NCMAX = NDMAX + MAXH;         // contact capacity of one forward pass
 // geometry block published by the smooth-dynamics pass
 constexpr int LSP_SLOTS = 8, LSP_W = 4, LSP_ALPHA = 0, LSP_COST = 1, LSP_D1 = 2, LSP_NXT = 3;   // line-search point slots
 constexpr int GE_PB = 0, GE_PL = 3, GE_RB = 6, GE_RL = 15, GE_AW = 24, GE_HW = 33, GE_CC = 42, GE_CU = 51, GE_N = 60;
@@ -65,7 +72,7 @@ template <typename T> struct GS {
   T lsp[LSP_SLOTS * LSP_W];   // line-search points (alpha, cost, d1, next Newton alpha), see lsEval
   T wrec[3 * CRW];
   T hrec[NHS * CRH];
-  unsigned char cst[64];   // per contact: bits 0-1 zone (0 satisfied, 1 quadratic, 2 cone)
+  unsigned char cst[80];   // per contact: bits 0-1 zone (0 satisfied, 1 quadratic, 2 cone)
 };
 
 struct Ln { int gl; int gi; unsigned mask; };   // lane in group, clamped dof index, member mask of the group
@@ -109,9 +116,10 @@ __device__ __forceinline__ double fdivPos(double a, double b) {
   return fma(fma(-b, q, a), r, q);
 }
 
-template <typename T> __device__ __forceinline__ T* crec(GS<T>& S, T* gs, int c, int nw) {
-  return c < nw ? S.wrec + c * CRW : (c - nw < NHS ? S.hrec + (c - nw) * CRH : gs + (c - nw - NHS) * CRH);
-}
+// record of contact c; nd = number of dense contacts (they come first)
+template <typename T> __device__ __forceinline__ T* crecD(GS<T>& S, T* gs, int c) { return c < NDS ? S.wrec + c * CRW : gs + (c - NDS) * CRW; }
+template <typename T> __device__ __forceinline__ T* crecH(GS<T>& S, T* gs, int hc) { return hc < NHS ? S.hrec + hc * CRH : gs + GSD + (hc - NHS) * CRH; }
+template <typename T> __device__ __forceinline__ T* crec(GS<T>& S, T* gs, int c, int nd) { return c < nd ? crecD(S, gs, c) : crecH(S, gs, c - nd); }
 
 // ---------------------------------------------------------------------------------------------- smooth dynamics
 // Every lane evaluates the (small, serial) smooth dynamics of its environment redundantly; the results go to shared
@@ -140,7 +148,7 @@ template <typename T> __device__ __noinline__ void gSmooth(const ModelConst<T>& 
 // Assembles column gi of H = M + sum_{c < ncon, zone != 0} J_c' W_c J_c in registers, factorises H = L L' across the
 // group and returns x[gi] of H x = b (b: one value per dof lane).  ncon = 0 gives M^-1 b (qacc_smooth).
 template <typename T>
-__device__ __forceinline__ T gHessSolve(GS<T>& S, const T* gs, int ncon, int nw, T b, const Ln L) {
+__device__ __forceinline__ T gHessSolve(GS<T>& S, const T* gs, int ncon, int nd, T b, const Ln L) {
   const int gi = L.gi;
   T h[NV];
   {
@@ -152,11 +160,11 @@ __device__ __forceinline__ T gHessSolve(GS<T>& S, const T* gs, int ncon, int nw,
 #pragma unroll
     for (int k = 9; k < NV; k++) { const T v = mb[(k - 9) * 6]; h[k] = top ? (T)0 : v; }
   }
-  // wheel pairs: dense 15-column rows
+  // dense pairs: 15-column rows
 #pragma unroll 1
-  for (int c = 0; c < nw; c++) {
+  for (int c = 0; c < nd; c++) {
     if ((S.cst[c] & 3) == 0) continue;
-    const T* rec = S.wrec + c * CRW;
+    const T* rec = c < NDS ? (const T*)(S.wrec + c * CRW) : gs + (c - NDS) * CRW;
     const T a0 = rec[gi], a1 = rec[16 + gi], a2 = rec[32 + gi];
     const typename V2T<T>::t w01 = ld2(rec + OSW), w23 = ld2(rec + OSW + 2), w45 = ld2(rec + OSW + 4);
     const T t0 = w01.x * a0 + w23.y * a1 + w45.x * a2;   // W = [w0 w3 w4; w3 w1 w5; w4 w5 w2]
@@ -172,10 +180,10 @@ __device__ __forceinline__ T gHessSolve(GS<T>& S, const T* gs, int ncon, int nw,
   // terrain pair: only the ball dofs 9..14 (rows hold dofs 8..15)
   const bool bl = gi >= 9;
 #pragma unroll 1
-  for (int c = nw; c < ncon; c++) {
+  for (int c = nd; c < ncon; c++) {
     if ((S.cst[c] & 3) == 0) continue;
-    const int hc = c - nw;
-    const T* rec = hc < NHS ? (const T*)(S.hrec + hc * CRH) : gs + (hc - NHS) * CRH;
+    const int hc = c - nd;
+    const T* rec = hc < NHS ? (const T*)(S.hrec + hc * CRH) : gs + GSD + (hc - NHS) * CRH;
     const int o = bl ? gi - 8 : 0;
     T a0 = rec[o], a1 = rec[8 + o], a2 = rec[16 + o];
     if (!bl) { a0 = 0; a1 = 0; a2 = 0; }
@@ -376,14 +384,13 @@ template <typename T> __device__ __forceinline__ Sum3<T> gsum3(T a, T b, T c, un
 // cost and derivatives of the 1-D line-search objective at alpha (PrimalEval); uniform over the group.  The point is
 // also parked in slot `slot` of S.lsp so that the search logic can refer to older points by index.
 template <typename T>
-__device__ __forceinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, const T* gs, int ncon, int nw, const LsCtx<T> q, T alpha, int slot, const Ln L,
+__device__ __forceinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, const T* gs, int ncon, int nw, int nd, const LsCtx<T> q, T alpha, int slot, const Ln L,
                                           const T* rec0) {
   T cost = 0, d1 = 0, d2 = 0;
 #pragma unroll 1
   for (int c = L.gl; c < ncon; c += G) {
-    const bool wheel = c < nw;
-    const T* sc = (c < G ? rec0 : (const T*)crec(S, (T*)gs, c, nw)) + (wheel ? OSW : OSH);
-    const int k = wheel ? 0 : 1;
+    const T* sc = (c < G ? rec0 : (const T*)crec(S, (T*)gs, c, nd)) + (c < nd ? OSW : OSH);
+    const int k = c < nw ? 0 : 1;
     const T mu = mc.mu[k];
     const typename V2T<T>::t l01 = ld2(sc + O_LS), l23 = ld2(sc + O_LS + 2), l4q = ld2(sc + O_LS + 4), lq = ld2(sc + O_LS + 6);
     const T U0 = l01.x, V0 = l01.y, UU = l23.x, UV = l23.y, VV = l4q.x;
@@ -422,27 +429,26 @@ __device__ __forceinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, con
 // removes the convergence pre-check (MATCH / REDUX / VOTE / branch) ptxas emits in front of every shuffle group with a
 // run-time member mask: ~5 % of the solver's instructions and ~12 % of its stall samples.
 template <typename T, bool U = false> struct GNewton {
-  const ModelConst<T>& mc; GS<T>& S; T* gs; const Ln L; const int ncon, nw;
+  const ModelConst<T>& mc; GS<T>& S; T* gs; const Ln L; const int ncon, nw, nd;   // nw wheel pairs <= nd dense contacts <= ncon
   const bool fast;   // fast solver mode: inexact line search (stop when |phi'| <= 1e-3 |phi'(0)|), same minimiser of the outer problem
   T qfs, qas;        // dof-lane registers
   T qacc, Ma, grad, search, Mv;
   T cost, gauss, gnorm2;
   int nevals = 0;    // line-search evaluations of this solve (work key of the scheduler)
   T* rec0;           // record of the contact this lane owns in every per-contact loop (c = gl; loop-invariant for the whole solve)
-  __device__ GNewton(const ModelConst<T>& m, GS<T>& s, T* g, const Ln l, int n, int w, bool f, T qf, T qa)
-      : mc(m), S(s), gs(g), L(l), ncon(n), nw(w), fast(f), qfs(qf), qas(qa) { rec0 = crec(S, gs, L.gl, nw); }
-  __device__ __forceinline__ T* recOf(int c) const { return c < G ? rec0 : crec(S, gs, c, nw); }
+  __device__ GNewton(const ModelConst<T>& m, GS<T>& s, T* g, const Ln l, int n, int w, int dn, bool f, T qf, T qa)
+      : mc(m), S(s), gs(g), L(l), ncon(n), nw(w), nd(dn), fast(f), qfs(qf), qas(qa) { rec0 = crec(S, gs, L.gl, nd); }
+  __device__ __forceinline__ T* recOf(int c) const { return c < G ? rec0 : crec(S, gs, c, nd); }
 
   // forces / zones / cone Hessian blocks at the current jar (contact lanes), cost, gradient (dof lanes)
   __device__ __forceinline__ void costGrad() {
     T cpart = 0;
 #pragma unroll 1
     for (int c = L.gl; c < ncon; c += G) {
-      const bool wheel = c < nw;
-      T* sc = recOf(c) + (wheel ? OSW : OSH);
+      T* sc = recOf(c) + (c < nd ? OSW : OSH);
       T h[6], f[3]; int st;
       const T jr[3] = {sc[O_JAR], sc[O_JAR + 1], sc[O_JAR + 2]};
-      cpart += coneLane(mc, wheel ? 0 : 1, sc[O_D0], jr, f, h, st, true);
+      cpart += coneLane(mc, c < nw ? 0 : 1, sc[O_D0], jr, f, h, st, true);
       S.cst[c] = (unsigned char)st;
       sc[O_FRC] = f[0]; sc[O_FRC + 1] = f[1]; sc[O_FRC + 2] = f[2];
       if (st) {
@@ -455,17 +461,17 @@ template <typename T, bool U = false> struct GNewton {
     T g = Ma - qfs;
     const int gi = L.gi;
 #pragma unroll 1
-    for (int c = 0; c < nw; c++) {
+    for (int c = 0; c < nd; c++) {
       if ((S.cst[c] & 3) == 0) continue;
-      const T* rec = S.wrec + c * CRW;
+      const T* rec = crecD(S, gs, c);
       g -= rec[gi] * rec[OSW + O_FRC] + rec[16 + gi] * rec[OSW + O_FRC + 1] + rec[32 + gi] * rec[OSW + O_FRC + 2];
     }
     if (gi >= 9) {
 #pragma unroll 1
-      for (int c = nw; c < ncon; c++) {
+      for (int c = nd; c < ncon; c++) {
         if ((S.cst[c] & 3) == 0) continue;
-        const int hc = c - nw;
-        const T* rec = hc < NHS ? (const T*)(S.hrec + hc * CRH) : (const T*)(gs + (hc - NHS) * CRH);
+        const int hc = c - nd;
+        const T* rec = crecH(S, gs, hc);
         g -= rec[gi - 8] * rec[OSH + O_FRC] + rec[gi] * rec[OSH + O_FRC + 1] + rec[8 + gi] * rec[OSH + O_FRC + 2];
       }
     }
@@ -491,12 +497,12 @@ template <typename T, bool U = false> struct GNewton {
     // jv = J search and the per-contact coefficients of the search (PrimalPrepare)
 #pragma unroll 1
     for (int c = L.gl; c < ncon; c += G) {
-      const bool wheel = c < nw;
+      const bool wheel = c < nd;
       T* rec = recOf(c);
       T* sc = rec + (wheel ? OSW : OSH);
       T w[3]; rowsDot(rec, wheel, S.vb[0], w);
       sc[O_JV] = w[0]; sc[O_JV + 1] = w[1]; sc[O_JV + 2] = w[2];
-      const int k = wheel ? 0 : 1;
+      const int k = c < nw ? 0 : 1;
       const T D0 = sc[O_D0], D1 = D0 * mc.d1r[k], D2 = D0 * mc.d2r[k];
       const T mu = mc.mu[k], f1 = mc.f1[k], f2 = mc.f2[k];
       const T j0 = sc[O_JAR], j1 = sc[O_JAR + 1], j2 = sc[O_JAR + 2];
@@ -520,7 +526,7 @@ template <typename T, bool U = false> struct GNewton {
 #pragma unroll 1
     for (;;) {
       if (U && !__any_sync(0xffffffffu, on)) break;      // both searches of the warp have finished
-      const LsPt<T> p = lsEval(mc, S, gs, ncon, nw, q, a, dst, L, rec0);
+      const LsPt<T> p = lsEval(mc, S, gs, ncon, nw, nd, q, a, dst, L, rec0);
       if (U && !on) continue;                             // passenger: state frozen
       nevals++;
       bool done = false;
@@ -603,15 +609,15 @@ template <typename T, bool U = false> struct GNewton {
     T cw = dof ? (T)0.5 * (mw - qfs) * (warm - qas) : (T)0, cs = 0;
 #pragma unroll 1
     for (int c = L.gl; c < ncon; c += G) {
-      const bool wheel = c < nw;
+      const bool wheel = c < nd;
       T* rec = recOf(c);
       T* sc = rec + (wheel ? OSW : OSH);
       T jw[3], js[3], f[3], h[6]; int st;
       rowsDot(rec, wheel, S.vb[0], jw); rowsDot(rec, wheel, S.vb[1], js);
 #pragma unroll
       for (int m = 0; m < 3; m++) { const T ar = sc[O_JV + m]; jw[m] -= ar; js[m] -= ar; }
-      cw += coneLane(mc, wheel ? 0 : 1, sc[O_D0], jw, f, h, st, false);
-      cs += coneLane(mc, wheel ? 0 : 1, sc[O_D0], js, f, h, st, false);
+      cw += coneLane(mc, c < nw ? 0 : 1, sc[O_D0], jw, f, h, st, false);
+      cs += coneLane(mc, c < nw ? 0 : 1, sc[O_D0], js, f, h, st, false);
       // park both candidates: jar <- warm-start residual, LS[0..2] <- smooth residual
       sc[O_JAR] = jw[0]; sc[O_JAR + 1] = jw[1]; sc[O_JAR + 2] = jw[2];
       sc[O_LS] = js[0]; sc[O_LS + 1] = js[1]; sc[O_LS + 2] = js[2];
@@ -622,7 +628,7 @@ template <typename T, bool U = false> struct GNewton {
       qacc = qas; Ma = qfs;
 #pragma unroll 1
       for (int c = L.gl; c < ncon; c += G) {
-        T* sc = recOf(c) + (c < nw ? OSW : OSH);
+        T* sc = recOf(c) + (c < nd ? OSW : OSH);
         sc[O_JAR] = sc[O_LS]; sc[O_JAR + 1] = sc[O_LS + 1]; sc[O_JAR + 2] = sc[O_LS + 2];
       }
     } else { qacc = warm; Ma = mw; }
@@ -634,14 +640,14 @@ template <typename T, bool U = false> struct GNewton {
       bool on = act && iter < mc.iterations;
 #pragma unroll 1
       while (__any_sync(0xffffffffu, on)) {
-        search = -gHessSolve(S, gs, ncon, nw, grad, L);
+        search = -gHessSolve(S, gs, ncon, nd, grad, L);
         const T alpha = lineSearch(scale, on);
         const bool step = on && alpha != 0;               // alpha == 0 ends the solve without touching the state
         if (step) {
           qacc += alpha * search; Ma += alpha * Mv;
 #pragma unroll 1
           for (int c = L.gl; c < ncon; c += G) {
-            T* sc = recOf(c) + (c < nw ? OSW : OSH);
+            T* sc = recOf(c) + (c < nd ? OSW : OSH);
             sc[O_JAR] += alpha * sc[O_JV]; sc[O_JAR + 1] += alpha * sc[O_JV + 1]; sc[O_JAR + 2] += alpha * sc[O_JV + 2];
           }
         }
@@ -653,13 +659,13 @@ template <typename T, bool U = false> struct GNewton {
     } else {
 #pragma unroll 1
     while (iter < mc.iterations) {
-      search = -gHessSolve(S, gs, ncon, nw, grad, L);
+      search = -gHessSolve(S, gs, ncon, nd, grad, L);
       const T alpha = lineSearch(scale);
       if (alpha == 0) break;
       qacc += alpha * search; Ma += alpha * Mv;
 #pragma unroll 1
       for (int c = L.gl; c < ncon; c += G) {
-        T* sc = recOf(c) + (c < nw ? OSW : OSH);
+        T* sc = recOf(c) + (c < nd ? OSW : OSH);
         sc[O_JAR] += alpha * sc[O_JV]; sc[O_JAR + 1] += alpha * sc[O_JV + 1]; sc[O_JAR + 2] += alpha * sc[O_JV + 2];
       }
       const T old = cost;
@@ -692,64 +698,137 @@ __device__ __forceinline__ void finishRecord(const ModelConst<T>& mc, T* sc, int
   sc[O_JV] = -mc.B * vel[0] - mc.K * imp * dist; sc[O_JV + 1] = -mc.B * vel[1]; sc[O_JV + 2] = -mc.B * vel[2];
 }
 
-// Contact generation (3 patched sphere-capsule pairs, tools/mujoco_fix.patch:9-18, + ball vs heightfield prisms in the
-// reference scan order) with the constraint rows built in place by the lane that found the contact.
-// Returns the contact count; nw = number of wheel contacts (they come first).
+// capsule against one heightfield prism; a single out-of-line copy keeps the stage kernel's code small
 template <typename T>
-__device__ __noinline__ int gCollide(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, const Ln L, int& nwOut) {
+__device__ __noinline__ bool gCapsulePrism(const V3<T>& p0, const V3<T>& p1, T r, const V3<T>& ta, const V3<T>& tb, const V3<T>& tc, T& dist, V3<T>& n, V3<T>& pos) {
+  return capsulePrism(p0, p1, r, ta, tb, tc, dist, n, pos);
+}
+// dense constraint rows of a contact at `pos` with frame F: base columns (b1 = +1 when the base tree is body 2), hinge column of
+// wheel wi (or -1), ball columns (the ball is body 1 of every robot pair) or zeros; returns the contact-frame velocity
+template <typename T>
+__device__ __forceinline__ void gDenseRows(const GS<T>& S, const T* ge, T* rec, const T* F, const V3<T>& pos, int wi, bool ball, T* vel) {
+  const V3<T> pB = ld3(ge + GE_PB), pL = ld3(ge + GE_PL);
+  const Rot<T> RB = {ld3(ge + GE_RB), ld3(ge + GE_RB + 3), ld3(ge + GE_RB + 6)};
+  const Rot<T> RL = {ld3(ge + GE_RL), ld3(ge + GE_RL + 3), ld3(ge + GE_RL + 6)};
+  const V3<T> rB = pos - pB, rL = pos - pL;
+  const V3<T> cb0 = cross(RB.c0, rB), cb1 = cross(RB.c1, rB), cb2 = cross(RB.c2, rB);
+  const V3<T> cl0 = cross(rL, RL.c0), cl1 = cross(rL, RL.c1), cl2 = cross(rL, RL.c2);
+  const int w = wi < 0 ? 0 : wi;
+  V3<T> ah = cross(ld3(ge + GE_AW + 3 * w), pos - ld3(ge + GE_HW + 3 * w));
+  if (wi < 0) ah = mk((T)0, (T)0, (T)0);
+  const T bs = ball ? (T)1 : (T)0;
+#pragma unroll 1
+  for (int k = 0; k < 3; k++) {
+    T* jr = rec + k * 16;
+    const V3<T> fk = mk(F[3 * k], F[3 * k + 1], F[3 * k + 2]);
+    jr[0] = fk.x; jr[1] = fk.y; jr[2] = fk.z;
+    jr[3] = dot(fk, cb0); jr[4] = dot(fk, cb1); jr[5] = dot(fk, cb2);
+    const T hq = dot(fk, ah);
+    jr[6] = wi == 0 ? hq : (T)0; jr[7] = wi == 1 ? hq : (T)0; jr[8] = wi == 2 ? hq : (T)0;
+    jr[9] = -bs * fk.x; jr[10] = -bs * fk.y; jr[11] = -bs * fk.z;
+    jr[12] = bs * dot(fk, cl0); jr[13] = bs * dot(fk, cl1); jr[14] = bs * dot(fk, cl2); jr[15] = 0;
+    T v = 0;
+    for (int q = 0; q < NV; q++) v += jr[q] * S.xv[q];
+    vel[k] = v;
+  }
+}
+template <bool DBG, typename T> __device__ __forceinline__ void gDbgContact(double* dbg, int c, int ty, T dist, const V3<T>& pos, const T* F) {
+  if (!DBG) return;
+  double* o = dbg + 14 * c;
+  o[0] = ty; o[1] = (double)dist; o[2] = (double)pos.x; o[3] = (double)pos.y; o[4] = (double)pos.z;
+  for (int k = 0; k < 9; k++) o[5 + k] = (double)F[k];
+}
+
+// Contact generation with the constraint rows built in place by the lane that found the contact:
+//   phase 1  lanes 0..5: ball x wheel capsules (patched sphere-capsule, tools/mujoco_fix.patch:9-18), ball x camera sticks
+//            (same patched routine), ball x tower cylinder
+//   phase 2  camera-stick and wheel capsules x heightfield prisms of each capsule's sub-grid (dense rows, appended)
+//   phase 3  ball x heightfield prisms in the reference scan order
+// Returns the contact count; nw = ball x wheel contacts (first), nd = all dense contacts (phases 1 + 2).
+// DBG: every contact is also written to dbg[c] = {type, dist, pos3, frame9} (bb_probe_forward; never in the step kernels).
+template <typename T, bool DBG = false>
+__device__ __noinline__ int gCollide(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, const Ln L, int& nwOut, int& ndOut,
+                                     double* dbg = nullptr) {
   const int gl = L.gl;
   const unsigned lt = (1u << gl) - 1u;
   const int gsh = (threadIdx.x & 31) & ~(G - 1);     // bit position of the group's lane 0 in a ballot
+  const unsigned gmask = (G == 32) ? 0xffffffffu : 0xffffu;
   const T* ge = S.geo;
-  const V3<T> pL = ld3(ge + GE_PL);
+  const V3<T> pB = ld3(ge + GE_PB), pL = ld3(ge + GE_PL);
+  const Rot<T> RB = {ld3(ge + GE_RB), ld3(ge + GE_RB + 3), ld3(ge + GE_RB + 6)};
   const Rot<T> RL = {ld3(ge + GE_RL), ld3(ge + GE_RL + 3), ld3(ge + GE_RL + 6)};
   const V3<T> bc = pL + RL.c2 * mc.dz;
   const T br = mc.ball_r;
-  // ---- wheel pairs on lanes 0..2
+  // ---- phase 1: the ball against the robot's own geoms
   bool hit = false; T dist = 0; V3<T> n = mk((T)0, (T)0, (T)1), pos = n;
   V3<T> cu = n;
   if (gl < 3) {
-    const V3<T> cc = ld3(ge + GE_CC + 3 * gl); cu = ld3(ge + GE_CU + 3 * gl);
-    T x = dot(cu, bc - cc);
-    x = x > mc.wheel_hl ? mc.wheel_hl : (x < -mc.wheel_hl ? -mc.wheel_hl : x);
-    const V3<T> dif = cc + cu * x - bc;
-    const T cd = bsqrt(dot(dif, dif)), mind = br + mc.wheel_r;
-    if (cd < mind) { hit = true; n = dif * ((T)1 / cd); dist = cd - mind; pos = bc + n * (br + (T)0.5 * dist); }
+    cu = ld3(ge + GE_CU + 3 * gl);
+    hit = sphereCapsule(bc, br, ld3(ge + GE_CC + 3 * gl), cu, mc.wheel_r, mc.wheel_hl, dist, n, pos);
+  } else if (gl < 5) {
+    cu = rot(RB, ld3(mc.stick_u[gl - 3]));
+    hit = sphereCapsule(bc, br, pB + rot(RB, ld3(mc.stick_c[gl - 3])), cu, mc.stick_r, mc.stick_hl, dist, n, pos);
+  } else if (gl == 5) {
+    hit = sphereCylinder(bc, br, pB + rot(RB, ld3(mc.tower_c)), RB.c2, mc.tower_r, mc.tower_hl, dist, n, pos);
   }
-  unsigned m = (__ballot_sync(L.mask, hit) >> gsh) & ((G == 32) ? 0xffffffffu : 0xffffu);
-  const int nw = __popc(m);
+  unsigned m = (__ballot_sync(L.mask, hit) >> gsh) & gmask;
+  const int nw = __popc(m & 7u);
+  int nd = __popc(m);
   if (hit) {
-    const int c = __popc(m & lt), ty = gl;
-    T* rec = S.wrec + c * CRW;
+    const int c = __popc(m & lt), ty = gl < 3 ? gl : (gl < 5 ? 10 + gl - 3 : 9);
+    T* rec = crecD(S, gs, c);
     T F[9] = {n.x, n.y, n.z, cu.x, cu.y, cu.z, 0, 0, 0};
-    makeFrame(F, true);
-    const V3<T> pB = ld3(ge + GE_PB);
-    const Rot<T> RB = {ld3(ge + GE_RB), ld3(ge + GE_RB + 3), ld3(ge + GE_RB + 6)};
-    const V3<T> rB = pos - pB, rL = pos - pL;
-    const V3<T> cb0 = cross(RB.c0, rB), cb1 = cross(RB.c1, rB), cb2 = cross(RB.c2, rB);
-    const V3<T> cl0 = cross(rL, RL.c0), cl1 = cross(rL, RL.c1), cl2 = cross(rL, RL.c2);
-    const V3<T> ah = cross(ld3(ge + GE_AW + 3 * ty), pos - ld3(ge + GE_HW + 3 * ty));
+    makeFrame(F, gl < 5);
     T vel[3];
-#pragma unroll 1
-    for (int k = 0; k < 3; k++) {
-      T* jr = rec + k * 16;
-      const V3<T> fk = mk(F[3 * k], F[3 * k + 1], F[3 * k + 2]);
-      jr[0] = fk.x; jr[1] = fk.y; jr[2] = fk.z;
-      jr[3] = dot(fk, cb0); jr[4] = dot(fk, cb1); jr[5] = dot(fk, cb2);
-      const T hq = dot(fk, ah);
-      jr[6] = ty == 0 ? hq : (T)0; jr[7] = ty == 1 ? hq : (T)0; jr[8] = ty == 2 ? hq : (T)0;
-      jr[9] = -fk.x; jr[10] = -fk.y; jr[11] = -fk.z;
-      jr[12] = dot(fk, cl0); jr[13] = dot(fk, cl1); jr[14] = dot(fk, cl2); jr[15] = 0;
-      T v = 0;
-      for (int q = 0; q < NV; q++) v += jr[q] * S.xv[q];
-      vel[k] = v;
-    }
+    gDenseRows(S, ge, rec, F, pos, gl < 3 ? gl : -1, true, vel);
     finishRecord(mc, rec + OSW, ty, dist, vel);
     S.cst[c] = 0;
+    gDbgContact<DBG>(dbg, c, ty, dist, pos, F);
   }
-  // ---- ball vs heightfield prisms
-  int cnt = 0;
+  // ---- phase 2: camera sticks (gi 0, 1) and wheel capsules (gi 2..4) against the heightfield
   const T sx = mc.hx;
+#pragma unroll 1
+  for (int gi = 0; gi < 5; gi++) {
+    V3<T> cc; T rad, hl;
+    if (gi < 2) { cc = pB + rot(RB, ld3(mc.stick_c[gi])); cu = rot(RB, ld3(mc.stick_u[gi])); rad = mc.stick_r; hl = mc.stick_hl; }
+    else { cc = ld3(ge + GE_CC + 3 * (gi - 2)); cu = ld3(ge + GE_CU + 3 * (gi - 2)); rad = mc.wheel_r; hl = mc.wheel_hl; }
+    const int ty = 4 + gi, wi = gi < 2 ? -1 : gi - 2;   // contact types 4, 5 (sticks) and 6..8 (wheels)
+    const V3<T> p0 = cc - cu * hl, p1 = cc + cu * hl;
+    const V3<T> lo = mk(bmin(p0.x, p1.x) - rad, bmin(p0.y, p1.y) - rad, bmin(p0.z, p1.z) - rad);
+    const V3<T> hi = mk(bmax(p0.x, p1.x) + rad, bmax(p0.y, p1.y) + rad, bmax(p0.z, p1.z) + rad);
+    HfGrid<T> gr;
+    if (!hfieldSubgrid(sx, mc.hbase, zscale, lo, hi, gr)) continue;
+    const int ncols = gr.cmax - gr.cmin, nrows = gr.rmax - gr.rmin, nprism = ncols > 0 && nrows > 0 ? 2 * ncols * nrows : 0;
+    int cnt = 0;
+#pragma unroll 1
+    for (int base = 0; base < nprism && cnt < MAXH; base += G) {
+      const int p = base + gl;
+      hit = false;
+      if (p < nprism) {
+        const int cell = p >> 1, r = gr.rmin + cell / ncols, c = gr.cmin + cell % ncols;
+        V3<T> ta, tb, tc; hfieldTriangle(hf, zscale, sx, gr.dx, r, c, p & 1, ta, tb, tc);
+        if (!(ta.z < gr.zmin && tb.z < gr.zmin && tc.z < gr.zmin)) hit = gCapsulePrism(p0, p1, rad, ta, tb, tc, dist, n, pos);
+      }
+      m = (__ballot_sync(L.mask, hit) >> gsh) & gmask;
+      if (m == 0) continue;
+      const int rank = cnt + __popc(m & lt), c = nd + rank;
+      if (hit && rank < MAXH && c < NDMAX) {
+        T* rec = crecD(S, gs, c);
+        T F[9] = {n.x, n.y, n.z, 0, 0, 0, 0, 0, 0};
+        makeFrame(F, false);
+        T vel[3];
+        gDenseRows(S, ge, rec, F, pos, wi, false, vel);
+        finishRecord(mc, rec + OSW, ty, dist, vel);
+        S.cst[c] = 0;
+        gDbgContact<DBG>(dbg, c, ty, dist, pos, F);
+      }
+      cnt += __popc(m);
+    }
+    nd += cnt < MAXH ? cnt : MAXH;
+    nd = nd < NDMAX ? nd : NDMAX;
+  }
+  // ---- phase 3: ball vs heightfield prisms
+  int cnt = 0;
   const bool skip = (sx < bc.x - br) || (-sx > bc.x + br) || (sx < bc.y - br) || (-sx > bc.y + br) || (zscale < bc.z - br) || (-mc.hbase > bc.z + br);
   if (!skip) {
     const T gsc = (T)(HN - 1) / ((T)2 * sx);
@@ -789,12 +868,12 @@ __device__ __noinline__ int gCollide(const ModelConst<T>& mc, GS<T>& S, const fl
           }
         }
       }
-      m = (__ballot_sync(L.mask, hit) >> gsh) & ((G == 32) ? 0xffffffffu : 0xffffu);
+      m = (__ballot_sync(L.mask, hit) >> gsh) & gmask;
       if (m == 0) continue;
       const int rank = cnt + __popc(m & lt);
       if (hit && rank < MAXH) {
-        const int c = nw + rank;
-        T* rec = rank < NHS ? S.hrec + rank * CRH : gs + (rank - NHS) * CRH;
+        const int c = nd + rank;
+        T* rec = crecH(S, gs, rank);
         T F[9] = {n.x, n.y, n.z, 0, 0, 0, 0, 0, 0};
         makeFrame(F, false);
         const V3<T> rL = pos - pL;
@@ -813,14 +892,15 @@ __device__ __noinline__ int gCollide(const ModelConst<T>& mc, GS<T>& S, const fl
         }
         finishRecord(mc, rec + OSH, 3, dist, vel);
         S.cst[c] = 0;
+        gDbgContact<DBG>(dbg, c, 3, dist, pos, F);
       }
       cnt += __popc(m);
     }
     cnt = cnt < MAXH ? cnt : MAXH;
   }
   __syncwarp(L.mask);
-  nwOut = nw;
-  return nw + cnt;
+  nwOut = nw; ndOut = nd;
+  return nd + cnt;
 }
 
 // ---------------------------------------------------------------------------------------------- one mj_forward (group)
@@ -829,11 +909,11 @@ __device__ __noinline__ int gCollide(const ModelConst<T>& mc, GS<T>& S, const fl
 // qfrc_smooth / qacc_smooth of this dof lane, S.M, the contact records (and S.xq normalised, S.kin when wantKin).
 // cta_sync: the warps of the CTA enter the three phases together (every thread of the CTA must make the call; `skip`
 // marks threads that only take part in the barriers), so the large straight-line phase code is fetched once per CTA.
-template <typename T>
+template <typename T, bool DBG = false>
 __device__ __forceinline__ int gForwardPre(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, const Ln L, bool wantKin,
-                                           int& nw, T& qfs, T& qas, bool skip = false, bool cta_sync = false) {
+                                           int& nw, int& nd, T& qfs, T& qas, bool skip = false, bool cta_sync = false, double* dbg = nullptr) {
   int ncon = 0;
-  nw = 0; qfs = 0; qas = 0;
+  nw = 0; nd = 0; qfs = 0; qas = 0;
   if (cta_sync) __syncthreads();
   if (!skip) {
     if (L.gl == 0) normalizeQuats(S.xq);
@@ -844,21 +924,21 @@ __device__ __forceinline__ int gForwardPre(const ModelConst<T>& mc, GS<T>& S, co
     __syncwarp(L.mask);
   }
   if (cta_sync) __syncthreads();
-  if (!skip) ncon = gCollide(mc, S, hf, zscale, gs, L, nw);   // consumes S.geo, which shares storage with the Cholesky factor
+  if (!skip) ncon = gCollide<T, DBG>(mc, S, hf, zscale, gs, L, nw, nd, dbg);   // consumes S.geo, which shares storage with the Cholesky factor
   if (cta_sync) __syncthreads();
   if (!skip) qas = gMassSolve(S, qfs, L);                     // qacc_smooth = M^-1 qfrc_smooth
   return ncon;
 }
 // in: S.xq, S.xv, S.ctrl, warm (dof-lane register)   out: returns qacc of this dof lane (and S.xq normalised).
-template <typename T>
+template <typename T, bool DBG = false>
 __device__ __noinline__ T gForward(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, const Ln L, T warm, bool fast,
-                                   bool wantKin, int& nconOut, int& niterOut, T* qasOut = nullptr, T* qfsOut = nullptr) {
-  int nw; T qfs, qas;
-  const int ncon = gForwardPre(mc, S, hf, zscale, gs, L, wantKin, nw, qfs, qas);
+                                   bool wantKin, int& nconOut, int& niterOut, T* qasOut = nullptr, T* qfsOut = nullptr, double* dbg = nullptr) {
+  int nw, nd; T qfs, qas;
+  const int ncon = gForwardPre<T, DBG>(mc, S, hf, zscale, gs, L, wantKin, nw, nd, qfs, qas, false, false, dbg);
   if (qasOut) { *qasOut = qas; *qfsOut = qfs; }
   nconOut = ncon; niterOut = 0;
   if (ncon == 0) return qas;
-  GNewton<T> nwt(mc, S, gs, L, ncon, nw, fast, qfs, qas);
+  GNewton<T> nwt(mc, S, gs, L, ncon, nw, nd, fast, qfs, qas);
   int niter;
   const T qacc = nwt.run(warm, niter);
   niterOut = niter;
@@ -925,26 +1005,26 @@ __device__ void gRk4(const ModelConst<T>& mc, GS<T>& S, const float* __restrict_
 // records).  ~6 KB per env and stage, i.e. < 0.3 ms per step of HBM time at 65,536 envs.
 constexpr int RK_Q0 = 0, RK_V0 = 20, RK_SUMV = 36, RK_SUMA = 52, RK_XV = 68, RK_QACC = 84, RK_WARM = 100, RK_CTRL = 116, RK_KIN = 120, RKN = 136;
 constexpr int CTX_M = 0, CTX_QFS = 120, CTX_QAS = 136, CTX_W = 152, CTX_H = CTX_W + 3 * CRW + 2, CTXN = CTX_H + NHS * CRH;
-constexpr int META_NCON = 0, META_NW = 1, META_NIT = 2, META_FLAGS = 3;   // int[N][4]; flags: bit 0 bad, bits 8.. max ncon
+constexpr int META_NCON = 0, META_NW = 1, META_NIT = 2, META_FLAGS = 3;   // int[N][4]; META_NW = nw | nd << 8; flags: bit 0 bad, bits 8.. max ncon
 
 template <typename T> __device__ __forceinline__ void gcopy(T* __restrict__ dst, const T* __restrict__ src, int n, const Ln L) {
   // n even, both 16-byte aligned
   for (int k = 2 * L.gl; k < n; k += 2 * G) *reinterpret_cast<typename V2T<T>::t*>(dst + k) = ld2(src + k);
 }
 // solver input of one env -> HBM (after gForwardPre) and back (before GNewton::run)
-template <typename T> __device__ __forceinline__ void ctxSave(T* __restrict__ cx, const GS<T>& S, int ncon, int nw, T qfs, T qas, const Ln L) {
+template <typename T> __device__ __forceinline__ void ctxSave(T* __restrict__ cx, const GS<T>& S, int ncon, int nd, T qfs, T qas, const Ln L) {
   gcopy(cx + CTX_M, S.M, MSZ, L);
   if (G == 16 || L.gl < 16) { cx[CTX_QFS + L.gl] = qfs; cx[CTX_QAS + L.gl] = qas; }
-  gcopy(cx + CTX_W, S.wrec, nw * CRW, L);
-  const int nh = ncon - nw < NHS ? ncon - nw : NHS;
+  gcopy(cx + CTX_W, S.wrec, (nd < NDS ? nd : NDS) * CRW, L);    // dense records beyond NDS already live in the global scratch
+  const int nh = ncon - nd < NHS ? ncon - nd : NHS;
   gcopy(cx + CTX_H, S.hrec, nh * CRH, L);
 }
-template <typename T> __device__ __forceinline__ void ctxLoad(const T* __restrict__ cx, GS<T>& S, int ncon, int nw, T& qfs, T& qas, const Ln L) {
+template <typename T> __device__ __forceinline__ void ctxLoad(const T* __restrict__ cx, GS<T>& S, int ncon, int nd, T& qfs, T& qas, const Ln L) {
   gcopy(S.M, cx + CTX_M, MSZ, L);
   qfs = cx[CTX_QFS + L.gi]; qas = cx[CTX_QAS + L.gi];
   if (L.gl >= NV) { qfs = 0; qas = 0; }
-  gcopy(S.wrec, cx + CTX_W, nw * CRW, L);
-  const int nh = ncon - nw < NHS ? ncon - nw : NHS;
+  gcopy(S.wrec, cx + CTX_W, (nd < NDS ? nd : NDS) * CRW, L);
+  const int nh = ncon - nd < NHS ? ncon - nd : NHS;
   gcopy(S.hrec, cx + CTX_H, nh * CRH, L);
   __syncwarp(L.mask);
 }

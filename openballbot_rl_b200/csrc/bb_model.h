@@ -147,17 +147,32 @@ inline void buildModelConst(ModelConst<double>& mc) {
       for (int k = 0; k < 3; k++) { double e[3] = {0, 0, 0}; e[k] = 1; const double cx[3] = {e[1] * d[2] - e[2] * d[1], e[2] * d[0] - e[0] * d[2], e[0] * d[1] - e[1] * d[0]};
         for (int r = 0; r < 3; r++) Jb[r][12 + k] = cx[r]; } }
     const double wb = invw(Jb);
-    for (int i = 0; i < 3; i++) {
+    // invweight0 of a base-tree body at its own COM r (base frame; R_B = 1 at qpos0): v = v_B + w x r (+ hinge column)
+    auto invwBase = [&](const double* r, int wheel) {
       double Jw[3][NV]; std::memset(Jw, 0, sizeof(Jw));
-      const double r[3] = {mc.anc[i][0] + mc.s0[i][0], mc.anc[i][1] + mc.s0[i][1], mc.anc[i][2] + mc.s0[i][2]};
       for (int k = 0; k < 3; k++) Jw[k][k] = 1;
       for (int k = 0; k < 3; k++) { double e[3] = {0, 0, 0}; e[k] = 1; const double cx[3] = {e[1] * r[2] - e[2] * r[1], e[2] * r[0] - e[0] * r[2], e[0] * r[1] - e[1] * r[0]};
         for (int q = 0; q < 3; q++) Jw[q][3 + k] = cx[q]; }
-      { const double* a = mc.ax[i]; const double* sv = mc.s0[i]; const double cx[3] = {a[1] * sv[2] - a[2] * sv[1], a[2] * sv[0] - a[0] * sv[2], a[0] * sv[1] - a[1] * sv[0]};
-        for (int q = 0; q < 3; q++) Jw[q][6 + i] = cx[q]; }
-      mc.dA[i] = wb + invw(Jw);
+      if (wheel >= 0) { const double* a = mc.ax[wheel]; const double* sv = mc.s0[wheel]; const double cx[3] = {a[1] * sv[2] - a[2] * sv[1], a[2] * sv[0] - a[0] * sv[2], a[0] * sv[1] - a[1] * sv[0]};
+        for (int q = 0; q < 3; q++) Jw[q][6 + wheel] = cx[q]; }
+      return invw(Jw);
+    };
+    for (int i = 0; i < 3; i++) {
+      const double r[3] = {mc.anc[i][0] + mc.s0[i][0], mc.anc[i][1] + mc.s0[i][1], mc.anc[i][2] + mc.s0[i][2]};
+      const double ww = invwBase(r, i);
+      mc.dA[i] = wb + ww;          // ball x wheel_i
+      mc.dA[6 + i] = ww;           // heightfield x wheel_i (the world body has no inverse weight)
     }
-    mc.dA[3] = wb;
+    mc.dA[3] = wb;                 // heightfield x ball
+    for (int i = 0; i < 2; i++) {  // camera bodies: their only massive geom is the stick, COM = stick centre
+      const double wc = invwBase(mc.stick_c[i], -1);
+      mc.dA[4 + i] = wc; mc.dA[10 + i] = wb + wc;
+    }
+    {  // base body proper: tower cylinder + ballast box
+      double mt, it, ia; cylinder(0.11, 0.14, 23.6, &mt, &it, &ia);
+      const double mb = 400.0 * 0.008, r[3] = {0, 0, (mt * 0.2 + mb * 0.002) / (mt + mb)};
+      mc.dA[9] = wb + invwBase(r, -1);
+    }
   }
 }
 

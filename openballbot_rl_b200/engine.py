@@ -25,7 +25,7 @@ class BallbotEngine:
                  cameras=True, im_h=64, im_w=64, camera_frame_rate=90.0, max_ep_steps=4000, max_allowed_tilt=20.0,
                  max_wheel_velocity=10.0, reward="directional", reward_scale=0.01, action_reg_coef=-0.0001,
                  survival_bonus=0.02, target_direction=(0.0, 1.0), goal_position=(0.0, 0.0), distance_scale=1.0, seed=0,
-                 auto_reset=True, env_offset=0, step_kernel="warp", solver="exact"):
+                 auto_reset=True, env_offset=0, step_kernel="warp", solver="exact", perlin_table=None, seed_stream="counter"):
         if not torch.cuda.is_available():
             raise EngineError("BallbotEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
         L = _lib.lib()
@@ -47,6 +47,8 @@ class BallbotEngine:
         cfg.distance_scale = float(distance_scale); cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF; cfg.auto_reset = int(bool(auto_reset))
         cfg.step_kernel = {"warp": 0, "split": 0, "thread": 1, "fused": 2}[step_kernel]
         cfg.solver_mode = {"exact": 0, "fast": 1}[solver]
+        cfg.perlin_table = -1 if perlin_table is None else int(bool(perlin_table))
+        cfg.seed_stream = {"counter": 0, "pcg64": 1}[seed_stream]
         self.cfg = cfg
         self._L = L
         self._h = C.c_void_p()
@@ -58,7 +60,7 @@ class BallbotEngine:
         self.cameras = bool(cameras)
         self.im_h, self.im_w = int(im_h), int(im_w)
         self.precision = int(precision)
-        N, dev = self.num_envs, self.device
+        N, dev = self.num_envs, self.device      # every tensor names its device explicitly: the caller's current device is irrelevant
         f32 = dict(dtype=torch.float32, device=dev)
         self.obs = {k: torch.zeros(N, 3, **f32) for k in OBS_KEYS}
         self.obs["relative_image_timestamp"] = torch.zeros(N, 1, **f32)
@@ -106,8 +108,11 @@ class BallbotEngine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ------------------------------------------------------------------ hot path
-    def reset(self, mask=None):
-        """Reset the envs selected by ``mask`` (uint8/bool CUDA tensor [N]; None = all). Returns the obs dict."""
+    def reset(self, mask=None, seeds=None):
+        """Reset the envs selected by ``mask`` (uint8/bool CUDA tensor [N]; None = all). ``seeds`` (int32 [N], optional) fixes the
+        terrain seed ``r_seed`` of the selected envs (ballbot_env.py:505-510) instead of drawing it. Returns the obs dict."""
+        if seeds is not None:
+            seeds = torch.as_tensor(seeds, dtype=torch.int32, device=self.device).reshape(self.num_envs).contiguous()
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
             keep = (mask == 0)
@@ -115,7 +120,7 @@ class BallbotEngine:
             self.pos2d.mul_(keep[:, None])
         else:
             self.reward.zero_(); self.terminated.zero_(); self.failure.zero_(); self.pos2d.zero_()
-        self._check(self._L.bb_reset(self._h, _ptr(mask), C.byref(self._io), self._stream()), "bb_reset")
+        self._check(self._L.bb_reset(self._h, _ptr(mask), _ptr(seeds), C.byref(self._io), self._stream()), "bb_reset")
         return self.obs
 
     def step(self, actions):
@@ -178,16 +183,44 @@ class BallbotEngine:
         self._check(self._L.bb_render_depth(self._h, _ptr(a), _ptr(b), self._stream()), "bb_render_depth")
         return a, b
 
+    def seed_pcg64(self, seeds):
+        """numpy-compatible terrain-seed streams (``seed_stream="pcg64"``): env i continues ``np.random.default_rng(seeds[i])``
+        exactly like the reference's per-env ``self._np_random`` (ballbot_env.py:378-384, 505-507)."""
+        seeds = np.atleast_1d(np.asarray(seeds)).astype(np.int64)
+        if seeds.shape != (self.num_envs,):
+            raise ValueError(f"seeds must have shape ({self.num_envs},)")
+        st = np.zeros((self.num_envs, 5), np.uint64)
+        m64 = (1 << 64) - 1
+        for i, sd in enumerate(seeds):
+            s = np.random.PCG64(int(sd)).state
+            v, inc = s["state"]["state"], s["state"]["inc"]
+            st[i] = (v >> 64, v & m64, inc >> 64, inc & m64, int(s["has_uint32"]) | (int(s["uinteger"]) << 32))
+        t = torch.from_numpy(st.view(np.int64)).to(self.device)
+        self._check(self._L.bb_set_rng_state(self._h, _ptr(t), self._stream()), "bb_set_rng_state")
+        torch.cuda.current_stream(self.device).synchronize()
+
+    @staticmethod
+    def _contact_rows(rows, n):
+        r = rows.cpu().numpy()[:n]
+        return dict(type=r[:, 0].astype(np.int32), dist=r[:, 1], pos=r[:, 2:5], frame=r[:, 5:14].reshape(n, 3, 3))
+
     def probe_forward(self, env, ctrl=(0.0, 0.0, 0.0)):
-        """One forward-dynamics evaluation of env ``env`` at its current state (solver / contact parity probe)."""
+        """One forward-dynamics evaluation of env ``env`` at its current state through the production device code
+        (solver / contact parity probe): qacc, qacc_smooth, qfrc_smooth, iteration count and the contact set."""
         dev = self.device
         c = torch.tensor(ctrl, dtype=torch.float64, device=dev)
-        out = torch.zeros(64, dtype=torch.float64, device=dev); cd = torch.zeros(53, dtype=torch.float64, device=dev)
-        cp = torch.zeros(53, 3, dtype=torch.float64, device=dev); cf = torch.zeros(53, 9, dtype=torch.float64, device=dev)
-        self._check(self._L.bb_probe_forward(self._h, int(env), _ptr(c), _ptr(out), _ptr(cd), _ptr(cp), _ptr(cf), self._stream()), "bb_probe_forward")
+        out = torch.zeros(64, dtype=torch.float64, device=dev)
+        rows = torch.zeros(_lib.PROBE_MAXCON, _lib.CONTACT_STRIDE, dtype=torch.float64, device=dev)
+        self._check(self._L.bb_probe_forward(self._h, int(env), _ptr(c), _ptr(out), _ptr(rows), self._stream()), "bb_probe_forward")
         o = out.cpu().numpy(); n = int(o[45])
-        return dict(qacc=o[:15], qacc_smooth=o[15:30], qfrc_smooth=o[30:45], ncon=n, niter=int(o[46]), consts=o[47:54],
-                    dist=cd.cpu().numpy()[:n], pos=cp.cpu().numpy()[:n], frame=cf.cpu().numpy()[:n].reshape(n, 3, 3))
+        return dict(qacc=o[:15], qacc_smooth=o[15:30], qfrc_smooth=o[30:45], ncon=n, niter=int(o[46]), consts=o[47:54], **self._contact_rows(rows, n))
+
+    def get_contacts(self, env):
+        """mjData.contact of env ``env`` at its current state: dict(type, dist, pos, frame)."""
+        rows = torch.zeros(_lib.PROBE_MAXCON, _lib.CONTACT_STRIDE, dtype=torch.float64, device=self.device)
+        n = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._check(self._L.bb_get_contacts(self._h, int(env), _ptr(rows), _ptr(n), self._stream()), "bb_get_contacts")
+        return self._contact_rows(rows, int(n.item()))
 
     def profile_begin(self, max_steps):
         self._check(self._L.bb_profile_begin(self._h, int(max_steps)), "bb_profile_begin")
@@ -243,7 +276,11 @@ class BallbotEngine:
         return self._hbuf
 
 
+def build_info():
+    return _lib.lib().bb_build_info().decode()
+
+
 def model_constants():
-    dA = (C.c_double * 4)(); mi = C.c_double(); ms = (C.c_double * 3)()
+    dA = (C.c_double * 12)(); mi = C.c_double(); ms = (C.c_double * 3)()
     _lib.lib().bb_model_constants(dA, C.byref(mi), ms)
     return dict(dA=np.array(dA[:]), meaninertia=mi.value, masses=np.array(ms[:]))

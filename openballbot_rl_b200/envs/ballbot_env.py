@@ -16,9 +16,17 @@ from .vec_env import BUILTIN_REWARDS, BUILTIN_TERRAINS, resolve_zscale
 
 _default_dtype = np.float32
 
+try:  # pragma: no cover - gymnasium is not installed in the build image
+    import gymnasium as _gym
+    _EnvBase = _gym.Env          # gym.make("ballbot-v0.1") / Monitor / SB3 wrappers check isinstance(env, gymnasium.Env)
+except Exception:
+    _EnvBase = object
 
-class BBotSimulation:
+
+class BBotSimulation(_EnvBase):
     metadata = {"render_modes": ["rgb_array"], "render_fps": 30}
+    if _EnvBase is object:   # gymnasium.Env provides the same property over the same `_np_random` attribute
+        np_random = property(lambda self: self._np_random)
 
     def __init__(self, xml_path=None, GUI=False, im_shape={"h": 64, "w": 64}, disable_cameras=False, depth_only=True,
                  log_options={"cams": False, "reward_terms": False}, max_ep_steps=None, terrain_type: str = "perlin",
@@ -64,7 +72,6 @@ class BBotSimulation:
         self.num_episodes = -1
         self.eval_env = eval_env[0]
         self._np_random = np.random.default_rng(eval_env[1]) if self.eval_env else None
-        self.np_random = None
         self.verbose = False
         self.step_counter = 0
         self.G_tau = 0.0
@@ -75,12 +82,12 @@ class BBotSimulation:
         self._reward_on_device = rtype == "directional"
         self.engine = BallbotEngine(
             num_envs=1, device=device, precision=precision, terrain="external", hfield_zscale=resolve_zscale(terrain_config),
+            perlin={k: tcfg[k] for k in ("scale", "octaves", "persistence", "lacunarity", "amplitude") if k in tcfg},
             cameras=not disable_cameras, im_h=h, im_w=w, camera_frame_rate=self.camera_frame_rate, max_ep_steps=self.max_ep_steps,
             max_allowed_tilt=self.max_allowed_tilt, max_wheel_velocity=self.max_wheel_velocity,
             reward="directional" if self._reward_on_device else "external", reward_scale=self.reward_scale,
             action_reg_coef=self.action_reg_coef, survival_bonus=self.survival_bonus,
             target_direction=rcfg.get("target_direction", [0.0, 1.0]), auto_reset=False)
-        self._perlin_params = {k: tcfg[k] for k in ("scale", "octaves", "persistence", "lacunarity", "amplitude") if k in tcfg}
         self._reset_goal_and_reward_objs()
 
     # ------------------------------------------------------------------ reference helpers
@@ -111,10 +118,10 @@ class BBotSimulation:
 
     # ------------------------------------------------------------------ gym.Env API
     def reset(self, seed=None, goal: str = "random", **kwargs):
-        if seed is not None or self.np_random is None:
-            self.np_random = np.random.default_rng(seed)
-        if self._np_random is None:
-            self._np_random = self.np_random
+        # gymnasium's Env.reset(seed=s) re-creates `_np_random` -- the very attribute the reference draws terrain seeds from
+        # (ballbot_env.py:378-384, 596-599): an explicit seed replaces the stream even for eval envs, no seed continues it
+        if seed is not None or self._np_random is None:
+            self._np_random = np.random.default_rng(seed)
         self._reset_goal_and_reward_objs()
         self.step_counter = 0
         tcfg = self.terrain_config.get("config", {}) or {}

@@ -16,6 +16,13 @@ from ..core.factories import create_reward, create_terrain
 from ..engine import BallbotEngine, OBS_KEYS
 from .spaces import create_action_space, create_observation_space
 
+try:  # pragma: no cover - stable_baselines3 is not installed in the build image
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase     # isinstance(env, VecEnv) must hold for PPO(..., env)
+    HAVE_SB3 = True
+except Exception:
+    _VecEnvBase = object
+    HAVE_SB3 = False
+
 BUILTIN_TERRAINS = ("perlin", "flat")
 BUILTIN_REWARDS = ("directional", "distance")
 HFIELD_HALF_EXTENT = 5.0      # ballbot.xml:23 size[0]
@@ -33,10 +40,17 @@ def resolve_zscale(terrain_config: dict) -> float:
     return DEFAULT_ZSCALE
 
 
-class BallbotVecEnv:
+class BallbotVecEnv(_VecEnvBase):
+    """``output="numpy"`` returns host arrays with SubprocVecEnv's conventions and, when stable_baselines3 is importable, the
+    class IS an SB3 ``VecEnv`` (``PPO("MultiInputPolicy", BallbotVecEnv(N, output="numpy"))`` runs unmodified).
+    ``output="torch"`` hands out the engine's persistent device tensors: ``reward`` / ``infos`` values are clones, but the
+    observation dict aliases buffers that the next ``step`` overwrites (clone what must outlive a step); its
+    ``terminal_observation`` is the [N,16] proprio block (no images)."""
+
     def __init__(self, num_envs: int, terrain_config: Optional[dict] = None, reward_config: Optional[dict] = None,
                  env_config: Optional[dict] = None, seed: int = 0, disable_cams: bool = False, device: int = 0, precision: int = 64,
-                 output: str = "torch", solver: str = "exact", env_offset: int = 0, terrain_type: Optional[str] = None):
+                 output: str = "torch", solver: str = "exact", env_offset: int = 0, terrain_type: Optional[str] = None,
+                 env_seeds=None, perlin_table: Optional[bool] = None):
         import openballbot_rl_b200.rewards  # noqa: F401  (registers the built-ins)
         import openballbot_rl_b200.terrain  # noqa: F401
         if terrain_config is None:
@@ -83,7 +97,12 @@ class BallbotVecEnv:
             action_reg_coef=rcfg.get("action_reg_coef", -0.0001), survival_bonus=rcfg.get("survival_bonus", 0.02),
             target_direction=rcfg.get("target_direction", [0.0, 1.0]), goal_position=rcfg.get("goal_position", [0.0, 0.0]),
             distance_scale=rcfg.get("scale", 1.0) if rtype == "distance" else 1.0,
-            seed=seed, auto_reset=not self._manual_reset, env_offset=env_offset, solver=solver)
+            seed=seed, auto_reset=not self._manual_reset, env_offset=env_offset, solver=solver, perlin_table=perlin_table,
+            seed_stream="pcg64" if env_seeds is not None else "counter")
+        if env_seeds is not None:
+            # the reference's per-env generators: training env i is seeded with seed + i by SB3, eval env i is built with
+            # eval_env=[True, seed + N + i] (train.py:83-97); terrain seeds are then integers(0, 10000) draws of that PCG64
+            self.engine.seed_pcg64(env_seeds)
         self.observation_space = create_observation_space({"h": im_h, "w": im_w}, 1, disable_cams)
         self.action_space = create_action_space()
         self._rng = np.random.default_rng(seed)       # terrain seeds of plugin terrains (ballbot_env.py:505-510)
@@ -93,6 +112,8 @@ class BallbotVecEnv:
         self.last_terrain_seeds = np.zeros(self.num_envs, np.int64)
         self.render_mode = None
         self._closed = False
+        if HAVE_SB3:   # pragma: no cover
+            _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
 
     # ------------------------------------------------------------------ helpers
     @property
@@ -123,7 +144,13 @@ class BallbotVecEnv:
         self.engine.set_hfield(env_ids.astype(np.int32), fields)
 
     # ------------------------------------------------------------------ VecEnv protocol
-    def reset(self):
+    def reset(self, terrain_seeds=None):
+        """``terrain_seeds`` (int[N], optional): replay recorded ``r_seed`` values instead of drawing them (built-in perlin)."""
+        if terrain_seeds is not None:
+            if self._terrain_plugin:
+                raise ValueError("terrain_seeds applies to the built-in perlin terrain")
+            self.engine.reset(seeds=terrain_seeds)
+            return self._obs_view()
         if self._terrain_shared:
             if not getattr(self, "_shared_uploaded", False):
                 cfg = self.terrain_config.get("config", {}) or {}
@@ -160,9 +187,12 @@ class BallbotVecEnv:
                 eng.reset(done_mask)
                 eng.reward.copy_(rew); eng.terminated.copy_(term); eng.failure.copy_(fail); eng.pos2d.copy_(pos)
         if self.output == "torch":
-            infos = {"failure": eng.failure, "pos2d": eng.pos2d, "terminal_observation": eng.terminal_obs if term_obs is None else term_obs,
-                     "episode_r": eng.episode_return, "episode_l": eng.episode_length}
-            return self._obs_view(), eng.reward, eng.terminated.bool(), infos
+            # [N]-sized results are handed out as fresh tensors (SubprocVecEnv returns new arrays every step); only the large
+            # observation buffers alias engine memory
+            infos = {"failure": eng.failure.clone(), "pos2d": eng.pos2d.clone(),
+                     "terminal_observation": eng.terminal_obs.clone() if term_obs is None else term_obs,
+                     "episode_r": eng.episode_return.clone(), "episode_l": eng.episode_length.clone()}
+            return self._obs_view(), eng.reward.clone(), eng.terminated.bool(), infos
         obs = self._obs_view()
         rewards = eng.reward.cpu().numpy()
         dones = eng.terminated.cpu().numpy().astype(bool)

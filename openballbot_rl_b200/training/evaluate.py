@@ -10,11 +10,17 @@ import torch
 
 
 @torch.no_grad()
-def evaluate_policy(venv, policy: Callable, max_steps: int = 4000, deterministic: bool = True) -> Dict[str, torch.Tensor]:
+def evaluate_policy(venv, policy: Callable, max_steps: int = 4000, deterministic: bool = True, terrain_seeds=None,
+                    reset: bool = True) -> Dict[str, torch.Tensor]:
     """Returns per-env ``returns`` / ``lengths`` / ``failure`` of the first episode of every env (torch-output ``BallbotVecEnv``).
-    ``policy(obs_dict, deterministic=...) -> actions [N,3]`` (e.g. ``BallbotPolicy``)."""
+    ``policy(obs_dict, deterministic=...) -> actions [N,3]`` (e.g. ``BallbotPolicy``).  ``terrain_seeds`` replays recorded
+    ``r_seed`` values (the terrains of an archived evaluation) instead of drawing new ones; ``reset=False`` starts from the
+    venv's current (freshly reset) state."""
     N, dev = venv.num_envs, venv.engine.device
-    obs = venv.reset()
+    if not reset:
+        obs = venv._obs_view()
+    else:
+        obs = venv.reset(terrain_seeds=terrain_seeds) if terrain_seeds is not None else venv.reset()
     ret = torch.zeros(N, device=dev); length = torch.zeros(N, dtype=torch.int32, device=dev)
     alive = torch.ones(N, dtype=torch.bool, device=dev); failed = torch.zeros(N, dtype=torch.bool, device=dev)
     for t in range(max_steps):

@@ -61,9 +61,9 @@ int hc_forward(int prec, const double* qpos, const double* qvel, const double* c
 void hc_step(int prec, double* qpos, double* qvel, double* warm, const double* ctrl, const float* hf, double zscale, double* kin, int* ncon, int* niter) {
   if (prec == 32) step<float>(qpos, qvel, warm, ctrl, hf, zscale, kin, ncon, niter); else step<double>(qpos, qvel, warm, ctrl, hf, zscale, kin, ncon, niter);
 }
-void hc_model(double* dA4, double* meaninertia, double* masses3 /*m0,mw,mL*/, double* c0) {
+void hc_model(double* dA12, double* meaninertia, double* masses3 /*m0,mw,mL*/, double* c0) {
   const ModelConst<double>& m = model<double>();
-  for (int i = 0; i < 4; i++) dA4[i] = m.dA[i];
+  for (int i = 0; i < NCT; i++) dA12[i] = m.dA[i];
   *meaninertia = m.meaninertia; masses3[0] = m.m0; masses3[1] = m.mw; masses3[2] = m.mL;
   for (int i = 0; i < 3; i++) c0[i] = m.c0[i];
 }

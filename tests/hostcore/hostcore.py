@@ -9,7 +9,7 @@ _SO = os.path.join(_HERE, "libbb_hostcore.so")
 _SRC = [os.path.join(_HERE, "hostcore.cpp"),
         os.path.join(_HERE, "..", "..", "openballbot_rl_b200", "csrc", "bb_core.cuh"),
         os.path.join(_HERE, "..", "..", "openballbot_rl_b200", "csrc", "bb_model.h")]
-NQ, NV, NC = 17, 15, 53
+NQ, NV, NC = 17, 15, 64
 
 
 def build(force=False):
@@ -55,6 +55,6 @@ def step(qpos, qvel, warm, ctrl, hfield=None, zscale=2.0, prec=64):
 
 
 def model():
-    dA = np.zeros(4); mi = C.c_double(); ms = np.zeros(3); c0 = np.zeros(3)
+    dA = np.zeros(12); mi = C.c_double(); ms = np.zeros(3); c0 = np.zeros(3)
     lib().hc_model(_p(dA), C.byref(mi), _p(ms), _p(c0))
     return dict(dA=dA, meaninertia=mi.value, masses=ms, c0=c0)

@@ -28,10 +28,17 @@ def test_header_and_library_agree():
 def test_config_struct_layout_matches_header():
     from openballbot_rl_b200 import _lib
     cfg = _lib.default_config()                           # bb_default_config runs on the host, no GPU needed
-    assert cfg.abi_version == 1 and cfg.precision == 64 and cfg.perlin_octaves == 4 and cfg.max_ep_steps == 4000
+    assert cfg.abi_version == 2 and cfg.perlin_table == -1 and cfg.seed_stream == 0 and cfg.precision == 64 and cfg.perlin_octaves == 4 and cfg.max_ep_steps == 4000
     assert abs(cfg.perlin_scale - 25.0) < 1e-6 and abs(cfg.reward_scale - 0.01) < 1e-9 and abs(cfg.survival_bonus - 0.02) < 1e-9
     assert abs(cfg.action_reg_coef + 1e-4) < 1e-9 and cfg.target_direction[1] == 1.0 and cfg.auto_reset == 1
     assert cfg.step_kernel == 0 and cfg.solver_mode == 0 and cfg.im_h == 64 and abs(cfg.hfield_zscale - 2.0) < 1e-6
+
+
+def test_build_info_names_the_current_sources():
+    from openballbot_rl_b200 import _lib
+    _lib.build()
+    info = _lib.lib().bb_build_info().decode()
+    assert info.startswith("libballbot_b200 abi 2 built ") and info.endswith("src " + _lib.source_hash()), info
 
 
 def test_engine_refuses_to_run_without_cuda():

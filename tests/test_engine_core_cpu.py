@@ -31,7 +31,9 @@ def _contact_state(rng, pen):
 def test_model_constants_agree(oracle_mod):
     mo, mh = oracle_mod.model_constants(), H.model()
     iw = mo["invweight0"][:, 0]
-    np.testing.assert_allclose(mh["dA"], [iw[7] + iw[4], iw[7] + iw[5], iw[7] + iw[6], iw[7]], rtol=1e-12)
+    # diagApprox per contact type: ball x wheel_i, hfield x ball, hfield x stick_i (cam bodies 2, 3), hfield x wheel_i, ball x tower, ball x stick_i
+    np.testing.assert_allclose(mh["dA"], [iw[7] + iw[4], iw[7] + iw[5], iw[7] + iw[6], iw[7], iw[2], iw[3], iw[4], iw[5], iw[6],
+                                          iw[7] + iw[1], iw[7] + iw[2], iw[7] + iw[3]], rtol=1e-11)
     assert abs(mh["meaninertia"] - mo["meaninertia"]) < 1e-13
     np.testing.assert_allclose(mh["masses"], [mo["mass"][1:4].sum(), mo["mass"][4], mo["mass"][7]], rtol=1e-13)
 
@@ -109,3 +111,46 @@ def test_stale_observation_kinematics(oracle_mod):
     np.testing.assert_allclose(kin[7:10], cvel[3:6], atol=1e-11)            # "angular_vel" <- cvel[3:6] (linear, at subtree COM)
     np.testing.assert_allclose(kin[10:13], xpos, atol=1e-12)
     assert np.abs(xquat - q[3:7]).max() > 1e-9                               # and it really is stale w.r.t. the new qpos
+
+
+def _rough_state(rng, hf2d, tilt, ball_noise, lift=0.0):
+    """Robot dropped onto rough terrain with a large tilt: wheel / stick capsules reach the heightfield, the ball may touch the tower."""
+    qpos = QPOS0.copy()
+    ax = rng.normal(size=3); ax[2] *= 0.2; ax /= np.linalg.norm(ax); ang = np.radians(rng.uniform(0, tilt))
+    q = np.r_[np.cos(ang / 2), np.sin(ang / 2) * ax]; qpos[3:7] = q
+    qpos[7:10] = rng.normal(size=3)
+    ql = rng.normal(size=4); ql /= np.linalg.norm(ql); qpos[13:17] = ql
+    xy = rng.uniform(-1.5, 1.5, 2)
+    c, r = (xy + 5) / 10 * 292
+    h = 2.0 * hf2d[int(round(r)), int(round(c))]
+    bc = np.array([xy[0], xy[1], h + 0.09 - rng.uniform(0, 0.02)])
+    qpos[10:13] = bc - _rot(ql) @ np.array([0, 0, -0.14])
+    qpos[0:3] = bc - _rot(q) @ (np.array([0, 0, -0.12 + lift]) + rng.normal(size=3) * ball_noise)
+    return qpos, rng.normal(size=15) * 0.3
+
+
+def test_extra_collision_pairs_agree(oracle_mod):
+    """Round-2 pairs (ORACLE_ASSUMPTIONS 7b): wheel and camera-stick capsules against the heightfield, ball against the sticks
+    (patched sphere-capsule) and the tower cylinder.  Contact sets (count, type, dist, pos, frame), Newton iterations and qacc of
+    the engine core against the oracle on tilted robots over a rough (fast_sin) Perlin field."""
+    rng = np.random.default_rng(5)
+    hf = oracle_mod.perlin_terrain(seed=77); hf2d = hf.reshape(293, 293)
+    e = oracle_mod.OracleEnv(); e.reset(hf)
+    pair2type = {0: 0, 1: 1, 2: 2, 3: 3, 5: 4, 6: 5, 7: 6, 8: 7, 9: 8, 10: 9, 11: 10, 12: 11}
+    seen = set()
+    for t in range(400):
+        qpos, qvel = _rough_state(rng, hf2d, 70.0 if t % 2 else 35.0, 0.03 if t % 4 == 0 else 0.004, rng.uniform(0.085, 0.1) if t % 10 == 0 else 0.0)
+        ctrl = rng.uniform(-10, 10, 3); warm = rng.normal(size=15) * (t % 2)
+        e.set_state(qpos, qvel, warm); fo = e.forward(ctrl); co = e.contacts()
+        if co["n"] >= 60:
+            continue                                                         # capacity edge (64 contacts): not compared
+        fh = H.forward(qpos, qvel, ctrl, warm, hf)
+        assert fh["ncon"] == co["n"], (t, fh["ncon"], co["n"])
+        np.testing.assert_array_equal(fh["type"], [pair2type[int(p)] for p in co["pair"]])
+        np.testing.assert_allclose(fh["dist"], co["dist"], atol=1e-13)
+        np.testing.assert_allclose(fh["pos"], co["pos"], atol=1e-13)
+        np.testing.assert_allclose(fh["frame"], co["frame"], atol=1e-11)
+        assert fh["niter"] == fo["niter"], t
+        assert np.abs(fh["qacc"] - fo["qacc"]).max() / max(1.0, np.abs(fo["qacc"]).max()) < 1e-8, t
+        seen.update(int(x) for x in fh["type"])
+    assert {4, 5, 6, 7, 8, 9, 10, 11} <= seen, seen                          # every new pair type occurred

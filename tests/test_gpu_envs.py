@@ -189,24 +189,54 @@ def test_fast_solver_mode_within_baseline_tolerance(oracle_mod):
     eng.close()
 
 
-def test_fixed_policy_episode_on_engine_matches_reference_eval(oracle_mod):
-    """The archived reference policy closed over the CUDA engine (device-resident obs -> torch policy -> bb_step):
-    reference recorded return 9.198632 / length 378 (deterministic eval, flat terrain)."""
-    import os
+# measured signed errors (engine vs the reference's own recorded deterministic episode), bounds ~1.5x: see tests/test_oracle.py
+FLAT_PAIRS = {"flat_seed10_10M": (0.036, 0.020), "flat_seed10_best150k": (0.010, 0.006), "flat_1M_800k": (0.006, 0.006),
+              "flat_1M_best100k": (0.004, 0.008), "flat_seed10_9p8M": (0.65, 0.55)}
+
+
+@pytest.mark.parametrize("name", list(FLAT_PAIRS))
+def test_fixed_policy_flat_episodes_on_engine_match_reference_evals(name):
+    """Every archived flat-terrain (policy zip, deterministic evaluation) pair closed over the CUDA engine
+    (device-resident obs -> torch policy -> bb_step); tests/golden/make_policy_pairs.py."""
     from openballbot_rl_b200.envs import BallbotVecEnv
-    from openballbot_rl_b200.training.policy import BallbotPolicy
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policy_flat_10M.npz"))
-    pol = BallbotPolicy().load_sb3_state({k: z[k] for k in z.files if not k.startswith(("eval_", "train_"))}).eval().cuda()
-    ref_ret, ref_len = float(z["eval_return"][0]), int(z["eval_length"][0])
-    N = 4
-    venv = BallbotVecEnv(N, terrain_config={"type": "flat", "config": {}}, reward_config=REWARD, env_config=ENV_CFG, precision=64)
-    venv.engine.cfg  # noqa: B018
     from openballbot_rl_b200.training.evaluate import evaluate_policy
-    out = evaluate_policy(venv, pol, max_steps=600, deterministic=True)
+    from tests import policy_pairs as P
+    m = P.meta(name); pol = P.policy(name, "cuda")
+    ref_len, ref_ret = m["eval_lengths"][0], m["eval_returns"][0]
+    venv = BallbotVecEnv(4, terrain_config={"type": "flat", "config": {}}, reward_config=REWARD, env_config=ENV_CFG, precision=64)
+    out = evaluate_policy(venv, pol, max_steps=800, deterministic=True)
     L, G = out["lengths"].cpu().numpy(), out["returns"].cpu().numpy()
     assert (L == L[0]).all()                                        # identical envs, deterministic policy
-    assert abs(int(L[0]) - ref_len) <= 0.08 * ref_len, (L, ref_len)
-    assert abs(float(G[0]) - ref_ret) <= 0.06 * ref_ret, (G, ref_ret)
+    tol_l, tol_r = FLAT_PAIRS[name]
+    assert abs(int(L[0]) - ref_len) <= tol_l * ref_len, (name, L, ref_len)
+    assert abs(float(G[0]) - ref_ret) <= tol_r * ref_ret, (name, G, ref_ret)
+    venv.close()
+
+
+def test_fixed_policy_perlin_first_evaluation_on_engine():
+    """The replayable perlin pin (tests/test_oracle.py::test_fixed_policy_perlin_first_evaluation_matches_reference) on the engine:
+    the eval envs' numpy PCG64 streams run ON THE DEVICE (seed_stream = pcg64, env i <- PCG64(20 + i)), the first reset draws the
+    recorded terrain seeds, and the eight episodes of envs 2..9 are compared with the reference's sorted lengths / returns."""
+    from openballbot_rl_b200.envs import BallbotVecEnv
+    from openballbot_rl_b200.training.evaluate import evaluate_policy
+    from tests import policy_pairs as P
+    m = P.meta("perlin_seed10_best50k"); pol = P.policy("perlin_seed10_best50k", "cuda")
+    venv = BallbotVecEnv(10, terrain_config=PERLIN, reward_config=REWARD, env_config=ENV_CFG, precision=64, env_seeds=[20 + i for i in range(10)])
+    venv.reset()
+    assert venv.engine.terrain_seeds().cpu().numpy()[2:10].tolist() == m["terrain_seeds_env2to9"]     # numpy's first draws, made on the device
+    out = evaluate_policy(venv, pol, max_steps=600, deterministic=True, reset=False)
+    L = np.sort(out["lengths"].cpu().numpy()[2:10]).astype(float)
+    G = out["returns"].cpu().numpy()[2:10][np.argsort(out["lengths"].cpu().numpy()[2:10], kind="stable")]
+    Lr, Gr = np.array(m["eval_lengths"], float), np.array(m["eval_returns"])
+    rel = np.abs(L - Lr) / Lr
+    assert np.sort(rel)[6] < 0.12, (L, Lr)
+    assert abs(np.median(L) - np.median(Lr)) < 0.06 * np.median(Lr), (L, Lr)
+    assert abs(np.median(G) - np.median(Gr)) < 0.15 * np.median(Gr), (G, Gr)
+    venv.close()
+    # same episodes with the seeds passed explicitly (bb_reset seeds_dev): identical lengths
+    venv = BallbotVecEnv(8, terrain_config=PERLIN, reward_config=REWARD, env_config=ENV_CFG, precision=64)
+    out2 = evaluate_policy(venv, pol, max_steps=600, deterministic=True, terrain_seeds=m["terrain_seeds_env2to9"])
+    assert np.array_equal(np.sort(out2["lengths"].cpu().numpy()), L.astype(np.int32))
     venv.close()
 
 
@@ -269,17 +299,15 @@ def test_bb_step_is_cuda_graph_capturable():
 
 def test_stochastic_policy_statistics_vs_reference_training_buffer():
     """Closed loop under the archived policy's own action noise: the reference's Monitor buffer at the 10 M-step checkpoint
-    (last 100 training episodes, flat terrain: return 8.005 +- 0.712, length 318.7 +- 36.0; tests/golden/make_policy_fixture.py)
+    (last 100 training episodes, flat terrain: return 8.005 +- 0.712, length 318.7 +- 36.0; tests/golden/make_policy_pairs.py)
     against first episodes of 512 engine envs driven by the same Gaussian policy.  Not like for like to the last digit -- the
     buffer spans the final policy updates -- so the stated bound is 10 % on the means and 35 % on the spreads (measured:
     339 +- 32 steps, 8.42 +- 0.63 return, i.e. +6 % / +5 %, the same sign and size as the deterministic episode's +2.4 % / +1.3 %)."""
-    import os
     from openballbot_rl_b200.envs import BallbotVecEnv
     from openballbot_rl_b200.training.evaluate import evaluate_policy
-    from openballbot_rl_b200.training.policy import BallbotPolicy
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "policy_flat_10M.npz"))
-    pol = BallbotPolicy().load_sb3_state({k: z[k] for k in z.files if not k.startswith(("eval_", "train_"))}).eval().cuda()
-    ref_l, ref_r = z["train_ep_lengths"].astype(np.float64), z["train_ep_returns"]
+    from tests import policy_pairs as P
+    m = P.meta("flat_seed10_10M"); pol = P.policy("flat_seed10_10M", "cuda")
+    ref_l, ref_r = np.array(m["train_ep_lengths"], np.float64), np.array(m["train_ep_returns"])
     venv = BallbotVecEnv(512, terrain_config={"type": "flat", "config": {}}, reward_config=REWARD, env_config=ENV_CFG, precision=64)
     torch.manual_seed(0)
     out = evaluate_policy(venv, pol, max_steps=700, deterministic=False)

@@ -30,7 +30,11 @@ def test_library_loaded_and_model_constants(oracle_mod):
     from openballbot_rl_b200.engine import model_constants
     mc = model_constants(); mo = oracle_mod.model_constants()
     iw = mo["invweight0"][:, 0]
-    np.testing.assert_allclose(mc["dA"], [iw[7] + iw[4], iw[7] + iw[5], iw[7] + iw[6], iw[7]], rtol=1e-12)
+    np.testing.assert_allclose(mc["dA"], [iw[7] + iw[4], iw[7] + iw[5], iw[7] + iw[6], iw[7], iw[2], iw[3], iw[4], iw[5], iw[6],
+                                          iw[7] + iw[1], iw[7] + iw[2], iw[7] + iw[3]], rtol=1e-11)
+    from openballbot_rl_b200 import _lib
+    from openballbot_rl_b200.engine import build_info
+    assert build_info().endswith("src " + _lib.source_hash()), build_info()       # the loaded .so was built from these sources
     assert abs(mc["meaninertia"] - mo["meaninertia"]) < 1e-12
 
 
