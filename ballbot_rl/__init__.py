@@ -4,7 +4,10 @@ import importlib
 import sys
 
 for _alias, _real in {"ballbot_rl.training": "openballbot_rl_b200.training",
-                      "ballbot_rl.training.utils": "openballbot_rl_b200.training.utils"}.items():
+                      "ballbot_rl.training.utils": "openballbot_rl_b200.training.utils",
+                      "ballbot_rl.policies": "openballbot_rl_b200.policies",                 # registers policy plugin "mlp"
+                      "ballbot_rl.policies.mlp_policy": "openballbot_rl_b200.policies.mlp_policy"}.items():
     _mod = importlib.import_module(_real)
     sys.modules[_alias] = _mod
 training = sys.modules["ballbot_rl.training"]
+policies = sys.modules["ballbot_rl.policies"]

@@ -88,6 +88,46 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+TORCH_OPS_PATH = os.path.join(_PKG, "libballbot_torch_ops.so")
+_TORCH_OPS_SRC = os.path.join(_CSRC, "bb_torch_ops.cpp")
+
+
+def build_torch_ops(force=False):
+    """Compile csrc/bb_torch_ops.cpp (host code: TORCH_LIBRARY(ballbot) over the C ABI) in-tree against the installed torch."""
+    srcs = [_TORCH_OPS_SRC, os.path.join(_PKG, "..", "include", "ballbot_b200.h")]
+    if not force and os.path.exists(TORCH_OPS_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(TORCH_OPS_PATH) for s in srcs):
+        return TORCH_OPS_PATH
+    build()
+    import torch
+    from torch.utils import cpp_extension as X
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = (["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", TORCH_OPS_PATH, _TORCH_OPS_SRC,
+            f"-D_GLIBCXX_USE_CXX11_ABI={int(torch.compiled_with_cxx11_abi())}"]
+           + [f"-I{d}" for d in X.include_paths()] + [f"-I{cuda_home}/include"]
+           + [f"-L{tlib}", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", f"-L{_PKG}", "-lballbot_b200",
+              "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"])
+    subprocess.check_call(cmd)
+    return TORCH_OPS_PATH
+
+
+_torch_ops = None
+
+
+def torch_ops():
+    """torch.ops.ballbot (loads libballbot_torch_ops.so, building it on first use); raises EngineError when it cannot be had."""
+    global _torch_ops
+    if _torch_ops is None:
+        import torch
+        try:
+            lib()                                   # libballbot_b200.so first: the ops library links against it
+            torch.ops.load_library(build_torch_ops())
+        except Exception as exc:
+            raise EngineError(f"torch.ops.ballbot is unavailable ({exc}); the ctypes binding of the same C ABI still works") from exc
+        _torch_ops = torch.ops.ballbot
+    return _torch_ops
+
+
 _lib = None
 
 

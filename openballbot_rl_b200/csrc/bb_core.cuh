@@ -406,8 +406,8 @@ BB_HD void closestSegTriangle(const V3<T>& p0, const V3<T>& p1, const V3<T>& a, 
 template <typename T>
 BB_HD bool capsulePrism(const V3<T>& p0, const V3<T>& p1, T r, const V3<T>& ta, const V3<T>& tb, const V3<T>& tc, T& dist, V3<T>& n, V3<T>& pos) {
   const V3<T> e1 = tb - ta, e2 = tc - ta;
-  V3<T> nn = cross(e1, e2); if (nn.z < 0) nn = -nn;
-  nn = nn * ((T)1 / bsqrt(dot(nn, nn)));
+  const V3<T> nc = cross(e1, e2);
+  const V3<T> nn = nc * ((nc.z < 0 ? (T)-1 : (T)1) / bsqrt(dot(nc, nc)));   // upward unit normal of the top plane
   V3<T> ps = p0, pt = ta;
   closestSegTriangle(p0, p1, ta, tb, tc, ps, pt);
   const T h0 = dot(p0 - ta, nn), h1 = dot(p1 - ta, nn);
@@ -423,6 +423,10 @@ BB_HD bool capsulePrism(const V3<T>& p0, const V3<T>& p1, T r, const V3<T>& ta, 
   if (dl >= r || dl < (T)1e-15) return false;
   dist = dl - r; n = dv * ((T)1 / dl); pos = pt + n * ((T)0.5 * dist);
   return true;
+}
+template <typename T>
+BB_NOINL bool capsulePrismNoInline(const V3<T>& p0, const V3<T>& p1, T r, const V3<T>& ta, const V3<T>& tb, const V3<T>& tc, T& dist, V3<T>& n, V3<T>& pos) {
+  return capsulePrism(p0, p1, r, ta, tb, tc, dist, n, pos);
 }
 // heightfield sub-grid of an axis-aligned box [lo, hi] (mjc_ConvexHField): false = the box misses the field
 template <typename T> struct HfGrid { int cmin, cmax, rmin, rmax; T dx, zmin; };
@@ -561,8 +565,8 @@ BB_HD void collide(const ModelConst<T>& mc, const Geo<T>& g, const V3<T>* capC, 
   }
   // ---- the other colliding geoms (ballbot.xml:41-69): camera sticks and wheel capsules against the heightfield, then the ball
   // against the sticks (patched sphere-capsule) and the tower cylinder.  Order = the oracle's.
-#pragma unroll 1
-  for (int gi = 0; gi < 5; gi++) {
+#pragma unroll
+  for (int gi = 0; gi < 5; gi++) {   // unrolled: capC / capU stay statically indexed
     V3<T> cc, cu; T rad, hl; int ty;
     if (gi < 2) { cc = g.pB + rot(g.RB, ld3(mc.stick_c[gi])); cu = rot(g.RB, ld3(mc.stick_u[gi])); rad = mc.stick_r; hl = mc.stick_hl; ty = 4 + gi; }
     else { cc = capC[gi - 2]; cu = capU[gi - 2]; rad = mc.wheel_r; hl = mc.wheel_hl; ty = 6 + gi - 2; }
@@ -578,7 +582,7 @@ BB_HD void collide(const ModelConst<T>& mc, const Geo<T>& g, const V3<T>* capC, 
           V3<T> ta, tb, tc; hfieldTriangle(hf, zscale, mc.hx, gr.dx, r, c, k, ta, tb, tc);
           if (ta.z < gr.zmin && tb.z < gr.zmin && tc.z < gr.zmin) continue;
           T dist; V3<T> n, pos;
-          if (!capsulePrism(p0, p1, rad, ta, tb, tc, dist, n, pos)) continue;
+          if (!capsulePrismNoInline(p0, p1, rad, ta, tb, tc, dist, n, pos)) continue;
           if (nc < NC) { st3(s.cF[nc], n); makeFrame(s.cF[nc], false); st3(s.cP[nc], pos); s.cDist[nc] = dist; s.ctype[nc] = (unsigned char)ty; nc++; }
           cnt++;
         }

@@ -2,6 +2,11 @@
 
 Replaces the N worker processes each holding a patched-MuJoCo ``MjModel/MjData`` in the reference
 (ballbot_rl/training/train.py:82-97 -> ballbot_gym/envs/ballbot_env.py:261-262).
+
+The hot-path calls (``step`` / ``reset`` / ``add_reward``) go through the PyTorch extension ``torch.ops.ballbot.*``
+(csrc/bb_torch_ops.cpp: dispatcher ops over the C ABI, current-stream and device-guard handling inside the op) when that
+library is available, and through ctypes on the very same C entry points otherwise (``binding="ctypes"`` forces it; non-torch
+hosts bind the C ABI directly).  Either way the work is done by the CUDA kernels of libballbot_b200.so.
 """
 import ctypes as C
 
@@ -25,7 +30,8 @@ class BallbotEngine:
                  cameras=True, im_h=64, im_w=64, camera_frame_rate=90.0, max_ep_steps=4000, max_allowed_tilt=20.0,
                  max_wheel_velocity=10.0, reward="directional", reward_scale=0.01, action_reg_coef=-0.0001,
                  survival_bonus=0.02, target_direction=(0.0, 1.0), goal_position=(0.0, 0.0), distance_scale=1.0, seed=0,
-                 auto_reset=True, env_offset=0, step_kernel="warp", solver="exact", perlin_table=None, seed_stream="counter"):
+                 auto_reset=True, env_offset=0, step_kernel="warp", solver="exact", perlin_table=None, seed_stream="counter",
+                 binding="auto"):
         if not torch.cuda.is_available():
             raise EngineError("BallbotEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
         L = _lib.lib()
@@ -86,6 +92,20 @@ class BallbotEngine:
         io.episode_return = self.episode_return.data_ptr(); io.episode_length = self.episode_length.data_ptr()
         io.status = self.status.data_ptr()
         self._io = io
+        empty = torch.empty(0, **f32)
+        self._io_list = [self.obs["orientation"], self.obs["angular_vel"], self.obs["vel"], self.obs["motor_state"], self.obs["actions"],
+                         self.obs["relative_image_timestamp"], self.obs.get("rgbd_0", empty), self.obs.get("rgbd_1", empty), self.reward,
+                         self.terminated, self.failure, self.pos2d, self.terminal_obs, self.episode_return, self.episode_length, self.status]
+        self._ops = None
+        if binding not in ("auto", "torch", "ctypes"):
+            raise ValueError("binding must be 'auto', 'torch' or 'ctypes'")
+        if binding != "ctypes":
+            try:
+                self._ops = _lib.torch_ops()
+            except EngineError:
+                if binding == "torch":
+                    raise
+        self.binding = "torch" if self._ops is not None else "ctypes"
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -120,7 +140,10 @@ class BallbotEngine:
             self.pos2d.mul_(keep[:, None])
         else:
             self.reward.zero_(); self.terminated.zero_(); self.failure.zero_(); self.pos2d.zero_()
-        self._check(self._L.bb_reset(self._h, _ptr(mask), _ptr(seeds), C.byref(self._io), self._stream()), "bb_reset")
+        if self._ops is not None:
+            self._ops.reset(self._h.value, mask, seeds, self._io_list)
+        else:
+            self._check(self._L.bb_reset(self._h, _ptr(mask), _ptr(seeds), C.byref(self._io), self._stream()), "bb_reset")
         return self.obs
 
     def step(self, actions):
@@ -130,12 +153,18 @@ class BallbotEngine:
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
         if actions.shape != (self.num_envs, 3):
             raise ValueError(f"actions must have shape ({self.num_envs}, 3), got {tuple(actions.shape)}")
-        self._check(self._L.bb_step(self._h, _ptr(actions), C.byref(self._io), self._stream()), "bb_step")
+        if self._ops is not None:
+            self._ops.step(self._h.value, actions, self._io_list)
+        else:
+            self._check(self._L.bb_step(self._h, _ptr(actions), C.byref(self._io), self._stream()), "bb_step")
         return self.obs, self.reward, self.terminated, self.failure
 
     def add_reward(self, term):
         term = term.to(device=self.device, dtype=torch.float32).contiguous()
-        self._check(self._L.bb_add_reward(self._h, _ptr(term), C.byref(self._io), self._stream()), "bb_add_reward")
+        if self._ops is not None:
+            self._ops.add_reward(self._h.value, term, self._io_list)
+        else:
+            self._check(self._L.bb_add_reward(self._h, _ptr(term), C.byref(self._io), self._stream()), "bb_add_reward")
 
     # ------------------------------------------------------------------ state / terrain access (parity tests, plugins)
     def set_state(self, qpos=None, qvel=None, warm=None):

@@ -19,6 +19,10 @@ def compute_gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor
         raise ValueError(f"shapes: rewards {tuple(rewards.shape)}, values {tuple(values.shape)} (need [T+1,N]), dones {tuple(dones.shape)}")
     rewards = rewards.float().contiguous(); values = values.float().contiguous()
     dones = dones.to(torch.uint8).contiguous()
+    try:
+        return _lib.torch_ops().gae(rewards, values, dones, float(gamma), float(gae_lambda))      # torch.ops.ballbot.gae
+    except _lib.EngineError:
+        pass                                                                                        # ctypes on the same C entry point
     adv = torch.empty_like(rewards); ret = torch.empty_like(rewards)
     stream = C.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream)
     p = lambda t: C.c_void_p(t.data_ptr())

@@ -67,3 +67,17 @@ def test_product_package_never_imports_the_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h")):
                     src = open(os.path.join(dirpath, f)).read()
                     assert not bad.search(src), os.path.join(dirpath, f)
+
+
+def test_torch_ops_library_builds_and_registers_the_ballbot_namespace():
+    """the PyTorch extension over the C ABI (csrc/bb_torch_ops.cpp) builds in-tree and registers
+    torch.ops.ballbot.{step, reset, add_reward, gae} with mutable-output schemas (no compute without a GPU)."""
+    import torch
+    from openballbot_rl_b200 import _lib
+    ops = _lib.torch_ops()
+    for name in ("step", "reset", "add_reward", "gae"):
+        assert hasattr(ops, name)
+    schema = str(torch.ops.ballbot.step.default._schema)
+    assert "Tensor(a!)[] outs" in schema and "int engine" in schema, schema
+    with pytest.raises(Exception):
+        ops.step(0, torch.zeros(4, 3), [torch.zeros(1)] * 16)        # CPU tensors: no kernel registered for the CPU backend (no fallback)

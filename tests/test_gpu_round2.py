@@ -144,7 +144,7 @@ def test_distance_reward_parity(oracle_mod):
             o, r, tm, fl, info = e.step(a[i])
             assert abs(rew[i] - r) < 1e-6, (t, i, rew[i], r)
             np.testing.assert_allclose(pos[i], info[:2], atol=1e-6)
-    assert rew.min() < -0.005                                            # the distance term dominates (0.01 * 1.5 * ~0.8 m)
+    assert rew.max() < 0.02 - 0.008                                      # survival bonus minus 0.01 * 1.5 * ~0.8 m of distance
     eng.close()
 
 
@@ -156,9 +156,16 @@ def test_fp32_perlin_single_step_with_terrain_contacts(oracle_mod):
     e64.reset()
     hfs = torch.stack([e64.get_hfield(i) for i in range(N)])
     rng = np.random.default_rng(4)
-    for t in range(70):                                                  # drop + landing
+    qpos = np.zeros((N, 17)); qvel = np.zeros((N, 15)); warm = np.zeros((N, 15)); have = np.zeros(N, bool)
+    for t in range(260):                                                 # drop (up to ~0.25 s on steep fields) + landing
         e64.step(torch.from_numpy(np.clip(rng.normal(size=(N, 3)), -1, 1).astype(np.float32)).cuda())
-    qpos, qvel, warm = [x.cpu().numpy() for x in e64.get_state()]
+        nc = ((e64.status.cpu().numpy() >> 8) & 255); alive = ~e64.terminated.cpu().numpy().astype(bool)
+        new = ((nc >= 5) & alive & ~have) | (t == 0)                     # first step with terrain contacts: keep that state
+        if new.any():
+            q, v, w = [x.cpu().numpy() for x in e64.get_state()]
+            qpos[new], qvel[new], warm[new] = q[new], v[new], w[new]
+            if t > 0:
+                have |= new
     e32 = _engine(num_envs=N, precision=32, terrain="external", cameras=False, auto_reset=False)
     e32.set_hfield(np.arange(N, dtype=np.int32), hfs); e32.reset(); e32.set_state(qpos, qvel, warm)
     a = rng.uniform(-1, 1, (N, 3)).astype(np.float32)
@@ -170,10 +177,10 @@ def test_fp32_perlin_single_step_with_terrain_contacts(oracle_mod):
     for i in range(N):
         o.reset(hfs[i].cpu().numpy()); o.set_state(qpos[i], qvel[i], warm[i]); o.mj_step(-10.0 * a[i].astype(np.float64))
         qo, vo, _, _ = o.get_state()
-        if ncon[i] >= 4:
+        if ncon[i] >= 4 and have[i]:
             with_terrain += 1
             worst = max(worst, _rel(q1[i], qo), _rel(v1[i], vo))
-    assert with_terrain >= N // 2, ncon
+    assert with_terrain >= N // 2, (ncon, have)
     assert worst < 1e-3, worst
     e64.close(); e32.close()
 
