@@ -76,6 +76,7 @@ std::tuple<at::Tensor, at::Tensor> gae(const at::Tensor& rewards, const at::Tens
   const c10::cuda::CUDAGuard guard(rewards.device());
   const int64_t T = rewards.size(0), N = rewards.size(1);
   at::Tensor adv = at::empty_like(rewards), ret = at::empty_like(rewards);
+  if (T * N == 0) return {adv, ret};
   const int rc = bb_gae(ptr<float>(rewards, at::kFloat, T * N, "rewards"), ptr<float>(values, at::kFloat, (T + 1) * N, "values"), ptr<uint8_t>(dones, at::kByte, T * N, "dones"),
                         (int32_t)T, (int32_t)N, (float)gamma, (float)lam, adv.data_ptr<float>(), ret.data_ptr<float>(), at::cuda::getCurrentCUDAStream().stream());
   TORCH_CHECK(rc == BB_OK, "bb_gae failed (", rc, ")");

@@ -169,3 +169,30 @@ def test_drop_in_alias_packages():
     assert R2 is ComponentRegistry and cr2 is create_reward
     assert callable(make_ballbot_env(terrain_type="flat")) and BBotSimulation.metadata["render_modes"] == ["rgb_array"]
     assert ballbot_gym.core is not None and ballbot_rl.training is not None
+
+
+def test_policy_plugin_mlp_is_registered_and_builds_the_reference_extractor():
+    """ballbot_rl/policies/__init__.py:8 registers the feature extractor as policy plugin "mlp"; `create_policy` returns the class
+    (factories.py:129-162) and the instance has the reference's layout: per-key extractors in the observation space's
+    (alphabetical) order, 56 features with cameras, state-dict keys `extractors.rgbd_k.*` as in an SB3 policy.pth."""
+    import torch
+    import importlib
+    import ballbot_rl  # noqa: F401  (alias package: importing it registers the plugin, like the reference)
+    import openballbot_rl_b200.policies as _pol
+    importlib.reload(_pol)             # other tests clear the registry: registration happens at import time, as in the reference
+    from ballbot_gym.core.factories import create_policy
+    from ballbot_gym.core.registry import ComponentRegistry
+    from openballbot_rl_b200.envs.spaces import create_observation_space
+    assert "mlp" in ComponentRegistry.list_policies()
+    cls = create_policy({"type": "mlp", "config": {"hidden_sizes": [128] * 4}})
+    assert cls.__name__ == "Extractor"
+    sp = create_observation_space({"h": 64, "w": 64}, 1, False)
+    ex = cls(sp).eval()
+    assert list(ex.extractors.keys()) == ["actions", "angular_vel", "motor_state", "orientation", "relative_image_timestamp", "rgbd_0", "rgbd_1", "vel"]
+    assert ex.features_dim == 56 and "extractors.rgbd_0.7.weight" in ex.state_dict()
+    obs = {k: torch.zeros((3,) + tuple(v.shape)) for k, v in sp.spaces.items()}
+    assert ex(obs).shape == (3, 56)
+    sp2 = create_observation_space({"h": 64, "w": 64}, 1, True)
+    assert cls(sp2).features_dim == 16                       # camera-less space still declares the timestamp (App. C #6)
+    with pytest.raises(ValueError, match="Failed to get policy"):
+        create_policy({"type": "transformer"})
