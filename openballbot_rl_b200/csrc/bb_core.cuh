@@ -32,6 +32,7 @@ static long bb_stats_ls_evals = 0;   // host-only instrumentation for scripts/ex
 namespace bb {
 
 constexpr int NQ = 17, NV = 15, HN = 293;
+constexpr int MIPB = 8, MIPN = (HN - 1 + MIPB - 1) / MIPB, MIP_CELLS = MIPN * MIPN;   // block maxima of 8 x 8 cells (37 x 37 per field)
 constexpr int MAXH = 50;          // mjMAXCONPAIR: max ball-hfield contacts per forward pass
 constexpr int NC = 64;            // contact capacity of one forward pass (3 wheel pairs + <= 50 ball-terrain prisms + the other pairs)
 // contact types (index of ModelConst::dA):
@@ -403,6 +404,15 @@ BB_HD void closestSegTriangle(const V3<T>& p0, const V3<T>& p1, const V3<T>& a, 
 }
 // capsule (segment p0-p1, radius r) against the prism under the top triangle (ta, tb, tc): closest feature of the top surface
 // patch; a segment point under the top plane only counts inside the prism's column (same conventions as the ball pair)
+// exact early-out of capsulePrism: both segment ends are more than r above the top plane => every segment point is, and the
+// distance to the triangle is at least the distance to its plane (no contact; the deep branch needs a point under the plane)
+template <typename T>
+BB_HD bool capsuleAbovePlane(const V3<T>& p0, const V3<T>& p1, T r, const V3<T>& ta, const V3<T>& tb, const V3<T>& tc) {
+  const V3<T> nc = cross(tb - ta, tc - ta);
+  const T sg = nc.z < 0 ? (T)-1 : (T)1;
+  const T h0 = sg * dot(p0 - ta, nc), h1 = sg * dot(p1 - ta, nc), rn = r * r * dot(nc, nc);     // heights scaled by |nc|
+  return h0 > 0 && h1 > 0 && h0 * h0 > rn && h1 * h1 > rn;
+}
 template <typename T>
 BB_HD bool capsulePrism(const V3<T>& p0, const V3<T>& p1, T r, const V3<T>& ta, const V3<T>& tb, const V3<T>& tc, T& dist, V3<T>& n, V3<T>& pos) {
   const V3<T> e1 = tb - ta, e2 = tc - ta;
@@ -581,6 +591,7 @@ BB_HD void collide(const ModelConst<T>& mc, const Geo<T>& g, const V3<T>* capC, 
         for (int k = 0; k < 2 && cnt < MAXH; k++) {
           V3<T> ta, tb, tc; hfieldTriangle(hf, zscale, mc.hx, gr.dx, r, c, k, ta, tb, tc);
           if (ta.z < gr.zmin && tb.z < gr.zmin && tc.z < gr.zmin) continue;
+          if (capsuleAbovePlane(p0, p1, rad, ta, tb, tc)) continue;
           T dist; V3<T> n, pos;
           if (!capsulePrismNoInline(p0, p1, rad, ta, tb, tc, dist, n, pos)) continue;
           if (nc < NC) { st3(s.cF[nc], n); makeFrame(s.cF[nc], false); st3(s.cP[nc], pos); s.cDist[nc] = dist; s.ctype[nc] = (unsigned char)ty; nc++; }

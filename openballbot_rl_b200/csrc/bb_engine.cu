@@ -69,6 +69,7 @@ struct DevState {
   int* meta;       // int[N][4]       split-phase step: ncon, nw, Newton iterations, flags
   int* step_count; int* cam_steps; unsigned* episode; int* tseed;
   float* hfield;   // [N][HF_CELLS] (HF_PER_ENV), [HF_CELLS] (HF_SHARED) or [table_n][HF_CELLS] (HF_TABLE)
+  float* hmip;     // block maxima (8 x 8 cells, MIP_CELLS per field) of every heightfield in `hfield`, same indexing
   unsigned long long* rng;   // [N][5] numpy PCG64 state per env (seed_stream = 1): state hi/lo, inc hi/lo, has_uint32 | uinteger << 32
   float* ptab;     // [2][293] circle coordinates of the tiled simplex noise (sin, cos) per grid index
   float* ep_ret; int* ep_len;
@@ -118,12 +119,14 @@ __device__ __forceinline__ int drawTerrainSeed(const EnvParams& p, const DevStat
   unsigned long long h = splitmix(p.seed ^ splitmix((unsigned long long)(p.env_offset + env) * 0x100000001B3ull + episode));
   return (int)(h % 10000ull);
 }
-// heightfield of env i
-__device__ __forceinline__ const float* hfOf(const EnvParams& p, const DevState& d, int i) {
-  if (p.hf_mode == HF_PER_ENV) return d.hfield + (size_t)i * HF_CELLS;
-  if (p.hf_mode == HF_TABLE) return d.hfield + (size_t)(p.terrain_seed >= 0 ? 0 : d.tseed[i]) * HF_CELLS;
-  return d.hfield;
+// heightfield of env i (field index: the env itself, its terrain seed in the table, or the one shared field)
+__device__ __forceinline__ size_t hfIndex(const EnvParams& p, const DevState& d, int i) {
+  if (p.hf_mode == HF_PER_ENV) return (size_t)i;
+  if (p.hf_mode == HF_TABLE) return (size_t)(p.terrain_seed >= 0 ? 0 : d.tseed[i]);
+  return 0;
 }
+__device__ __forceinline__ const float* hfOf(const EnvParams& p, const DevState& d, int i) { return d.hfield + hfIndex(p, d, i) * HF_CELLS; }
+__device__ __forceinline__ const float* mipOf(const EnvParams& p, const DevState& d, int i) { return d.hmip + hfIndex(p, d, i) * MIP_CELLS; }
 
 // --------------------------------------------------------------------------------------------- step
 template <typename T>
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCK
     const float* hf = hfOf(p, d, i);
     T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
     T* cq = refresh ? (T*)d.camq + (size_t)i * CST : nullptr;
-    bbg::gRk4(cmc<T>(), S, hf, (T)p.zscale, gs, cq, L, warm, p.solver_mode != 0, ncmax, nit);
+    bbg::gRk4(cmc<T>(), S, hf, mipOf(p, d, i), (T)p.zscale, gs, cq, L, warm, p.solver_mode != 0, ncmax, nit);
   }
   stepFinish(p, d, actions, io, i, S, L, warm, bad, ncmax, nit);
 }
@@ -368,7 +371,9 @@ k_stage(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io, in
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / bbg::G;
   const int slot = (blockIdx.x * (blockDim.x >> 5) + warp) * bbg::EPW + grp;
   const bool live = slot < p.N;              // threads beyond the last env only take part in the CTA barriers
-  const int i = live ? slot : p.N - 1;
+  // work-sorted order (the same one k_newton uses): the envs of a CTA enter the barrier-synchronised phases together, so
+  // free-falling envs share CTAs with free-falling envs and landed ones with landed ones
+  const int i = d.order[live ? slot : p.N - 1];
   bool skip = !live;
   bbg::GS<T>& S = reinterpret_cast<bbg::GS<T>*>(smem_raw)[warp * bbg::EPW + grp];
   const ModelConst<T>& mc = cmc<T>();
@@ -437,7 +442,7 @@ k_stage(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io, in
   }
   T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
   int nw, nd; T qfs, qas;
-  const int ncon = bbg::gForwardPre(mc, S, hf, (T)p.zscale, gs, L, stage == 3, nw, nd, qfs, qas, skip, BB_WPB_STAGE > 1);
+  const int ncon = bbg::gForwardPre(mc, S, hf, mipOf(p, d, i), (T)p.zscale, gs, L, stage == 3, nw, nd, qfs, qas, skip, BB_WPB_STAGE > 1);
   if (skip) return;
   if (dof) {
     rk[bbg::RK_XV + L.gl] = xv;
@@ -509,7 +514,7 @@ template <typename T> __global__ void k_probe_warp(EnvParams p, DevState d, int 
   __syncwarp(L.mask);
   const float* hf = hfOf(p, d, env);
   int ncon, niter; T qas, qfs;
-  const T qacc = bbg::gForward<T, true>(cmc<T>(), S, hf, (T)p.zscale, (T*)d.gscr + (size_t)env * bbg::GSCR, L, warm, p.solver_mode != 0, true, ncon, niter, &qas, &qfs, dbg);
+  const T qacc = bbg::gForward<T, true>(cmc<T>(), S, hf, mipOf(p, d, env), (T)p.zscale, (T*)d.gscr + (size_t)env * bbg::GSCR, L, warm, p.solver_mode != 0, true, ncon, niter, &qas, &qfs, dbg);
   if (L.gl < NV) { out[L.gl] = (double)qacc; out[15 + L.gl] = (double)qas; out[30 + L.gl] = (double)qfs; }
   if (L.gl == 0) { out[45] = ncon; out[46] = niter; }
 }
@@ -917,6 +922,22 @@ __global__ void k_scatter_hfield(const int* __restrict__ ids, int n, const float
   const int k = (int)(t / HF_CELLS); const int cell = (int)(t - (size_t)k * HF_CELLS);
   dst[(size_t)ids[k] * HF_CELLS + cell] = src[t];
 }
+// block maxima of a heightfield: mip cell (br, bc) = max over the vertices of cells [8 br, 8 br + 8) x [8 bc, 8 bc + 8), i.e. vertex
+// rows / cols 8 b .. 8 b + 8.  Field f = list[k] (reset list, id list) or k; grid.y strides over the fields.
+__global__ void k_hf_mip(const float* __restrict__ hf, float* __restrict__ mip, const int* __restrict__ list, const int* __restrict__ count, int fixed_count) {
+  const int n = count ? *count : fixed_count;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= MIP_CELLS) return;
+  const int br = cell / MIPN, bc = cell - br * MIPN;
+  const int r1 = min(8 * br + 8, HN - 1), c1 = min(8 * bc + 8, HN - 1);
+  for (int k = blockIdx.y; k < n; k += gridDim.y) {
+    const size_t f = list ? (size_t)list[k] : (size_t)k;
+    const float* h = hf + f * HF_CELLS;
+    float m = -1e30f;
+    for (int r = 8 * br; r <= r1; r++) for (int c = 8 * bc; c <= c1; c++) m = fmaxf(m, h[r * HN + c]);
+    mip[f * MIP_CELLS + cell] = m;
+  }
+}
 __global__ void k_get_hfield(EnvParams p, DevState d, int env, float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < HF_CELLS) out[c] = hfOf(p, d, env)[c];
@@ -1034,7 +1055,8 @@ static int launchResetAndRender(bb_engine* e, const bb_io* io, cudaStream_t s, b
     if (e->cfg.terrain_type == BB_TERRAIN_PERLIN && e->p.hf_mode == HF_PER_ENV) {
       dim3 grid(blocksFor(HF_CELLS, 256), N < 128 ? N : 128);
       k_terrain<<<grid, 256, 0, s>>>(e->p, e->d, e->d.reset_list, e->d.counters, 0, nullptr, nullptr);
-      e->launches++;
+      k_hf_mip<<<dim3(blocksFor(MIP_CELLS, 128), N < 128 ? N : 128), 128, 0, s>>>(e->d.hfield, e->d.hmip, e->d.reset_list, e->d.counters, 0);
+      e->launches += 2;
     }
     if (ev) cudaEventRecord(ev[2], s);
     if (e->cfg.precision == 64) k_reset<double><<<blocksFor(N, 128), 128, 0, s>>>(e->p, e->d, *io);
@@ -1165,6 +1187,9 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   if (p.hf_mode != HF_TABLE) BB_CUDA_C(cudaMemset(d.hfield, 0, hfbytes));
   BB_CUDA_C(cudaMalloc(&d.ptab, sizeof(float) * 2 * HN));
   k_perlin_table<<<blocksFor(HN, 128), 128>>>(cfg->perlin_scale, d.ptab);
+  const size_t nfields = p.hf_mode == HF_PER_ENV ? (size_t)N : (p.hf_mode == HF_TABLE ? (size_t)e->table_n : 1);
+  BB_CUDA_C(cudaMalloc(&d.hmip, sizeof(float) * MIP_CELLS * nfields));
+  BB_CUDA_C(cudaMemset(d.hmip, 0, sizeof(float) * MIP_CELLS * nfields));
   BB_CUDA_C(cudaMalloc(&d.rng, sizeof(unsigned long long) * 5 * (size_t)N));
   BB_CUDA_C(cudaMemset(d.rng, 0, sizeof(unsigned long long) * 5 * (size_t)N));
   BB_CUDA_C(cudaMalloc(&e->probe_out, sizeof(double) * 64));
@@ -1176,6 +1201,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
     k_iota<<<blocksFor(e->table_n, 256), 256>>>(e->table_n, cfg->terrain_seed >= 0 ? cfg->terrain_seed : 0, seeds);
     dim3 grid(blocksFor(HF_CELLS, 256), e->table_n < 592 ? e->table_n : 592);
     k_terrain<<<grid, 256>>>(p, d, nullptr, nullptr, e->table_n, seeds, d.hfield);
+    k_hf_mip<<<dim3(blocksFor(MIP_CELLS, 128), e->table_n < 592 ? e->table_n : 592), 128>>>(d.hfield, d.hmip, nullptr, nullptr, e->table_n);
     BB_CUDA_C(cudaDeviceSynchronize());
     cudaFree(seeds);
   }
@@ -1196,7 +1222,7 @@ int bb_destroy(bb_engine* e) {
   DevState& d = e->d;
   cudaFree(d.st); cudaFree(d.camq); cudaFree(d.gscr); cudaFree(d.rk); cudaFree(d.ctx); cudaFree(d.meta); cudaFree(d.step_count); cudaFree(d.cam_steps); cudaFree(d.episode); cudaFree(d.tseed);
   cudaFree(d.work); cudaFree(d.order); cudaFree(d.bins);
-  cudaFree(d.ep_ret); cudaFree(d.ep_len); cudaFree(d.counters); cudaFree(d.reset_list); cudaFree(d.refresh_list); cudaFree(d.hfield); cudaFree(d.ptab); cudaFree(d.rng); cudaFree(e->probe_out);
+  cudaFree(d.ep_ret); cudaFree(d.ep_len); cudaFree(d.counters); cudaFree(d.reset_list); cudaFree(d.refresh_list); cudaFree(d.hfield); cudaFree(d.hmip); cudaFree(d.ptab); cudaFree(d.rng); cudaFree(e->probe_out);
   if (e->prof_ev) { for (int i = 0; i < 5 * e->prof_cap; i++) cudaEventDestroy(e->prof_ev[i]); free(e->prof_ev); }
   if (e->host_ready) {
     cudaFreeHost(e->h_act); cudaFree(e->d_act); cudaFree(e->d_obs16); cudaFreeHost(e->h_obs16); cudaFreeHost(e->h_reward); cudaFreeHost(e->h_pos2d);
@@ -1312,14 +1338,17 @@ int bb_set_hfield(bb_engine* e, const int32_t* ids, int32_t n, const float* hf, 
   if (e->cfg.terrain_type == BB_TERRAIN_SHARED) {   // the one field shared by every env
     if (n != 1) return fail(e, BB_ERR_INVALID, "bb_set_hfield: a shared-terrain engine takes exactly one heightfield");
     BB_CUDA(cudaMemcpyAsync(e->d.hfield, hf, sizeof(float) * HF_CELLS, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    e->launches++;
+    k_hf_mip<<<dim3(blocksFor(MIP_CELLS, 128), 1), 128, 0, (cudaStream_t)stream>>>(e->d.hfield, e->d.hmip, nullptr, nullptr, 1);
+    e->launches += 2;
+    BB_CUDA(cudaGetLastError());
     return BB_OK;
   }
   if (e->p.hf_mode != HF_PER_ENV) return fail(e, BB_ERR_INVALID, "bb_set_hfield: engine has no per-env heightfields (flat terrain or Perlin table); create it with BB_TERRAIN_EXTERNAL");
   if (n == 0) return BB_OK;
   const size_t tot = (size_t)n * HF_CELLS;
   k_scatter_hfield<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids, n, hf, e->d.hfield);
-  e->launches++;
+  k_hf_mip<<<dim3(blocksFor(MIP_CELLS, 128), n < 128 ? n : 128), 128, 0, (cudaStream_t)stream>>>(e->d.hfield, e->d.hmip, ids, nullptr, n);
+  e->launches += 2;
   BB_CUDA(cudaGetLastError());
   return BB_OK;
 }

@@ -747,8 +747,8 @@ template <bool DBG, typename T> __device__ __forceinline__ void gDbgContact(doub
 // Returns the contact count; nw = ball x wheel contacts (first), nd = all dense contacts (phases 1 + 2).
 // DBG: every contact is also written to dbg[c] = {type, dist, pos3, frame9} (bb_probe_forward; never in the step kernels).
 template <typename T, bool DBG = false>
-__device__ __noinline__ int gCollide(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, const Ln L, int& nwOut, int& ndOut,
-                                     double* dbg = nullptr) {
+__device__ __noinline__ int gCollide(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, const float* __restrict__ mip, T zscale, T* gs, const Ln L,
+                                     int& nwOut, int& ndOut, double* dbg = nullptr) {
   const int gl = L.gl;
   const unsigned lt = (1u << gl) - 1u;
   const int gsh = (threadIdx.x & 31) & ~(G - 1);     // bit position of the group's lane 0 in a ballot
@@ -785,10 +785,34 @@ __device__ __noinline__ int gCollide(const ModelConst<T>& mc, GS<T>& S, const fl
     S.cst[c] = 0;
     gDbgContact<DBG>(dbg, c, ty, dist, pos, F);
   }
-  // ---- phase 2: camera sticks (gi 0, 1) and wheel capsules (gi 2..4) against the heightfield
+  // ---- coarse heightfield reject (exact): lane g < 6 takes geom g (sticks, wheels, ball), reads the block maxima of the
+  // 8 x 8-cell mip under the geom's sub-grid and compares with the geom's lowest point; a geom whose sub-grid lies entirely
+  // below it would have every prism z-rejected, so its scan (phases 2 / 3) is skipped without touching the heightfield
   const T sx = mc.hx;
+  bool need = false;
+  if (gl < 6) {
+    V3<T> lo, hi;
+    if (gl < 5) {
+      V3<T> cc; T rad, hl;
+      if (gl < 2) { cc = pB + rot(RB, ld3(mc.stick_c[gl])); cu = rot(RB, ld3(mc.stick_u[gl])); rad = mc.stick_r; hl = mc.stick_hl; }
+      else { cc = ld3(ge + GE_CC + 3 * (gl - 2)); cu = ld3(ge + GE_CU + 3 * (gl - 2)); rad = mc.wheel_r; hl = mc.wheel_hl; }
+      const V3<T> p0 = cc - cu * hl, p1 = cc + cu * hl;
+      lo = mk(bmin(p0.x, p1.x) - rad, bmin(p0.y, p1.y) - rad, bmin(p0.z, p1.z) - rad);
+      hi = mk(bmax(p0.x, p1.x) + rad, bmax(p0.y, p1.y) + rad, bmax(p0.z, p1.z) + rad);
+    } else { lo = mk(bc.x - br, bc.y - br, bc.z - br); hi = mk(bc.x + br, bc.y + br, bc.z + br); }
+    HfGrid<T> gr;
+    if (hfieldSubgrid(sx, mc.hbase, zscale, lo, hi, gr) && gr.cmax > gr.cmin && gr.rmax > gr.rmin) {
+      float zm = -1e30f;
+      for (int br_ = gr.rmin >> 3; br_ <= (gr.rmax - 1) >> 3; br_++)
+        for (int bc_ = gr.cmin >> 3; bc_ <= (gr.cmax - 1) >> 3; bc_++) zm = fmaxf(zm, mip[br_ * MIPN + bc_]);
+      need = !((T)zm * zscale < gr.zmin);
+    }
+  }
+  const unsigned needm = (__ballot_sync(L.mask, need) >> gsh) & gmask;
+  // ---- phase 2: camera sticks (gi 0, 1) and wheel capsules (gi 2..4) against the heightfield
 #pragma unroll 1
   for (int gi = 0; gi < 5; gi++) {
+    if (!((needm >> gi) & 1u)) continue;
     V3<T> cc; T rad, hl;
     if (gi < 2) { cc = pB + rot(RB, ld3(mc.stick_c[gi])); cu = rot(RB, ld3(mc.stick_u[gi])); rad = mc.stick_r; hl = mc.stick_hl; }
     else { cc = ld3(ge + GE_CC + 3 * (gi - 2)); cu = ld3(ge + GE_CU + 3 * (gi - 2)); rad = mc.wheel_r; hl = mc.wheel_hl; }
@@ -807,7 +831,8 @@ __device__ __noinline__ int gCollide(const ModelConst<T>& mc, GS<T>& S, const fl
       if (p < nprism) {
         const int cell = p >> 1, r = gr.rmin + cell / ncols, c = gr.cmin + cell % ncols;
         V3<T> ta, tb, tc; hfieldTriangle(hf, zscale, sx, gr.dx, r, c, p & 1, ta, tb, tc);
-        if (!(ta.z < gr.zmin && tb.z < gr.zmin && tc.z < gr.zmin)) hit = gCapsulePrism(p0, p1, rad, ta, tb, tc, dist, n, pos);
+        if (!(ta.z < gr.zmin && tb.z < gr.zmin && tc.z < gr.zmin) && !capsuleAbovePlane(p0, p1, rad, ta, tb, tc))
+          hit = gCapsulePrism(p0, p1, rad, ta, tb, tc, dist, n, pos);
       }
       m = (__ballot_sync(L.mask, hit) >> gsh) & gmask;
       if (m == 0) continue;
@@ -829,7 +854,7 @@ __device__ __noinline__ int gCollide(const ModelConst<T>& mc, GS<T>& S, const fl
   }
   // ---- phase 3: ball vs heightfield prisms
   int cnt = 0;
-  const bool skip = (sx < bc.x - br) || (-sx > bc.x + br) || (sx < bc.y - br) || (-sx > bc.y + br) || (zscale < bc.z - br) || (-mc.hbase > bc.z + br);
+  const bool skip = !((needm >> 5) & 1u);   // box test and mip test of lane 5
   if (!skip) {
     const T gsc = (T)(HN - 1) / ((T)2 * sx);
     int cmin = (int)bfloor((bc.x - br + sx) * gsc), cmax = (int)bceil((bc.x + br + sx) * gsc);
@@ -910,7 +935,7 @@ __device__ __noinline__ int gCollide(const ModelConst<T>& mc, GS<T>& S, const fl
 // cta_sync: the warps of the CTA enter the three phases together (every thread of the CTA must make the call; `skip`
 // marks threads that only take part in the barriers), so the large straight-line phase code is fetched once per CTA.
 template <typename T, bool DBG = false>
-__device__ __forceinline__ int gForwardPre(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, const Ln L, bool wantKin,
+__device__ __forceinline__ int gForwardPre(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, const float* __restrict__ mip, T zscale, T* gs, const Ln L, bool wantKin,
                                            int& nw, int& nd, T& qfs, T& qas, bool skip = false, bool cta_sync = false, double* dbg = nullptr) {
   int ncon = 0;
   nw = 0; nd = 0; qfs = 0; qas = 0;
@@ -924,17 +949,17 @@ __device__ __forceinline__ int gForwardPre(const ModelConst<T>& mc, GS<T>& S, co
     __syncwarp(L.mask);
   }
   if (cta_sync) __syncthreads();
-  if (!skip) ncon = gCollide<T, DBG>(mc, S, hf, zscale, gs, L, nw, nd, dbg);   // consumes S.geo, which shares storage with the Cholesky factor
+  if (!skip) ncon = gCollide<T, DBG>(mc, S, hf, mip, zscale, gs, L, nw, nd, dbg);   // consumes S.geo, which shares storage with the Cholesky factor
   if (cta_sync) __syncthreads();
   if (!skip) qas = gMassSolve(S, qfs, L);                     // qacc_smooth = M^-1 qfrc_smooth
   return ncon;
 }
 // in: S.xq, S.xv, S.ctrl, warm (dof-lane register)   out: returns qacc of this dof lane (and S.xq normalised).
 template <typename T, bool DBG = false>
-__device__ __noinline__ T gForward(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, const Ln L, T warm, bool fast,
+__device__ __noinline__ T gForward(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, const float* __restrict__ mip, T zscale, T* gs, const Ln L, T warm, bool fast,
                                    bool wantKin, int& nconOut, int& niterOut, T* qasOut = nullptr, T* qfsOut = nullptr, double* dbg = nullptr) {
   int nw, nd; T qfs, qas;
-  const int ncon = gForwardPre<T, DBG>(mc, S, hf, zscale, gs, L, wantKin, nw, nd, qfs, qas, false, false, dbg);
+  const int ncon = gForwardPre<T, DBG>(mc, S, hf, mip, zscale, gs, L, wantKin, nw, nd, qfs, qas, false, false, dbg);
   if (qasOut) { *qasOut = qas; *qfsOut = qfs; }
   nconOut = ncon; niterOut = 0;
   if (ncon == 0) return qas;
@@ -955,7 +980,7 @@ template <typename T> __device__ __noinline__ void gIntegrate(T* dst, const T* s
 // in: S.xq/S.xv = state, S.ctrl, warm ; out: S.xq/S.xv = new state, warm = last-stage qacc, S.kin = last-stage kinematics.
 // qlast (global, NQ) receives the last-stage configuration when non-null.
 template <typename T>
-__device__ void gRk4(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, T zscale, T* gs, T* qlast, const Ln L, T& warm, bool chain_warm,
+__device__ void gRk4(const ModelConst<T>& mc, GS<T>& S, const float* __restrict__ hf, const float* __restrict__ mip, T zscale, T* gs, T* qlast, const Ln L, T& warm, bool chain_warm,
                      int& ncmax, int& nitsum) {
   const T h = mc.timestep;
   const bool dof = L.gl < NV;
@@ -970,7 +995,7 @@ __device__ void gRk4(const ModelConst<T>& mc, GS<T>& S, const float* __restrict_
   for (int st = 0; st < 5; st++) {
     if (st < 4) {
       int nc, ni;
-      qacc = gForward(mc, S, hf, zscale, gs, L, warm, chain_warm, st == 3, nc, ni);
+      qacc = gForward(mc, S, hf, mip, zscale, gs, L, warm, chain_warm, st == 3, nc, ni);
       ncmax = nc > ncmax ? nc : ncmax; nitsum += ni;
       const T bw = (st == 0 || st == 3) ? (T)(1.0 / 6.0) : (T)(1.0 / 3.0);
       sumv += bw * xv; suma += bw * qacc;
