@@ -40,6 +40,9 @@ BYTES_TERRAIN = 343396.0                   # one regenerated 293x293 float32 hei
 # the stage and solver launches on purpose (~6 KB per env and stage written and read back; it buys the instruction-fetch
 # fix described in DESIGN.md and costs ~0.2 ms of HBM time per step), plus register-spill lines of the smooth-dynamics pass.
 NCU_TRAFFIC = {"step": (736.5e6 + 329.0e6 + 37.3e6) / 32768.0, "depth": (104.36e6 + 163.02e6) / (32768.0 / 6.0)}
+# fp64 work of the step kernels (5 x k_stage + 4 x k_newton) from profiles/r02a_ncu_full_perlin32k.txt: thread-level
+# (dfma x 2 + dmul + dadd) x elapsed cycles, summed over the nine launches of one step, per env (perlin, fp64, exact solver)
+NCU_FP64_FLOP_PER_ENV_STEP = 1.4160e10 / 32768.0
 
 
 def load_peaks():
@@ -157,6 +160,68 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
+# ----------------------------------------------------------------------------------------------- PPO iteration (BASELINE configs[3])
+def ppo_main(args, rank, local_rank, world):
+    """Full PPO loop of the paper's setup on the GPU engine: perlin terrain + depth cameras, frozen depth encoders + MLP policy,
+    rollouts sharded across the GPUs, ONE flat-buffer gradient all-reduce per minibatch over NCCL, fused AdamW step.
+    A "step" is one PPO iteration (rollout of n_steps per env + n_epochs of minibatch updates); value = env-steps/s including
+    the learner.  Hyper-parameters: configs/train/ppo_directional.yaml:73-99 except n_steps / batch size (scaled to the env count)."""
+    import torch
+    import torch.distributed as dist
+    from openballbot_rl_b200.training.policy import BallbotPolicy
+    from openballbot_rl_b200.training.ppo import PPOConfig, PPOLearner
+    from openballbot_rl_b200.training.utils import make_ballbot_vec_env
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    envs = args.envs or 16384
+    T = args.ppo_n_steps
+    batch = args.ppo_batch or max(256, (world * envs * T) // 80)
+    torch.manual_seed(rank)
+    venv = make_ballbot_vec_env(world * envs, terrain_config={"type": "perlin", "config": {}}, seed=0, device=local_rank, rank=rank, world_size=world)
+    pol = BallbotPolicy().to(dev)
+    iters, warm = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    L = PPOLearner(venv, pol, PPOConfig(n_steps=T, batch_size=batch), total_timesteps=10 ** 12)
+    hist = []
+    for it in range(warm):
+        L.update(L.collect()[0])
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    for k in L.timing:
+        L.timing[k] = 0.0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for it in range(iters):
+        torch.cuda.synchronize(dev); t0 = time.perf_counter()
+        buf, stats = L.collect()
+        torch.cuda.synchronize(dev); t1 = time.perf_counter()
+        info = L.update(buf)
+        torch.cuda.synchronize(dev); t2 = time.perf_counter()
+        L.timing["collect_s"] += t1 - t0; L.timing["update_s"] += t2 - t1
+        hist.append({**stats, **info})
+    ev1.record(); torch.cuda.synchronize(dev)
+    tms = torch.tensor([ev0.elapsed_time(ev1), L.timing["collect_s"] * 1e3, L.timing["update_s"] * 1e3, L.timing["allreduce_s"] * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, col, upd, ar = (float(x) for x in tms.tolist())
+    if rank == 0:
+        steps_total = world * envs * T * iters
+        print(json.dumps({"metric": METRIC, "value": steps_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": iters, "warmup": warm,
+                          "ms_per_step": ms / iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 physics / f32 policy",
+                          "data": "synthetic",
+                          "config": {"workload": f"full PPO iteration (BASELINE.json configs[3]): perlin + depth cameras, frozen encoders + 4x128 MLP policy, {envs} envs/GPU x {T} steps per rollout",
+                                     "envs_per_gpu": envs, "n_steps": T, "global_batch": batch, "n_epochs": 5, "parallelism": f"env-sharded x{world}; one flat-buffer gradient all-reduce per minibatch (NCCL)"},
+                          "ppo": {"collect_ms_per_iter": col / iters, "update_ms_per_iter": upd / iters, "allreduce_host_ms_per_iter": ar / iters,
+                                  "allreduce_share_of_update": ar / upd if upd else None, "rollout_only_env_steps_per_s": world * envs * T * iters / (col * 1e-3),
+                                  "minibatches_per_epoch": hist[-1]["minibatches_per_epoch"], "updates_last_iter": hist[-1]["n_updates"], "early_stop_last_iter": hist[-1]["early_stop"],
+                                  "allreduce_bytes": 4 * (L.n_param + 2), "note": "allreduce time is host wall-clock around dist.all_reduce (enqueue + wait for the previous kernels), an upper bound of the NCCL time"}}))
+    venv.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -164,7 +229,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="perlin", choices=["perlin", "flat"])
+    ap.add_argument("--workload", default="perlin", choices=["perlin", "flat", "ppo"])
+    ap.add_argument("--ppo-n-steps", type=int, default=64, help="--workload ppo: rollout length per iteration")
+    ap.add_argument("--ppo-batch", type=int, default=0, help="--workload ppo: GLOBAL minibatch size (default: 80 minibatches per epoch like the reference)")
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default 65536 perlin / 4096 flat)")
     ap.add_argument("--precision", type=int, default=64, choices=[32, 64])
     ap.add_argument("--preroll", type=int, default=-1, help="untimed steps that desynchronise the episodes (default 300 perlin / 0 flat)")
@@ -177,6 +244,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "ppo":
+        return ppo_main(args, rank, local_rank, world)
     envs = args.envs or (65536 if args.workload == "perlin" else 4096)
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     workload_name = ("perlin uneven terrain + ball-hfield contacts + depth raycast 2x64x64 every 6th step, terrain regen on reset"
@@ -333,7 +402,16 @@ def main():
                "terrain": resets_per_step_gpu * BYTES_TERRAIN if perlin and not table else 0.0,
                "depth": (refresh_per_step + resets_per_step_gpu) * BYTES_DEPTH_REFRESH, "reset": resets_per_step_gpu * 600.0}
         dom = max(kern, key=lambda k: kern[k])
-        achieved = alg[dom] / max(kern[dom] * 1e-3, 1e-12) / 1e9
+        achieved = alg[dom] / max(kern[dom] * 1e-3, 1e-12) / 1e9 if prof_steps else None
+        compute = None
+        if prof_steps and perlin and args.precision == 64 and args.solver == "exact":
+            from openballbot_rl_b200.engine import fp64_peak_tflops
+            pk = fp64_peak_tflops(local_rank)
+            ach = NCU_FP64_FLOP_PER_ENV_STEP * envs / (kern["step"] * 1e-3) / 1e12
+            compute = {"bound": "fp64 pipe", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk if pk else None,
+                       "flop_per_env_step": NCU_FP64_FLOP_PER_ENV_STEP,
+                       "flop_source": "ncu thread-level dfma x 2 + dmul + dadd of the nine step-kernel launches (profiles/r02a_ncu_full_perlin32k.txt), scaled by envs",
+                       "peak_source": "bb_fp64_peak: DFMA chains on this GPU, best of 4 (ncu reports 64 DFMA / cycle / SM = 37.2 TFLOP/s at 1965 MHz)"}
         whole = sum(alg.values()) / (ms_max / steps * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -342,14 +420,15 @@ def main():
                 "run": dict(preroll_steps=preroll, phase_stagger_steps=stagger, terrain_storage="table of 10,000 Perlin fields (3.4 GB)" if table else "per-env fields",
                             l2="working set (state + split-phase context + heightfields + images) exceeds the 126 MB L2; no flush needed",
                             resets_in_timed_region=total_resets, mean_episode_len=(world * envs * steps / total_resets) if total_resets else None),
-                "roofline": {"bound": "hbm", "kernel": "k_stage x5 + k_newton x4 (one step)" if dom == "step" else f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "roofline": {"bound": "hbm", "kernel": "k_stage x5 + k_newton x4 (one step)" if dom == "step" else f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak if achieved is not None else None, "compute": compute,
                              "traffic": (NCU_TRAFFIC[dom] * (envs if dom == "step" else refresh_per_step + resets_per_step_gpu)
                                          if perlin and args.precision == 64 and dom in NCU_TRAFFIC else None),
                              "traffic_source": "profiles/r01c_ncu_full_perlin32k.txt (per-env figure of the 32,768-env capture x this launch's envs)",
                              "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
                              "alg_bytes_per_launch": alg[dom], "kernel_ms_per_launch": kern[dom], "kernel_ms_all": kern, "kernel_ms_source": f"CUDA events around every kernel group, {prof_steps} steps right after the timed region",
                              "whole_step_achieved_gbs": whole, "whole_step_frac": whole / peak,
-                             "note": "not HBM-bound: the constraint solver (k_newton, 64 % of the step) is bound by the latency of its dependent chain (ncu: wait 2.6 cycles per issue, IPC 1.6 of 4, FP64 pipe 16 %, DRAM 1 %); depth ray-cast and terrain noise are instruction-issue bound (IPC 3.0 / 3.5); see profiles/README.md"},
+                             "note": "not HBM-bound: the step kernels are fp64 dependent-chain code (k_newton: wait 2.7 cycles per issue, IPC 1.25 of 4, fp64 pipe 19 %, DRAM 1 %; k_stage: barrier / instruction-fetch / L2 latency); `compute` relates their fp64 flop count to the measured DFMA peak; the depth ray-cast is instruction-issue bound (IPC 3.3); see profiles/README.md"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "bb_step_host (C ABI, host buffers); depth images stay device-resident for the policy encoder"},
                 "e2e_images": ({"value": e2e_img_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_img, "steps": e2e_img_steps,

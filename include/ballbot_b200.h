@@ -192,6 +192,19 @@ int bb_profile_end(bb_engine* e, double* ms4, int32_t* nsteps);
 int bb_gae(const float* rewards_dev, const float* values_dev, const uint8_t* dones_dev, int32_t T, int32_t N, float gamma,
            float gae_lambda, float* advantages_dev, float* returns_dev, void* cuda_stream);
 
+/* Fused PPO optimiser step on flat device buffers: replaces, for the reference's learner (SB3 PPO.train driven from
+ * ballbot_rl/training/train.py:126-141,284; hyper-parameters configs/train/ppo_directional.yaml:73-99), the host-side sequence
+ * "mean of the all-reduced gradient -> approx-KL early stop (> 1.5 target_kl) -> clip_grad_norm_ -> AdamW.step" with no host
+ * synchronisation.  grad_dev float[n + 2]: the (all-reduced, SUM) flat gradient followed by {sum of KL * samples, samples};
+ * ctrl_dev double[8]: [0] sticky stop flag, [1] optimiser step count, [2] last gradient norm, [3] last KL, [4] updates applied;
+ * scratch_dev double[1].  kl_limit <= 0 disables the early stop, max_grad_norm <= 0 the clipping. */
+int bb_adamw_step(float* param_dev, const float* grad_dev, float* m_dev, float* v_dev, int32_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, float max_grad_norm, float kl_limit, double* ctrl_dev, double* scratch_dev, void* cuda_stream);
+
+/* profiling aid: measured fp64 FMA throughput of `device` in TFLOP/s (8 independent DFMA chains per thread, 148 x 8 CTAs);
+ * the denominator of bench.py's roofline.compute (the step kernels are fp64-latency bound, not HBM bound) */
+int bb_fp64_peak(int32_t device, double* tflops);
+
 /* number of kernel launches issued by this engine so far (bench.py's gpu_launches claim) */
 int64_t bb_launch_count(const bb_engine* e);
 /* engine model constants for tests: dA[12] (diagApprox per contact type), meaninertia, masses (m0, mw, mL) */

@@ -305,6 +305,15 @@ class BallbotEngine:
         return self._hbuf
 
 
+def fp64_peak_tflops(device=0):
+    """Measured fp64 FMA throughput of the device (bb_fp64_peak), TFLOP/s."""
+    v = C.c_double()
+    rc = _lib.lib().bb_fp64_peak(int(device), C.byref(v))
+    if rc != 0:
+        raise EngineError(f"bb_fp64_peak failed ({rc})")
+    return v.value
+
+
 def build_info():
     return _lib.lib().bb_build_info().decode()
 

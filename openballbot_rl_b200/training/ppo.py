@@ -9,8 +9,16 @@ forces: the rollout buffer stores the 56 policy *features* (proprio 16 + 2 x 20 
 images -- the encoders are frozen in the reference too (mlp_policy.py:129-131), so the features are exactly what the MLPs
 see -- and an embedding is recomputed only when its camera refreshed (every 6th step, ballbot_env.py:743-767).
 
-Multi-GPU: every rank owns a shard of the envs and of the rollout; the only collectives are the flat-gradient all-reduce
-per minibatch, one scalar all-reduce per epoch for the KL stop, and the rollout-statistics reduce.
+Multi-GPU: every rank owns a shard of the envs and of the rollout (shards may be uneven: the ranks agree once per iteration
+on the global sample count and the number of minibatches, and every gradient is weighted by its local sample count).  The only
+collectives are ONE all-reduce per minibatch of a persistent flat buffer -- the gradients of every trainable parameter (which
+are views of it) plus {KL x samples, samples} in its tail -- one scalar all-reduce per epoch for the early-stop flag, and the
+rollout-statistics reduce.  On CUDA the step after the all-reduce is the fused kernel ``bb_adamw_step``
+(csrc/bb_rollout.cu): mean, target-KL stop (sticky device flag, no host sync per minibatch), gradient clipping and AdamW.
+
+Differences from SB3 that the batch size forces: ``batch_size`` is the GLOBAL minibatch size; the reference's 256 is for
+10 envs x 2048 steps (80 minibatches per epoch) -- scale it with the env count (e.g. 65,536 envs x 128 steps -> 2^19) to keep
+a comparable number of updates per iteration.
 """
 from dataclasses import dataclass
 from typing import Callable, Dict, Optional
@@ -73,15 +81,30 @@ class PPOLearner:
             p.requires_grad_(False)
         policy.encoders.eval()
         self.params = [p for p in policy.parameters() if p.requires_grad]
-        self.opt = torch.optim.AdamW(self.params, lr=lr_schedule(1.0) if cfg.learning_rate < 0 else cfg.learning_rate,
-                                     weight_decay=cfg.weight_decay)
+        if _world() > 1:                            # identical initial weights on every rank
+            for p in policy.parameters():
+                dist.broadcast(p.data, src=0)
+        # ---- persistent flat buffers: parameters and gradients are views, so one all-reduce and one fused step serve them all
+        n = sum(p.numel() for p in self.params)
+        self.n_param = n
+        self.flat_p = torch.empty(n, device=self.device); self.flat_g = torch.zeros(n + 2, device=self.device)
+        self.adam_m = torch.zeros(n, device=self.device); self.adam_v = torch.zeros(n, device=self.device)
+        o = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat_p[o:o + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[o:o + k].view_as(p)
+            p.grad = self.flat_g[o:o + k].view_as(p)
+            o += k
+        self.ctrl = torch.zeros(8, dtype=torch.float64, device=self.device)       # stop flag, step count, grad norm, KL, updates
+        self._scratch = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.lr = lr_schedule(1.0) if cfg.learning_rate < 0 else cfg.learning_rate
+        self.betas, self.eps = (0.9, 0.999), 1e-8
         self.gen = torch.Generator(device=self.device); self.gen.manual_seed(seed + 7919 * (dist.get_rank() if _world() > 1 else 0))
         self.num_timesteps = 0
         self._emb = None
         self._obs = None
-        if _world() > 1:                            # identical initial weights on every rank
-            for p in policy.parameters():
-                dist.broadcast(p.data, src=0)
+        self.timing = {"collect_s": 0.0, "update_s": 0.0, "allreduce_s": 0.0}
 
     # ------------------------------------------------------------------ features with the embedding cache
     @torch.no_grad()
@@ -143,68 +166,110 @@ class PPOLearner:
         buf["val"][T] = self._value(feat)
         self._obs = obs
         buf["adv"], buf["ret"] = self.gae_fn(buf["rew"], buf["val"], buf["done"], cfg.gamma, cfg.gae_lambda)
-        self.num_timesteps += T * N * _world()
         stats = reduce_rollout_stats(ep_r, ep_l, ep_d, steps=T * N)
+        self.num_timesteps += stats["env_steps"]                     # global count (SUM over ranks): identical on every rank
         return buf, stats
 
     # ------------------------------------------------------------------ update
+    def _optimizer_step(self, kl_limit: float):
+        """mean over the global minibatch -> KL early stop -> clip -> AdamW on the flat buffers (fused kernel on CUDA)."""
+        cfg, n = self.cfg, self.n_param
+        if self.flat_p.is_cuda:
+            import ctypes as C
+            from .. import _lib
+            vp = lambda t: C.c_void_p(t.data_ptr())
+            with torch.cuda.device(self.device):
+                rc = _lib.lib().bb_adamw_step(vp(self.flat_p), vp(self.flat_g), vp(self.adam_m), vp(self.adam_v), n, self.lr, self.betas[0], self.betas[1],
+                                              self.eps, cfg.weight_decay, cfg.max_grad_norm, kl_limit, vp(self.ctrl), vp(self._scratch),
+                                              C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+            if rc != 0:
+                raise RuntimeError(f"bb_adamw_step failed ({rc})")
+            return
+        # host-logic path for CPU tensors (gloo tests of the learner): the same arithmetic with torch ops
+        g, cnt = self.flat_g[:n], float(self.flat_g[n + 1]) or 1.0
+        kl = float(self.flat_g[n]) / cnt
+        if float(self.ctrl[0]) != 0.0 or (kl_limit > 0 and kl > kl_limit):
+            self.ctrl[0] = 1.0; self.ctrl[3] = kl
+            return
+        gn = float(g.norm()) / cnt
+        scale = (cfg.max_grad_norm / (gn + 1e-6) if cfg.max_grad_norm > 0 and gn > cfg.max_grad_norm else 1.0) / cnt
+        step = float(self.ctrl[1]) + 1.0
+        b1, b2 = self.betas
+        gi = g * scale
+        self.adam_m.mul_(b1).add_(gi, alpha=1 - b1); self.adam_v.mul_(b2).addcmul_(gi, gi, value=1 - b2)
+        self.flat_p.mul_(1 - self.lr * cfg.weight_decay)
+        self.flat_p.addcdiv_(self.adam_m / (1 - b1 ** step), (self.adam_v / (1 - b2 ** step)).sqrt() + self.eps, value=-self.lr)
+        self.ctrl[1] = step; self.ctrl[2] = gn; self.ctrl[3] = kl; self.ctrl[4] += 1
+
     def update(self, buf) -> Dict[str, float]:
-        cfg = self.cfg
+        cfg, dev = self.cfg, self.device
         T, N, F = buf["feat"].shape
         n = T * N
         feat = buf["feat"].reshape(n, F); act = buf["act"].reshape(n, 3); old_logp = buf["logp"].reshape(n)
         adv = buf["adv"].reshape(n); ret = buf["ret"].reshape(n)
         if cfg.learning_rate < 0:
-            lr = lr_schedule(1.0 - min(1.0, self.num_timesteps / self.total_timesteps))
-            for g in self.opt.param_groups:
-                g["lr"] = lr
-        acc = torch.zeros(4, device=self.device)   # policy loss, value loss, entropy, KL summed on the device
-        n_updates = 0
-        bs = min(cfg.batch_size, n)
-        stop = False
+            self.lr = lr_schedule(1.0 - min(1.0, self.num_timesteps / self.total_timesteps))
+        # ---- the ranks agree on the minibatch count once per iteration; shards may be uneven (ADVICE r1): every rank cuts its
+        # own samples into the same number of chunks, and gradients are summed weighted by chunk size, divided by the global size
+        world = _world()
+        n_glob = torch.tensor([float(n)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(n_glob, op=dist.ReduceOp.SUM)
+        n_mb = max(1, int(-(-int(n_glob.item()) // max(1, cfg.batch_size))))       # ceil: the remainder minibatch is trained on, as in SB3
+        n_mb = min(n_mb, n) if n > 0 else n_mb
+        bounds = [(k * n) // n_mb for k in range(n_mb + 1)]
+        kl_limit = 1.5 * cfg.target_kl if cfg.target_kl is not None else -1.0
+        self.ctrl[0] = 0.0; self.ctrl[4] = 0.0
+        acc = torch.zeros(3, device=dev)           # policy loss, value loss, entropy summed on the device
+        import time as _time
         for epoch in range(cfg.n_epochs):
-            perm = torch.randperm(n, device=self.device, generator=self.gen)
-            for s in range(0, n - bs + 1, bs):
-                idx = perm[s:s + bs]
-                mean, log_std = self._dist(feat[idx])
-                logp = self._log_prob(act[idx], mean, log_std)
-                a = adv[idx]
-                if cfg.normalize_advantage and bs > 1:
-                    a = (a - a.mean()) / (a.std() + 1e-8)
-                ratio = (logp - old_logp[idx]).exp()
-                pl = -torch.min(a * ratio, a * ratio.clamp(1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
-                vl = nn.functional.mse_loss(self._value(feat[idx]), ret[idx])
-                ent = (log_std + 1.4189385332046727).sum(-1).mean()
-                loss = pl + cfg.vf_coef * vl - cfg.ent_coef * ent
-                with torch.no_grad():
-                    lr_ = logp - old_logp[idx]
-                    kl = allreduce_mean_(((lr_.exp() - 1) - lr_).mean().reshape(1))
-                if cfg.target_kl is not None and float(kl) > 1.5 * cfg.target_kl:   # same decision on every rank (reduced KL)
-                    stop = True
-                    break
-                self.opt.zero_grad(set_to_none=True)
-                loss.backward()
-                flat = torch.cat([p.grad.reshape(-1) for p in self.params])
-                allreduce_mean_(flat)                                               # PPO gradient all-reduce (NCCL over NVLink)
-                nrm = flat.norm()
-                flat.mul_(torch.clamp(cfg.max_grad_norm / (nrm + 1e-6), max=1.0))
-                o = 0
-                for p in self.params:
-                    p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
-                self.opt.step()
-                acc += torch.stack([pl.detach(), vl.detach(), ent.detach(), kl[0]])
-                n_updates += 1
-            if stop:
+            perm = torch.randperm(n, device=dev, generator=self.gen)
+            for k in range(n_mb):
+                idx = perm[bounds[k]:bounds[k + 1]]
+                b = idx.numel()
+                self.flat_g.zero_()
+                if b:
+                    mean, log_std = self._dist(feat[idx])
+                    logp = self._log_prob(act[idx], mean, log_std)
+                    a = adv[idx]
+                    if cfg.normalize_advantage and b > 1:
+                        a = (a - a.mean()) / (a.std() + 1e-8)
+                    ratio = (logp - old_logp[idx]).exp()
+                    pl = -torch.min(a * ratio, a * ratio.clamp(1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+                    vl = nn.functional.mse_loss(self._value(feat[idx]), ret[idx])
+                    ent = (log_std + 1.4189385332046727).sum(-1).mean()
+                    loss = (pl + cfg.vf_coef * vl - cfg.ent_coef * ent) * float(b)         # weighted by the local sample count
+                    loss.backward()                                                        # accumulates into the flat buffer's views
+                    with torch.no_grad():
+                        lr_ = logp - old_logp[idx]
+                        self.flat_g[self.n_param] = ((lr_.exp() - 1) - lr_).sum()
+                        self.flat_g[self.n_param + 1] = float(b)
+                        acc += torch.stack([pl.detach(), vl.detach(), ent.detach()])
+                if world > 1:
+                    t0 = _time.perf_counter()
+                    dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)   # the PPO gradient all-reduce (NCCL over NVLink): one per minibatch
+                    self.timing["allreduce_s"] += _time.perf_counter() - t0
+                self._optimizer_step(kl_limit)
+            if kl_limit > 0 and float(self.ctrl[0]) != 0.0:              # ONE host sync per epoch: the reduced KL is identical on every rank
                 break
-        m = (acc / max(1, n_updates)).tolist()
-        return {"policy_loss": m[0], "value_loss": m[1], "entropy": m[2], "approx_kl": m[3], "n_updates": n_updates}
+        c = self.ctrl.tolist()
+        n_updates = int(c[4])
+        m = (acc / max(1, n_mb * (epoch + 1))).tolist()
+        return {"policy_loss": m[0], "value_loss": m[1], "entropy": m[2], "approx_kl": c[3], "grad_norm": c[2], "n_updates": n_updates,
+                "minibatches_per_epoch": n_mb, "early_stop": bool(c[0])}
 
     def learn(self, total_timesteps: Optional[int] = None, callback: Optional[Callable] = None):
+        import time as _time
         if total_timesteps is not None:
             self.total_timesteps = int(total_timesteps)
+        sync = (lambda: torch.cuda.synchronize(self.device)) if self.flat_p.is_cuda else (lambda: None)
         while self.num_timesteps < self.total_timesteps:
+            sync(); t0 = _time.perf_counter()
             buf, stats = self.collect()
+            sync(); t1 = _time.perf_counter()
             info = self.update(buf)
+            sync(); t2 = _time.perf_counter()
+            self.timing["collect_s"] += t1 - t0; self.timing["update_s"] += t2 - t1
             if callback is not None:
                 callback({**stats, **info, "num_timesteps": self.num_timesteps})
         return self

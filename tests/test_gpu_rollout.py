@@ -63,3 +63,38 @@ def test_depth_frame_collection(tmp_path):
     assert files[0] == "depth_0000.npy" and len(files) == (n + 99) // 100
     assert 0.0 < frames.min() and frames.max() <= 1.0
     venv.close()
+
+
+def test_fused_adamw_step_matches_torch_adamw_with_clipping_and_kl_stop():
+    """bb_adamw_step (mean of the all-reduced flat gradient, clip_grad_norm_, AdamW, sticky target-KL stop on the device) against
+    torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW on the same gradients."""
+    import ctypes as C
+    from openballbot_rl_b200 import _lib
+    torch.manual_seed(0)
+    n = 114_000
+    p_ref = torch.nn.Parameter(torch.randn(n, device="cuda") * 0.1)
+    opt = torch.optim.AdamW([p_ref], lr=1e-3, weight_decay=0.01)
+    p = p_ref.detach().clone(); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    g = torch.zeros(n + 2, device="cuda"); ctrl = torch.zeros(8, dtype=torch.float64, device="cuda"); scr = torch.zeros(1, dtype=torch.float64, device="cuda")
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    L = _lib.lib()
+    for step in range(6):
+        cnt = 512.0
+        grad_mean = torch.randn(n, device="cuda") * (0.02 if step % 2 else 0.0005)       # every other step exceeds max_grad_norm = 0.5
+        g[:n] = grad_mean * cnt; g[n] = 0.01 * cnt; g[n + 1] = cnt                          # SUM over the minibatch, KL below the limit
+        rc = L.bb_adamw_step(vp(p), vp(g), vp(m), vp(v), n, 1e-3, 0.9, 0.999, 1e-8, 0.01, 0.5, 0.45, vp(ctrl), vp(scr), None)
+        assert rc == 0
+        p_ref.grad = grad_mean.clone()
+        torch.nn.utils.clip_grad_norm_([p_ref], 0.5)
+        opt.step()
+        assert torch.allclose(p, p_ref.detach(), rtol=2e-5, atol=2e-7), step
+    c = ctrl.cpu().numpy()
+    assert c[0] == 0 and c[1] == 6 and c[4] == 6 and abs(c[3] - 0.01) < 1e-7
+    # KL above 1.5 x target: the step is skipped, the flag sticks for the rest of the iteration
+    before = p.clone()
+    g[n] = 0.5 * 512.0
+    assert L.bb_adamw_step(vp(p), vp(g), vp(m), vp(v), n, 1e-3, 0.9, 0.999, 1e-8, 0.01, 0.5, 0.45, vp(ctrl), vp(scr), None) == 0
+    g[n] = 0.0
+    assert L.bb_adamw_step(vp(p), vp(g), vp(m), vp(v), n, 1e-3, 0.9, 0.999, 1e-8, 0.01, 0.5, 0.45, vp(ctrl), vp(scr), None) == 0
+    c = ctrl.cpu().numpy()
+    assert torch.equal(p, before) and c[0] == 1 and c[1] == 6

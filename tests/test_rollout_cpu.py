@@ -96,3 +96,29 @@ def test_two_rank_gradient_allreduce_keeps_replicas_identical():
     (p0, s0, n0), (p1, s1, n1) = out[0], out[1]
     assert np.array_equal(p0, p1)                       # different shards, same averaged gradients => identical replicas
     assert s0 == s1 == 2 * 8 * 8 and n0 == n1 == 2 * 8 * 8
+
+
+def _worker_uneven(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(7 + rank)
+    pol = BallbotPolicy(cameras=False, hidden=16)
+    cfg = PPOConfig(n_steps=8, batch_size=24, n_epochs=2, learning_rate=1e-3, clip_range=0.2)
+    n_envs = 8 if rank == 0 else 5                      # 13 envs over 2 ranks: shard_envs gives 7 / 6, any uneven split must work
+    L = PPOLearner(StubVecEnv(n_envs, seed=rank), pol, cfg, total_timesteps=10 ** 6, gae_fn=_gae_torch, seed=3)
+    buf, stats = L.collect()
+    info = L.update(buf)
+    out[rank] = (torch.cat([p.detach().reshape(-1) for p in pol.parameters()]).numpy(), stats["env_steps"], L.num_timesteps, info["minibatches_per_epoch"], info["n_updates"])
+    dist.destroy_process_group()
+
+
+def test_uneven_env_shards_do_not_desynchronise_the_ranks():
+    """ranks with different env counts must issue the same collectives (same minibatch count), count the same global
+    timesteps and weight their gradients by sample count, so that the replicas stay identical."""
+    mgr = mp.Manager(); out = mgr.dict()
+    mp.spawn(_worker_uneven, args=(2, _free_port(), out), nprocs=2, join=True)
+    (p0, s0, n0, m0, u0), (p1, s1, n1, m1, u1) = out[0], out[1]
+    assert np.array_equal(p0, p1)
+    assert s0 == s1 == n0 == n1 == 8 * (8 + 5)
+    assert m0 == m1 == -(-8 * 13 // 24) and u0 == u1 == 2 * m0                 # ceil(104 / 24) = 5 minibatches incl. the remainder, 2 epochs
