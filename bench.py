@@ -213,10 +213,10 @@ def ppo_main(args, rank, local_rank, world):
                           "data": "synthetic",
                           "config": {"workload": f"full PPO iteration (BASELINE.json configs[3]): perlin + depth cameras, frozen encoders + 4x128 MLP policy, {envs} envs/GPU x {T} steps per rollout",
                                      "envs_per_gpu": envs, "n_steps": T, "global_batch": batch, "n_epochs": 5, "parallelism": f"env-sharded x{world}; one flat-buffer gradient all-reduce per minibatch (NCCL)"},
-                          "ppo": {"collect_ms_per_iter": col / iters, "update_ms_per_iter": upd / iters, "allreduce_host_ms_per_iter": ar / iters,
+                          "ppo": {"collect_ms_per_iter": col / iters, "update_ms_per_iter": upd / iters, "allreduce_ms_per_iter": ar / iters,
                                   "allreduce_share_of_update": ar / upd if upd else None, "rollout_only_env_steps_per_s": world * envs * T * iters / (col * 1e-3),
                                   "minibatches_per_epoch": hist[-1]["minibatches_per_epoch"], "updates_last_iter": hist[-1]["n_updates"], "early_stop_last_iter": hist[-1]["early_stop"],
-                                  "allreduce_bytes": 4 * (L.n_param + 2), "note": "allreduce time is host wall-clock around dist.all_reduce (enqueue + wait for the previous kernels), an upper bound of the NCCL time"}}))
+                                  "allreduce_bytes": 4 * (L.n_param + 2), "note": "allreduce time = CUDA events around every dist.all_reduce on the compute stream (NCCL kernel + waiting for the slowest rank)"}}))
     venv.close()
     if world > 1:
         dist.destroy_process_group()

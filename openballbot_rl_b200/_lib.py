@@ -136,12 +136,13 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        try:                                   # a fresh checkout: compile once if the toolchain is here, else fail loudly
+    if needs_build():
+        try:                                   # a fresh checkout or edited sources: (re)compile if the toolchain is here
             build(force=True)
         except Exception as exc:
-            raise EngineError(f"{LIB_PATH} not found and could not be built ({exc}): run `python -c 'import __graft_entry__ "
-                              "as g; g.build()'` (nvcc, sm_100a). The ballbot engine has no CPU fallback.") from exc
+            if not os.path.exists(LIB_PATH):   # ... else fail loudly; a stale library is reported by bb_build_info() (source hash)
+                raise EngineError(f"{LIB_PATH} not found and could not be built ({exc}): run `python -c 'import __graft_entry__ "
+                                  "as g; g.build()'` (nvcc, sm_100a). The ballbot engine has no CPU fallback.") from exc
     L = C.CDLL(LIB_PATH)
     vp = C.c_void_p
     L.bb_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]

@@ -221,6 +221,7 @@ class PPOLearner:
         kl_limit = 1.5 * cfg.target_kl if cfg.target_kl is not None else -1.0
         self.ctrl[0] = 0.0; self.ctrl[4] = 0.0
         acc = torch.zeros(3, device=dev)           # policy loss, value loss, entropy summed on the device
+        ar_events = []
         import time as _time
         for epoch in range(cfg.n_epochs):
             perm = torch.randperm(n, device=dev, generator=self.gen)
@@ -246,13 +247,20 @@ class PPOLearner:
                         self.flat_g[self.n_param + 1] = float(b)
                         acc += torch.stack([pl.detach(), vl.detach(), ent.detach()])
                 if world > 1:
-                    t0 = _time.perf_counter()
-                    dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)   # the PPO gradient all-reduce (NCCL over NVLink): one per minibatch
-                    self.timing["allreduce_s"] += _time.perf_counter() - t0
+                    if self.flat_g.is_cuda:      # device time of the collective: CUDA events on the stream NCCL synchronises with
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)   # the PPO gradient all-reduce (NCCL over NVLink): one per minibatch
+                        e1.record(); ar_events.append((e0, e1))
+                    else:
+                        t0 = _time.perf_counter()
+                        dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+                        self.timing["allreduce_s"] += _time.perf_counter() - t0
                 self._optimizer_step(kl_limit)
             if kl_limit > 0 and float(self.ctrl[0]) != 0.0:              # ONE host sync per epoch: the reduced KL is identical on every rank
                 break
-        c = self.ctrl.tolist()
+        c = self.ctrl.tolist()                       # (synchronises the stream: the events below are complete)
+        self.timing["allreduce_s"] += sum(a.elapsed_time(b) for a, b in ar_events) * 1e-3
         n_updates = int(c[4])
         m = (acc / max(1, n_mb * (epoch + 1))).tolist()
         return {"policy_loss": m[0], "value_loss": m[1], "entropy": m[2], "approx_kl": c[3], "grad_norm": c[2], "n_updates": n_updates,

@@ -24,10 +24,14 @@ class Config(C.Structure):
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "ballbot_oracle.cpp")
-    if force or not os.path.exists(_SO) or (os.path.exists(src) and os.path.getmtime(_SO) < os.path.getmtime(src)):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    """make -C oracle: libballbot_oracle.so (bbo_* API) and libballbot_cpu_ref.so (the oracle behind the engine's bb_* ABI)."""
+    if force:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "clean"])
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
+
+
+CPU_REF_SO = os.path.join(_HERE, "_build", "libballbot_cpu_ref.so")
 
 
 _lib = None

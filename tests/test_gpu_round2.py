@@ -265,3 +265,39 @@ def test_engine_runs_on_its_own_device_whatever_the_current_device_is():
     (q0, v0, _), (q1, v1, _) = e0.get_state(), e1.get_state()
     assert q1.device.index == 1 and torch.equal(q0.cpu(), q1.cpu()) and torch.equal(v0.cpu(), v1.cpu())
     e0.close(); e1.close()
+
+
+def test_cuda_engine_and_cpu_ref_backend_through_one_harness():
+    """the same C ABI implemented twice -- libballbot_b200.so (CUDA) and oracle/_build/libballbot_cpu_ref.so (the fp64
+    oracle) -- driven by ONE harness with the same script: perlin terrain, cameras, auto-reset, numpy PCG64 terrain seeds.
+    Observations / rewards / flags / seeds / states are compared after every step."""
+    from tests.backend_harness import Backend, pcg64_states
+    N = 6
+    kw = dict(num_envs=N, terrain_type=1, cameras=1, max_ep_steps=40, seed_stream=1, auto_reset=1, perlin_table=0)
+    bc, br = Backend("cuda", **kw), Backend("cpu_ref", **kw)
+    st = pcg64_states([100 + i for i in range(N)])
+    bc.set_rng_state(st); br.set_rng_state(st)
+    oc, orf = bc.reset(), br.reset()
+    assert bc.terrain_seeds().tolist() == br.terrain_seeds().tolist()
+    rng = np.random.default_rng(1)
+    resets = 0
+    for t in range(90):
+        a = np.clip(rng.normal(size=(N, 3)), -1, 1).astype(np.float32)
+        oc, orf = bc.step(a), br.step(a)
+        np.testing.assert_array_equal(oc["terminated"], orf["terminated"]); np.testing.assert_array_equal(oc["failure"], orf["failure"])
+        np.testing.assert_allclose(oc["reward"], orf["reward"], atol=1e-6)
+        for k in ("orientation", "angular_vel", "vel", "motor_state", "actions", "rel_image_ts", "pos2d"):
+            np.testing.assert_allclose(oc[k], orf[k], atol=2e-6, err_msg=f"{k} t={t}")
+        d = oc["terminated"].astype(bool)
+        if d.any():
+            resets += int(d.sum())
+            np.testing.assert_allclose(oc["terminal_obs"][d], orf["terminal_obs"][d], atol=2e-6)
+            np.testing.assert_array_equal(oc["episode_length"][d], orf["episode_length"][d])
+            np.testing.assert_allclose(oc["episode_return"][d], orf["episode_return"][d], atol=1e-5)
+        assert bc.terrain_seeds().tolist() == br.terrain_seeds().tolist()
+        assert (np.abs(oc["rgbd_0"] - orf["rgbd_0"]) > 1e-3).mean() < 0.01
+    (qc, vc, _), (qr, vr, _) = bc.get_state(), br.get_state()
+    assert _rel(qc, qr) < 1e-6 and _rel(vc, vr) < 1e-6 and resets >= N
+    rows_c, rows_r = bc.contacts(0), br.contacts(0)
+    assert rows_c.shape == rows_r.shape
+    bc.close(); br.close()
