@@ -144,6 +144,9 @@ int bb_perlin_terrain(bb_engine* e, const int32_t* seeds_dev, int32_t n_seeds, f
  * (ComponentRegistry.get_terrain("perlin")(n, **cfg), terrain/__init__.py:19): out_host float[nseeds, n*n] */
 int bb_perlin_grid(int32_t device, int32_t n, float scale, int32_t octaves, float persistence, float lacunarity, float amplitude,
                    const int32_t* seeds_host, int32_t nseeds, float* out_host);
+/* raw untiled 2-D simplex fBm == noise.snoise2(i / scale, j / scale, octaves, persistence, lacunarity, base=seed) for i, j < n
+ * (terrain/gradient.py:74-80, gradient_type="perlin"): out_host float[n*n] */
+int bb_snoise2_grid(int32_t device, int32_t n, float scale, int32_t octaves, float persistence, float lacunarity, int32_t base, float* out_host);
 /* depth ray-cast of both cameras for every env at its CURRENT state (sensors/rgbd.py:46-82), ignoring the cadence */
 int bb_render_depth(bb_engine* e, float* rgbd_0, float* rgbd_1, void* cuda_stream);
 

@@ -58,7 +58,7 @@ EXPORTED = ["bb_create", "bb_destroy", "bb_default_config", "bb_last_error", "bb
             "bb_add_reward", "bb_set_state", "bb_get_state", "bb_set_hfield", "bb_get_hfield", "bb_get_terrain_seeds",
             "bb_perlin_terrain", "bb_render_depth", "bb_step_host", "bb_reset_host", "bb_launch_count",
             "bb_model_constants", "bb_probe_forward", "bb_profile_begin", "bb_profile_end", "bb_perlin_grid", "bb_gae", "bb_host_buffers",
-            "bb_set_rng_state", "bb_get_contacts", "bb_build_info", "bb_fp64_peak", "bb_adamw_step"]
+            "bb_set_rng_state", "bb_get_contacts", "bb_build_info", "bb_fp64_peak", "bb_adamw_step", "bb_snoise2_grid"]
 
 
 def needs_build():
@@ -155,6 +155,7 @@ def lib():
     L.bb_reset.argtypes = [vp, vp, vp, C.POINTER(IO), vp]
     L.bb_set_rng_state.argtypes = [vp, vp, vp]
     L.bb_get_contacts.argtypes = [vp, C.c_int32, vp, vp, vp]
+    L.bb_snoise2_grid.argtypes = [C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_int32, vp]
     L.bb_adamw_step.argtypes = [vp, vp, vp, vp, C.c_int32] + [C.c_float] * 7 + [vp, vp, vp]
     L.bb_fp64_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     L.bb_build_info.argtypes = []

@@ -637,6 +637,46 @@ __device__ float perlinHeight(const int* __restrict__ perm, int i, int j, int se
   perlinCircle(i, scale, si, ci); perlinCircle(j, scale, sj, cj);
   return perlinFbm(perm, si, ci, sj, cj, seed, oct, pers, lac, amp);
 }
+// 2-D simplex noise of noise._simplex (untiled branch of snoise2: terrain/gradient.py:74-80), same unfused float arithmetic
+__device__ float simplex2(const int* __restrict__ perm, float x, float y) {
+  const float F2 = 0.3660254037844386f, G2 = 0.21132486540518713f;
+  const float s = FM(FA(x, y), F2), i = floorf(FA(x, s)), j = floorf(FA(y, s)), t = FM(FA(i, j), G2);
+  float xx[3], yy[3];
+  xx[0] = FS(x, FS(i, t)); yy[0] = FS(y, FS(j, t));
+  const int i1 = xx[0] > yy[0], j1 = xx[0] <= yy[0];
+  xx[2] = FS(FA(xx[0], FM(G2, 2.0f)), 1.0f); yy[2] = FS(FA(yy[0], FM(G2, 2.0f)), 1.0f);
+  xx[1] = FA(FS(xx[0], (float)i1), G2); yy[1] = FA(FS(yy[0], (float)j1), G2);
+  const int I = (int)i & 255, J = (int)j & 255;
+  const int g[3] = {dperm(perm, I + dperm(perm, J)) % 12, dperm(perm, I + i1 + dperm(perm, J + j1)) % 12, dperm(perm, I + 1 + dperm(perm, J + 1)) % 12};
+  float n[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const float f = FS(FS(0.5f, FM(xx[c], xx[c])), FM(yy[c], yy[c]));
+    if (f > 0.f) {
+      // GRAD3 = {1,1,0},{-1,1,0},{1,-1,0},{-1,-1,0},{1,0,1},{-1,0,1},{1,0,-1},{-1,0,-1},{0,1,1},{0,-1,1},{0,1,-1},{0,-1,-1}: only x, y are used
+      const int gi = g[c];
+      const float gx = gi < 8 ? ((gi & 1) ? -1.f : 1.f) : 0.f;
+      const float gy = gi < 4 ? ((gi & 2) ? -1.f : 1.f) : (gi < 8 ? 0.f : ((gi & 1) ? -1.f : 1.f));
+      const float f2 = FM(f, f);
+      n[c] = FM(FM(f2, f2), FA(FM(gx, xx[c]), FM(gy, yy[c])));
+    }
+  }
+  return FM(FA(FA(n[0], n[1]), n[2]), 70.0f);
+}
+__global__ void __launch_bounds__(256) k_snoise2_grid(int n, float scale, int oct, float pers, float lac, int base, float* __restrict__ out) {
+  __shared__ int perm[256];
+  perm[threadIdx.x] = c_perm[threadIdx.x];
+  __syncthreads();
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= n * n) return;
+  const float x = (float)((double)(cell / n) / (double)scale), y = (float)((double)(cell % n) / (double)scale), z = (float)base;
+  float freq = 1.f, amp = 1.f, mx = 1.f, total = simplex2(perm, FA(x, z), FA(y, z));
+  for (int o = 1; o < oct; o++) {
+    freq = FM(freq, lac); amp = FM(amp, pers); mx = FA(mx, amp);
+    total = FA(total, FM(simplex2(perm, FA(FM(x, freq), z), FA(FM(y, freq), z)), amp));
+  }
+  out[cell] = __fdiv_rn(total, mx);
+}
 #undef FM
 #undef FA
 #undef FS
@@ -1436,6 +1476,21 @@ int bb_perlin_grid(int32_t device, int32_t n, float scale, int32_t octaves, floa
   }
   cudaFree(dseeds); cudaFree(dout);
   if (rc != BB_OK) snprintf(g_create_error, sizeof(g_create_error), "bb_perlin_grid: CUDA error %s", cudaGetErrorString(cudaGetLastError()));
+  return rc;
+}
+
+// host-in / host-out raw 2-D simplex fBm (untiled noise.snoise2): out[i * n + j] = snoise2(i / scale, j / scale, octaves, persistence, lacunarity, base)
+int bb_snoise2_grid(int32_t device, int32_t n, float scale, int32_t octaves, float persistence, float lacunarity, int32_t base, float* out_host) {
+  if (n < 1 || !out_host || octaves < 1 || scale == 0.f) return BB_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) { snprintf(g_create_error, sizeof(g_create_error), "bb_snoise2_grid: CUDA device %d not available; no CPU fallback", device); return BB_ERR_NO_DEVICE; }
+  DevGuard guard(device);
+  if (cudaMemcpyToSymbol(c_perm, h_perm, sizeof(h_perm)) != cudaSuccess) return BB_ERR_CUDA;
+  float* dout = nullptr; const size_t cells = (size_t)n * n;
+  if (cudaMalloc(&dout, sizeof(float) * cells) != cudaSuccess) return BB_ERR_CUDA;
+  k_snoise2_grid<<<(unsigned)((cells + 255) / 256), 256>>>(n, scale, octaves, persistence, lacunarity, base, dout);
+  const int rc = cudaMemcpy(out_host, dout, sizeof(float) * cells, cudaMemcpyDeviceToHost) == cudaSuccess ? BB_OK : BB_ERR_CUDA;
+  cudaFree(dout);
   return rc;
 }
 

@@ -156,8 +156,8 @@ def generate_bowl_terrain(n: int, depth: float = 0.6, radius: float = 0.4, cente
 
 def generate_gradient_terrain(n: int, max_slope: float = 20.0, gradient_type: str = "linear", smoothness: float = 0.5, direction: str = "x",
                               seed: Optional[int] = None) -> np.ndarray:
-    """terrain/gradient.py. The 'perlin' variant needs noise.snoise2 in its NON-tiled 2-D form, which the reference takes
-    from the `noise` C extension; it is not part of the GPU engine and raises here (documented gap)."""
+    """terrain/gradient.py:7-93. The 'perlin' variant modulates the linear ramp with the untiled 2-D ``noise.snoise2``
+    (3 octaves, persistence 0.3, base = seed), evaluated by the engine's device code (``bb_snoise2_grid``; needs a CUDA device)."""
     assert n % 2 == 1, "n should be odd for heightfield symmetry"
     assert 0 <= max_slope <= 45, "max_slope should be between 0 and 45 degrees"
     assert gradient_type in ["linear", "radial", "perlin"], "gradient_type must be 'linear', 'radial', or 'perlin'"
@@ -171,7 +171,13 @@ def generate_gradient_terrain(n: int, max_slope: float = 20.0, gradient_type: st
     elif gradient_type == "radial":
         t = hmax * np.clip(np.sqrt(X ** 2 + Y ** 2) / np.sqrt(2.0), 0.0, 1.0)
     else:
-        raise NotImplementedError("gradient_type='perlin' (2-D untiled snoise2) is not provided by the B200 engine")
+        import ctypes as C
+        from .. import _lib
+        noise = np.empty(n * n, np.float32)
+        rc = _lib.lib().bb_snoise2_grid(0, int(n), 25.0, 3, 0.3, 2.0, int(seed) if seed is not None else 0, C.c_void_p(noise.ctypes.data))
+        if rc != 0:
+            raise _lib.EngineError(f"bb_snoise2_grid failed ({rc}): {_lib.lib().bb_last_error(None).decode()}")
+        t = hmax * (((X if direction == "x" else Y) + 1.0) / 2.0 + noise.reshape(n, n).astype(np.float64) * smoothness)
     return _normalise(t).flatten()
 
 

@@ -261,6 +261,11 @@ int bb_perlin_grid(int32_t, int32_t n, float scale, int32_t octaves, float persi
   for (int k = 0; k < nseeds; k++) bbo_perlin_terrain(n, scale, octaves, persistence, lacunarity, amplitude, seeds[k], out + (size_t)k * n * n);
   return BB_OK;
 }
+int bb_snoise2_grid(int32_t, int32_t n, float scale, int32_t octaves, float persistence, float lacunarity, int32_t base, float* out) {
+  if (n < 1 || !out || octaves < 1 || scale == 0.f) return BB_ERR_INVALID;
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) out[i * n + j] = bbo_snoise2((float)(i / (double)scale), (float)(j / (double)scale), octaves, persistence, lacunarity, base);
+  return BB_OK;
+}
 int bb_render_depth(bb_engine* e, float* img0, float* img1, void*) {
   if (!e || !img0 || !img1) return BB_ERR_INVALID;
   const size_t npix = (size_t)e->cfg.im_h * e->cfg.im_w;

@@ -341,3 +341,21 @@ def test_seed_independent_plugin_terrain_is_shared_and_auto_resets_on_device():
     venv = BallbotVecEnv(2, terrain_config={"type": "hills", "config": {"num_hills": 3}}, reward_config=REWARD, env_config=cfg, disable_cams=True)
     assert not venv._terrain_shared and venv._manual_reset
     venv.close()
+
+
+def test_gradient_perlin_terrain_matches_oracle_noise(oracle_mod):
+    """terrain/gradient.py:70-93 (gradient_type="perlin"): device 2-D simplex fBm against the oracle's restatement of the untiled
+    noise.snoise2, then the reference's own formula on top."""
+    from openballbot_rl_b200.terrain import shapes
+    n, seed, smooth, slope = 65, 9, 0.5, 20.0
+    out = shapes.generate_gradient_terrain(n, max_slope=slope, gradient_type="perlin", smoothness=smooth, direction="y", seed=seed)
+    L = oracle_mod.lib()
+    noise = np.array([[L.bbo_snoise2(np.float32(i / 25.0), np.float32(j / 25.0), 3, 0.3, 2.0, seed) for j in range(n)] for i in range(n)], np.float64)
+    c = n // 2
+    u = (np.arange(n) - c) / c
+    X, Y = np.meshgrid(u, u, indexing="ij")
+    t = np.tan(np.radians(slope)) * 2.0 * ((Y + 1.0) / 2.0 + noise * smooth)
+    ref = ((t - t.min()) / (t.max() - t.min())).flatten()
+    assert out.shape == (n * n,) and out.min() == 0.0 and out.max() == 1.0
+    np.testing.assert_allclose(out, ref, atol=2e-6)
+    assert np.abs(noise).max() > 0.2                                     # the noise term is really there

@@ -154,8 +154,14 @@ def test_create_terrain_runtime_seed_overrides_config():
     assert flat.shape == (129 * 129,) and not flat.any()
 
 
-def test_gradient_perlin_variant_is_a_documented_gap():
-    with pytest.raises(NotImplementedError):
+def test_gradient_perlin_variant_runs_the_device_noise():
+    """gradient_type="perlin" evaluates the untiled 2-D snoise2 with the engine's device code (bb_snoise2_grid): like the perlin
+    terrain it needs a CUDA device and has no CPU implementation in the product (GPU parity: tests/test_gpu_envs.py)."""
+    import torch
+    from openballbot_rl_b200._lib import EngineError
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present: covered by the GPU parity test")
+    with pytest.raises(EngineError):
         shapes.generate_gradient_terrain(33, gradient_type="perlin")
 
 
