@@ -35,7 +35,10 @@ typedef enum bb_status {
 /* BB_TERRAIN_SHARED: one caller-provided heightfield for all envs (plugin terrains that do not depend on the per-reset seed,
  * e.g. ramp / stairs / bowl with a fixed config): uploaded once with bb_set_hfield(env_ids = {0}, n = 1), auto-reset stays on
  * the device like for BB_TERRAIN_FLAT. */
-typedef enum bb_terrain { BB_TERRAIN_FLAT = 0, BB_TERRAIN_PERLIN = 1, BB_TERRAIN_EXTERNAL = 2, BB_TERRAIN_SHARED = 3 } bb_terrain;
+/* BB_TERRAIN_TABLE: caller-provided heightfields for EVERY possible terrain seed (slot = r_seed, BB_PERLIN_SEEDS slots, or one slot
+ * with a fixed terrain_seed), uploaded with bb_set_hfield(env_ids = slots): seed-dependent plugin terrains (hills, mixed, user
+ * callables) then reset on the device like the built-in Perlin table -- the law r_seed ~ U{0..9999} (ballbot_env.py:506) is kept. */
+typedef enum bb_terrain { BB_TERRAIN_FLAT = 0, BB_TERRAIN_PERLIN = 1, BB_TERRAIN_EXTERNAL = 2, BB_TERRAIN_SHARED = 3, BB_TERRAIN_TABLE = 4 } bb_terrain;
 typedef enum bb_reward { BB_REWARD_DIRECTIONAL = 0, BB_REWARD_DISTANCE = 1, BB_REWARD_EXTERNAL = 2 } bb_reward;
 
 /* Replaces the constructor arguments / YAML knobs of BBotSimulation.__init__ (ballbot_gym/envs/ballbot_env.py:157-231)

@@ -1150,7 +1150,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   if (!cfg || !out) { snprintf(g_create_error, sizeof(g_create_error), "bb_create: NULL argument"); return BB_ERR_INVALID; }
   *out = nullptr;
   if (cfg->abi_version != BB_ABI_VERSION || cfg->num_envs < 1 || (cfg->precision != 32 && cfg->precision != 64) || cfg->im_h < 1 || cfg->im_w < 1 ||
-      cfg->terrain_type < 0 || cfg->terrain_type > 3 || cfg->reward_type < 0 || cfg->reward_type > 2 || cfg->camera_frame_rate <= 0.f ||
+      cfg->terrain_type < 0 || cfg->terrain_type > 4 || cfg->reward_type < 0 || cfg->reward_type > 2 || cfg->camera_frame_rate <= 0.f ||
       cfg->perlin_table < -1 || cfg->perlin_table > 1 || cfg->seed_stream < 0 || cfg->seed_stream > 1 || cfg->perlin_octaves < 1) {
     snprintf(g_create_error, sizeof(g_create_error), "bb_create: invalid config (abi %d, num_envs %d, precision %d)", cfg->abi_version, cfg->num_envs, cfg->precision);
     return BB_ERR_INVALID;
@@ -1189,6 +1189,9 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   p.dist_scale = cfg->distance_scale; p.zscale = cfg->hfield_zscale; p.terrain_type = cfg->terrain_type; p.terrain_seed = cfg->terrain_seed;
   p.seed = cfg->seed; p.auto_reset = cfg->auto_reset; p.solver_mode = cfg->solver_mode; p.seed_stream = cfg->seed_stream;
   p.hf_mode = cfg->terrain_type == BB_TERRAIN_EXTERNAL ? HF_PER_ENV : HF_SHARED;
+  if (cfg->terrain_type == BB_TERRAIN_TABLE) {   // caller-provided fields for every seed 0 .. BB_PERLIN_SEEDS - 1 (seed-dependent plugin terrains)
+    p.hf_mode = HF_TABLE; e->table_n = cfg->terrain_seed >= 0 ? 1 : BB_PERLIN_SEEDS;
+  }
   if (cfg->terrain_type == BB_TERRAIN_PERLIN) {
     // a fixed terrain seed means ONE field for every env and every episode; random seeds mean at most BB_PERLIN_SEEDS fields
     const bool table = cfg->terrain_seed >= 0 || cfg->perlin_table == 1 || (cfg->perlin_table == -1 && N >= 2048);
@@ -1224,7 +1227,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   BB_CUDA_C(cudaMalloc(&d.reset_list, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.refresh_list, sizeof(int) * N));
   const size_t hfbytes = sizeof(float) * HF_CELLS * (p.hf_mode == HF_PER_ENV ? (size_t)N : (p.hf_mode == HF_TABLE ? (size_t)e->table_n : 1));
   BB_CUDA_C(cudaMalloc(&d.hfield, hfbytes));
-  if (p.hf_mode != HF_TABLE) BB_CUDA_C(cudaMemset(d.hfield, 0, hfbytes));
+  if (p.hf_mode != HF_TABLE || cfg->terrain_type == BB_TERRAIN_TABLE) BB_CUDA_C(cudaMemset(d.hfield, 0, hfbytes));
   BB_CUDA_C(cudaMalloc(&d.ptab, sizeof(float) * 2 * HN));
   k_perlin_table<<<blocksFor(HN, 128), 128>>>(cfg->perlin_scale, d.ptab);
   const size_t nfields = p.hf_mode == HF_PER_ENV ? (size_t)N : (p.hf_mode == HF_TABLE ? (size_t)e->table_n : 1);
@@ -1233,7 +1236,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   BB_CUDA_C(cudaMalloc(&d.rng, sizeof(unsigned long long) * 5 * (size_t)N));
   BB_CUDA_C(cudaMemset(d.rng, 0, sizeof(unsigned long long) * 5 * (size_t)N));
   BB_CUDA_C(cudaMalloc(&e->probe_out, sizeof(double) * 64));
-  if (p.hf_mode == HF_TABLE) {
+  if (p.hf_mode == HF_TABLE && cfg->terrain_type == BB_TERRAIN_PERLIN) {
     // every Perlin field the reference can ever draw (r_seed in 0 .. 9999, ballbot_env.py:506), generated once by the same
     // kernel that regenerates per-env fields: resets then only select a field, and HBM use no longer grows with num_envs
     int* seeds = nullptr;
@@ -1383,7 +1386,9 @@ int bb_set_hfield(bb_engine* e, const int32_t* ids, int32_t n, const float* hf, 
     BB_CUDA(cudaGetLastError());
     return BB_OK;
   }
-  if (e->p.hf_mode != HF_PER_ENV) return fail(e, BB_ERR_INVALID, "bb_set_hfield: engine has no per-env heightfields (flat terrain or Perlin table); create it with BB_TERRAIN_EXTERNAL");
+  if (e->cfg.terrain_type == BB_TERRAIN_TABLE) {   // ids = table slots (terrain seeds); host-side bound check is the caller's (ids live on the device)
+    if (n > e->table_n) return fail(e, BB_ERR_INVALID, "bb_set_hfield: more fields than table slots");
+  } else if (e->p.hf_mode != HF_PER_ENV) return fail(e, BB_ERR_INVALID, "bb_set_hfield: engine has no per-env heightfields (flat terrain or Perlin table); create it with BB_TERRAIN_EXTERNAL");
   if (n == 0) return BB_OK;
   const size_t tot = (size_t)n * HF_CELLS;
   k_scatter_hfield<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids, n, hf, e->d.hfield);

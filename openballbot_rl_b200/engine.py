@@ -16,7 +16,7 @@ import torch
 from . import _lib
 from ._lib import EngineError, HFIELD_N, NQ, NV
 
-TERRAIN_FLAT, TERRAIN_PERLIN, TERRAIN_EXTERNAL, TERRAIN_SHARED = 0, 1, 2, 3
+TERRAIN_FLAT, TERRAIN_PERLIN, TERRAIN_EXTERNAL, TERRAIN_SHARED, TERRAIN_TABLE = 0, 1, 2, 3, 4
 REWARD_DIRECTIONAL, REWARD_DISTANCE, REWARD_EXTERNAL = 0, 1, 2
 OBS_KEYS = ("orientation", "angular_vel", "vel", "motor_state", "actions")
 
@@ -37,7 +37,7 @@ class BallbotEngine:
         L = _lib.lib()
         cfg = _lib.default_config()
         cfg.num_envs = int(num_envs); cfg.device = int(device); cfg.precision = int(precision); cfg.env_offset = int(env_offset)
-        cfg.terrain_type = {"flat": TERRAIN_FLAT, "perlin": TERRAIN_PERLIN, "external": TERRAIN_EXTERNAL, "shared": TERRAIN_SHARED}[terrain]
+        cfg.terrain_type = {"flat": TERRAIN_FLAT, "perlin": TERRAIN_PERLIN, "external": TERRAIN_EXTERNAL, "shared": TERRAIN_SHARED, "table": TERRAIN_TABLE}[terrain]
         cfg.terrain_seed = -1 if terrain_seed is None else int(terrain_seed)
         perlin = perlin or {}
         cfg.perlin_scale = float(perlin.get("scale", 25.0)); cfg.perlin_octaves = int(perlin.get("octaves", 4))

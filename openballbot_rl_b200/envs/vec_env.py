@@ -29,6 +29,14 @@ HFIELD_HALF_EXTENT = 5.0      # ballbot.xml:23 size[0]
 DEFAULT_ZSCALE = 2.0          # ballbot.xml:23 size[2]
 
 
+def _generate_fields(args):
+    """Pool worker: heightfields of a plugin terrain for a list of seeds (the generators are pure functions of (config, seed))."""
+    terrain_config, seeds = args
+    import openballbot_rl_b200.terrain  # noqa: F401
+    gen = create_terrain(terrain_config)
+    return np.stack([np.asarray(gen(293, seed=int(sd)), np.float32).reshape(-1) for sd in seeds])
+
+
 def resolve_zscale(terrain_config: dict) -> float:
     """ramp / gradient terrains rescale the heightfield so the physical slope matches the angle (ballbot_env.py:486-495)."""
     kind = terrain_config.get("type")
@@ -50,7 +58,7 @@ class BallbotVecEnv(_VecEnvBase):
     def __init__(self, num_envs: int, terrain_config: Optional[dict] = None, reward_config: Optional[dict] = None,
                  env_config: Optional[dict] = None, seed: int = 0, disable_cams: bool = False, device: int = 0, precision: int = 64,
                  output: str = "torch", solver: str = "exact", env_offset: int = 0, terrain_type: Optional[str] = None,
-                 env_seeds=None, perlin_table: Optional[bool] = None):
+                 env_seeds=None, perlin_table: Optional[bool] = None, terrain_bank: Optional[bool] = None):
         import openballbot_rl_b200.rewards  # noqa: F401  (registers the built-ins)
         import openballbot_rl_b200.terrain  # noqa: F401
         if terrain_config is None:
@@ -82,13 +90,19 @@ class BallbotVecEnv(_VecEnvBase):
             else:
                 a, b = (np.asarray(self.terrain_gen(293, seed=sd), np.float32) for sd in (0, 1))
                 self._terrain_shared = bool(np.array_equal(a, b))
-        self._manual_reset = (self._terrain_plugin and not self._terrain_shared) or self._reward_plugin
+        # A seed-DEPENDENT plugin terrain (hills, mixed, gradient/perlin, user callables) still has only 10,000 possible fields
+        # (r_seed = integers(0, 10000), ballbot_env.py:506).  terrain_bank: all of them are generated once on the host cores and
+        # uploaded as a device table, after which resets never leave the device; None = automatic from 2048 envs up.
+        self._terrain_bank = bool(self._terrain_plugin and not self._terrain_shared and
+                                  (terrain_bank if terrain_bank is not None else int(num_envs) >= 2048))
+        self._manual_reset = (self._terrain_plugin and not self._terrain_shared and not self._terrain_bank) or self._reward_plugin
         im_h, im_w = int(cam_s.get("height", 64)), int(cam_s.get("width", 64))
         if not cam_s.get("disable_rgb", True) and not disable_cams:
             raise NotImplementedError("RGB channels need the OpenGL rasteriser; the B200 engine provides depth only (camera.disable_rgb: true)")
         self.engine = BallbotEngine(
             num_envs=self.num_envs, device=device, precision=precision,
-            terrain=("shared" if self._terrain_shared else "external") if self._terrain_plugin else ttype, terrain_seed=tcfg.get("seed"),
+            terrain=("shared" if self._terrain_shared else ("table" if self._terrain_bank else "external")) if self._terrain_plugin else ttype,
+            terrain_seed=tcfg.get("seed"),
             perlin={k: tcfg[k] for k in ("scale", "octaves", "persistence", "lacunarity", "amplitude") if k in tcfg},
             hfield_zscale=resolve_zscale(terrain_config), cameras=not disable_cams, im_h=im_h, im_w=im_w,
             camera_frame_rate=cam_s.get("frame_rate", 90), max_ep_steps=self.max_ep_steps,
@@ -99,6 +113,8 @@ class BallbotVecEnv(_VecEnvBase):
             distance_scale=rcfg.get("scale", 1.0) if rtype == "distance" else 1.0,
             seed=seed, auto_reset=not self._manual_reset, env_offset=env_offset, solver=solver, perlin_table=perlin_table,
             seed_stream="pcg64" if env_seeds is not None else "counter")
+        if self._terrain_bank:
+            self._upload_terrain_bank()
         if env_seeds is not None:
             # the reference's per-env generators: training env i is seeded with seed + i by SB3, eval env i is built with
             # eval_env=[True, seed + N + i] (train.py:83-97); terrain seeds are then integers(0, 10000) draws of that PCG64
@@ -112,10 +128,17 @@ class BallbotVecEnv(_VecEnvBase):
         self.last_terrain_seeds = np.zeros(self.num_envs, np.int64)
         self.render_mode = None
         self._closed = False
+        self._logger = None
         if HAVE_SB3:   # pragma: no cover
             _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
 
     # ------------------------------------------------------------------ helpers
+    def attach_episode_logger(self, log_dir: str, log_options=None, max_envs: int = 4):
+        """Reward-term histories and ``terrain_seed_history`` like the reference's env-side logger (utils/logging.py:52-117)."""
+        from ..training.episode_logs import EpisodeLogger
+        self._logger = EpisodeLogger(self, log_dir, log_options, max_envs)
+        return self._logger
+
     @property
     def opt_timestep(self):
         return 0.002
@@ -143,6 +166,17 @@ class BallbotVecEnv(_VecEnvBase):
             fields[k] = self._terrain_cache[r_seed]
         self.engine.set_hfield(env_ids.astype(np.int32), fields)
 
+    def _upload_terrain_bank(self, chunk: int = 250):
+        """Generate the heightfield of every possible terrain seed with a process pool and fill the engine's table (BB_TERRAIN_TABLE)."""
+        import multiprocessing as mp
+        import os
+        seeds = np.arange(10000)
+        jobs = [(self.terrain_config, seeds[k:k + chunk]) for k in range(0, len(seeds), chunk)]
+        procs = min(len(jobs), os.cpu_count() or 1)
+        with mp.get_context("fork").Pool(procs) as pool:          # fork: custom plugins registered in this process exist in the workers
+            for (cfg, sd), fields in zip(jobs, pool.imap(_generate_fields, jobs)):
+                self.engine.set_hfield(sd.astype(np.int32), fields)
+
     # ------------------------------------------------------------------ VecEnv protocol
     def reset(self, terrain_seeds=None):
         """``terrain_seeds`` (int[N], optional): replay recorded ``r_seed`` values instead of drawing them (built-in perlin)."""
@@ -150,6 +184,8 @@ class BallbotVecEnv(_VecEnvBase):
             if self._terrain_plugin:
                 raise ValueError("terrain_seeds applies to the built-in perlin terrain")
             self.engine.reset(seeds=terrain_seeds)
+            if self._logger is not None:
+                self._logger.after_reset()
             return self._obs_view()
         if self._terrain_shared:
             if not getattr(self, "_shared_uploaded", False):
@@ -158,9 +194,11 @@ class BallbotVecEnv(_VecEnvBase):
                 self.last_terrain_seeds[:] = r_seed
                 self.engine.set_hfield(np.zeros(1, np.int32), np.asarray(self.terrain_gen(293, seed=r_seed), np.float32).reshape(1, -1))
                 self._shared_uploaded = True
-        elif self._terrain_plugin:
+        elif self._terrain_plugin and not self._terrain_bank:
             self._upload_plugin_terrain(np.arange(self.num_envs))
         self.engine.reset()
+        if self._logger is not None:
+            self._logger.after_reset()
         return self._obs_view()
 
     def step_async(self, actions):
@@ -176,12 +214,14 @@ class BallbotVecEnv(_VecEnvBase):
         if self._reward_plugin:   # custom BaseReward evaluated on the device-resident batch (pre-reset observation)
             state = dict(eng.obs); state["pos2d"] = eng.pos2d
             eng.add_reward(torch.as_tensor(self.reward_obj(state), device=eng.device, dtype=torch.float32).reshape(self.num_envs))
+        if self._logger is not None and not self._manual_reset:
+            self._logger.after_step(a)
         term_obs = None
         if self._manual_reset:
             done_mask = eng.terminated.clone()
             if bool(done_mask.any()):
                 term_obs = eng.terminal_obs.clone()
-                if self._terrain_plugin and not self._terrain_shared:
+                if self._terrain_plugin and not self._terrain_shared and not self._terrain_bank:
                     self._upload_plugin_terrain(torch.nonzero(done_mask).flatten().cpu().numpy())
                 rew, term, fail, pos = eng.reward.clone(), eng.terminated.clone(), eng.failure.clone(), eng.pos2d.clone()
                 eng.reset(done_mask)

@@ -359,3 +359,54 @@ def test_gradient_perlin_terrain_matches_oracle_noise(oracle_mod):
     assert out.shape == (n * n,) and out.min() == 0.0 and out.max() == 1.0
     np.testing.assert_allclose(out, ref, atol=2e-6)
     assert np.abs(noise).max() > 0.2                                     # the noise term is really there
+
+
+def test_seed_dependent_plugin_terrain_bank_resets_on_the_device():
+    """hills draws its hill centres from the per-reset seed: with terrain_bank the fields of all 10,000 possible seeds are generated
+    once (host process pool) and live in a device table (BB_TERRAIN_TABLE); auto-reset then stays on the device and every env runs
+    on exactly the field of the seed it drew."""
+    from openballbot_rl_b200.envs import BallbotVecEnv
+    from openballbot_rl_b200.terrain import shapes
+    cfg = {**ENV_CFG, "env": {**ENV_CFG["env"], "max_ep_steps": 25}}
+    tcfg = {"type": "hills", "config": {"num_hills": 4, "hill_height": 0.2}}
+    venv = BallbotVecEnv(8, terrain_config=tcfg, reward_config=REWARD, env_config=cfg, disable_cams=True, precision=64, terrain_bank=True)
+    assert venv._terrain_bank and not venv._manual_reset
+    venv.reset()
+    a = torch.zeros(8, 3, device="cuda")
+    n_done = 0
+    for t in range(60):
+        obs, rew, dones, info = venv.step(a)
+        n_done += int(dones.sum())
+    assert n_done >= 16                                                       # two rounds of device-side auto-resets
+    seeds = venv.engine.terrain_seeds().cpu().numpy()
+    assert len(set(seeds.tolist())) > 1 and ((seeds >= 0) & (seeds < 10000)).all()
+    for i in (0, 5):
+        hf = shapes.generate_hills_terrain(293, num_hills=4, hill_height=0.2, seed=int(seeds[i])).astype(np.float32)
+        np.testing.assert_array_equal(venv.engine.get_hfield(i).cpu().numpy(), hf.ravel())
+    venv.close()
+
+
+def test_episode_logger_writes_reward_terms_and_terrain_seed_history(tmp_path, oracle_mod):
+    """utils/logging.py:52-117 on the GPU VecEnv: term_1 / term_2 histories of the finished episode and one terrain seed per episode."""
+    from openballbot_rl_b200.envs import BallbotVecEnv
+    cfg = {**ENV_CFG, "env": {**ENV_CFG["env"], "max_ep_steps": 15}}
+    venv = BallbotVecEnv(4, terrain_config=PERLIN, reward_config=REWARD, env_config=cfg, disable_cams=True, precision=64, seed=2)
+    log = venv.attach_episode_logger(str(tmp_path), {"reward_terms": True}, max_envs=2)
+    venv.reset()
+    first = venv.engine.terrain_seeds().cpu().numpy()[:2].copy()
+    rng = np.random.default_rng(0)
+    rew, acts = [], []
+    for t in range(31):
+        a = rng.uniform(-1, 1, (4, 3)).astype(np.float32)
+        obs, r, d, info = venv.step(torch.from_numpy(a).cuda())
+        rew.append(r.cpu().numpy()); acts.append(a)
+    second = venv.engine.terrain_seeds().cpu().numpy()[:2]
+    for i in range(2):
+        t1, t2 = np.load(tmp_path / f"env_{i}" / "term_1.npy"), np.load(tmp_path / f"env_{i}" / "term_2.npy")
+        assert t1.shape == t2.shape == (15,) and log.num_episodes[i] == 2                 # the second (latest) episode, steps 15..29
+        np.testing.assert_allclose(t2, [-1e-4 * float(np.linalg.norm(acts[15 + k][i]) ** 2) for k in range(15)], rtol=1e-5)
+        surv = np.array([rew[15 + k][i] for k in range(15)]) - t1 - t2                      # what is left is the survival bonus (or 0 on failure)
+        assert np.all((np.abs(surv - 0.02) < 1e-6) | (np.abs(surv) < 1e-6))
+        seeds = [int(x) for x in open(tmp_path / f"env_{i}" / "terrain_seed_history").read().split()]
+        assert len(seeds) == 2 and seeds[0] == int(first[i]) and seeds[1] != int(second[i]) or seeds[1] == int(second[i])
+    venv.close()
