@@ -36,7 +36,7 @@ class Config(C.Structure):
         ("reward_type", C.c_int32), ("reward_scale", C.c_float), ("action_reg_coef", C.c_float),
         ("survival_bonus", C.c_float), ("target_direction", C.c_float * 2), ("goal_position", C.c_float * 2),
         ("distance_scale", C.c_float), ("seed", C.c_uint64), ("auto_reset", C.c_int32), ("step_kernel", C.c_int32), ("solver_mode", C.c_int32),
-        ("perlin_table", C.c_int32), ("seed_stream", C.c_int32),
+        ("perlin_table", C.c_int32), ("seed_stream", C.c_int32), ("depth_kernel", C.c_int32),
     ]
 
 

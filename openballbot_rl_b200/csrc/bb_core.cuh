@@ -26,7 +26,7 @@
 #endif
 
 #if defined(BB_STATS) && !defined(__CUDA_ARCH__)
-static long bb_stats_ls_evals = 0;   // host-only instrumentation for scripts/exp (never defined in the product build)
+static long bb_stats_ls_evals = 0, bb_stats_newton = 0;   // host-only instrumentation for scripts/exp (never defined in the product build)
 #endif
 
 namespace bb {
@@ -746,7 +746,8 @@ template <typename T> struct Newton {
   const ModelConst<T>& mc; const Geo<T>& g; Scratch<T>& s;
   T qG0, qG1, qG2;   // Gauss quadratic along the search direction
   T cost, gauss;
-  BB_HDN Newton(const ModelConst<T>& m, const Geo<T>& gg, Scratch<T>& ss) : mc(m), g(gg), s(ss) {}
+  bool fast;         // solver_mode 1: lineSearchFast instead of the reference's exact search (same minimiser, fewer evaluations)
+  BB_HDN Newton(const ModelConst<T>& m, const Geo<T>& gg, Scratch<T>& ss, bool f = false) : mc(m), g(gg), s(ss), fast(f) {}
 
   // total cost at arbitrary qacc (warm-start test); uses s.Mv / s.cJv as temporaries
   BB_HD T costAt(const T* qa) {
@@ -827,6 +828,58 @@ template <typename T> struct Newton {
     if (flag) pnext = eval(p.alpha - p.d1 / p.d2);
     return flag;
   }
+  // solver_mode 1.  The search direction is the exact Newton direction, so phi(0) = cost, phi'(0) = grad . search and
+  // phi''(0) = -phi'(0) are known without an evaluation and the first 1-D Newton point is alpha = 1.  The search is a
+  // safeguarded 1-D Newton iteration on phi' inside a bracket [lo, hi] that stops at the strong Wolfe conditions
+  // (c1 = 1e-4, c2 = 0.1) instead of the reference's |phi'| < tolerance * ls_tolerance * |search| / scale.  phi' jumps at
+  // the apex of a friction cone (T = 0): for the omniwheel pairs (friction 1 : 0.001) the tangential residual is almost
+  // one-dimensional, every search line passes within ~1e-6 of an apex and the minimiser very often sits on it.  The apex
+  // of wheel pair c is at alpha_c = -UV_c / VV_c (minimum of T^2 along the line), so a Newton step that would jump across
+  // it lands on it first; from there the iteration converges inside the apex's narrow smooth valley.  (The reference's
+  // search reaches the same point by bisection: ~20 evaluations.)
+  BB_HD T lineSearchFast(T gtol) {
+    T d0 = 0; for (int i = 0; i < NV; i++) d0 += s.grad[i] * s.search[i];
+    const T c0 = cost, wtol = bmax((T)0.1 * babs(d0), gtol);
+    T kink[3]; int nk = -1; unsigned kused = 0;
+    T lo = 0, hi = -1, a = 1, wprev = (T)1e30, bestA = 0, bestC = c0; bool have = false;
+    for (int k = 0; k < 30; k++) {
+      const LsPt<T> p = eval(a);
+      const bool armijo = p.cost <= c0 + (T)1e-4 * a * d0;
+      if (armijo && (!have || p.cost < bestC)) { bestA = a; bestC = p.cost; have = true; }
+      if (armijo && babs(p.d1) <= wtol) return a;
+      if (!armijo || p.d1 > 0) hi = a; else lo = a;
+      T an = a - p.d1 / p.d2;
+      if (hi < 0) { if (!(an > a * (T)1.1)) an = a * (T)1.1; if (an > a * 4) an = a * 4; }
+      else {
+        const T w = hi - lo, mid = (T)0.5 * (lo + hi);
+        if (w < (T)1e-12 * hi) break;
+        // bisect when the cost rose although phi' < 0 (a cone switched), when the step leaves the bracket, or when two
+        // evaluations did not halve the bracket
+        if ((!armijo && p.d1 < 0) || !(an > lo && an < hi) || (k >= 2 && (k & 1) == 0 && w > (T)0.5 * wprev)) an = mid;
+        if ((k & 1) == 0) wprev = w;
+      }
+      if (nk < 0) {   // apex positions of the anisotropic (wheel) pairs, computed when the unit step was not accepted
+        nk = 0;
+        for (int c = 0; c < s.nc && nk < 3; c++) {
+          const int kf = ctFric(s.ctype[c]); if (kf != 0) continue;
+          const T f1 = mc.f1[kf], f2 = mc.f2[kf];
+          const T u1 = s.cJar[c][1] * f1, u2 = s.cJar[c][2] * f2, v1 = s.cJv[c][1] * f1, v2 = s.cJv[c][2] * f2;
+          const T UV = u1 * v1 + u2 * v2, VV = v1 * v1 + v2 * v2;
+          kink[nk++] = VV > (T)1e-30 ? -UV / VV : (T)-1;
+        }
+      }
+      int kb = -1;
+      for (int i = 0; i < nk; i++) {
+        const T kk = kink[i];
+        if ((kused >> i) & 1u || !(kk > 0)) continue;
+        const bool between = an > a ? (kk > a && kk < an) : (kk < a && kk > an);
+        if (between && (kb < 0 || babs(kk - a) < babs(kink[kb] - a))) kb = i;
+      }
+      if (kb >= 0) { an = kink[kb]; kused |= 1u << kb; }
+      a = an;
+    }
+    return have ? bestA : (T)0;
+  }
   BB_HD T lineSearch(T scale) {
     T sn = 0; for (int i = 0; i < NV; i++) sn += s.search[i] * s.search[i];
     sn = bsqrt(sn);
@@ -837,6 +890,7 @@ template <typename T> struct Newton {
     for (int c = 0; c < s.nc; c++) contactVel(g, s, c, vc, s.cJv[c]);
     qG0 = gauss; qG1 = 0; qG2 = 0;
     for (int i = 0; i < NV; i++) { qG1 += s.search[i] * (s.Ma[i] - s.qfs[i]); qG2 += (T)0.5 * s.search[i] * s.Mv[i]; }
+    if (fast) return lineSearchFast(gtol);
     int it = 0;
     const LsPt<T> p0 = eval((T)0);
     LsPt<T> p1 = eval(p0.alpha - p0.d1 / p0.d2), p2 = p0, pmid, p1n, p2n;
@@ -886,6 +940,9 @@ template <typename T> struct Newton {
       for (int c = 0; c < s.nc; c++) { s.cJar[c][0] += alpha * s.cJv[c][0]; s.cJar[c][1] += alpha * s.cJv[c][1]; s.cJar[c][2] += alpha * s.cJv[c][2]; }
       const T old = cost;
       update(qacc);
+#if defined(BB_STATS) && !defined(__CUDA_ARCH__)
+      bb_stats_newton++;
+#endif
       T gn = 0; for (int i = 0; i < NV; i++) gn += s.grad[i] * s.grad[i];
       iter++;
       if (scale * (old - cost) < mc.tolerance || scale * bsqrt(gn) < mc.tolerance) break;
@@ -898,7 +955,7 @@ template <typename T> struct Newton {
 // ---------------------------------------------------------------------------------------------- one mj_forward
 template <typename T>
 BB_NOINL void forwardDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, const T* ctrl, const T* warm, const float* hf, T zscale,
-                           Scratch<T>& s, T* qacc, KinOut<T>* kin) {
+                           Scratch<T>& s, T* qacc, KinOut<T>* kin, bool fast = false) {
   Geo<T> g; V3<T> capC[3], capU[3];
   smoothDynamics(mc, qpos, qvel, ctrl, s.M, s.qfs, g, capC, capU, kin);
   // qacc_smooth = M^-1 qfrc_smooth
@@ -929,7 +986,7 @@ BB_NOINL void forwardDynamics(const ModelConst<T>& mc, T* qpos, const T* qvel, c
       s.cAref[c][1] = -mc.B * vel[1];
       s.cAref[c][2] = -mc.B * vel[2];
     }
-    Newton<T> nw(mc, g, s);
+    Newton<T> nw(mc, g, s, fast);
     niter = nw.run(warm, qacc);
   }
   if (kin) { kin->ncon = s.nc; kin->niter = niter; }
@@ -959,17 +1016,20 @@ template <typename T> BB_HD void integratePos(T* qpos, const T* v, T h) {
 // kinematics of the LAST stage evaluation (what the reference env reads stale after mj_step).
 template <typename T>
 BB_HD void rk4Step(const ModelConst<T>& mc, T* qpos, T* qvel, T* warm, const T* ctrl, const float* hf, T zscale, Scratch<T>& s,
-                   KinOut<T>* kin, T* qlast = nullptr) {
+                   KinOut<T>* kin, T* qlast = nullptr, bool fast = false) {
   const T h = mc.timestep;
   // stage state (xq, xv), saved initial state (q0, v0), RK4-weighted sums of stage velocities / accelerations
-  T q0[NQ], v0[NV], xq[NQ], xv[NV], sumv[NV], suma[NV], acc[NV];
+  T q0[NQ], v0[NV], xq[NQ], xv[NV], sumv[NV], suma[NV], acc[NV], wchain[NV];
   normalizeQuats(qpos);   // mj_kinematics normalises qpos in place during the first forward pass
   for (int i = 0; i < NQ; i++) { q0[i] = qpos[i]; xq[i] = qpos[i]; }
   for (int i = 0; i < NV; i++) { v0[i] = qvel[i]; xv[i] = qvel[i]; sumv[i] = (T)0; suma[i] = (T)0; acc[i] = (T)0; }
   int ncmax = 0, nit = 0;
 #pragma unroll 1
   for (int st = 0; st < 4; st++) {
-    forwardDynamics(mc, xq, xv, ctrl, warm, hf, zscale, s, acc, kin);
+    // solver_mode 1 chains the warm start through the stages (acc = the previous stage's solution); the reference restarts
+    // every stage from qacc_warmstart of the previous step
+    forwardDynamics(mc, xq, xv, ctrl, (fast && st > 0) ? (const T*)wchain : (const T*)warm, hf, zscale, s, acc, kin, fast);
+    if (fast) { for (int i = 0; i < NV; i++) wchain[i] = acc[i]; }
     if (kin) { ncmax = kin->ncon > ncmax ? kin->ncon : ncmax; nit += kin->niter; }
     const T bw = (st == 0 || st == 3) ? (T)(1.0 / 6.0) : (T)(1.0 / 3.0);       // RK4_B
     for (int i = 0; i < NV; i++) { sumv[i] += bw * xv[i]; suma[i] += bw * acc[i]; }

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(64) k_step(EnvParams p, DevState d, const floa
   if (!bad) {
     Scratch<T> s;
     const float* hf = hfOf(p, d, i);
-    rk4Step(cmc<T>(), qpos, qvel, warm, ctrl, hf, (T)p.zscale, s, &kin, qlast);
+    rk4Step(cmc<T>(), qpos, qvel, warm, ctrl, hf, (T)p.zscale, s, &kin, qlast, p.solver_mode != 0);
     for (int k = 0; k < NQ; k++) bad |= !(babs(qpos[k]) < (T)1e10);
     for (int k = 0; k < NV; k++) bad |= !(babs(qvel[k]) < (T)1e10);
     status = kin.ncon << 8;
@@ -466,7 +466,7 @@ k_stage(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io, in
 // k_newton<T>: constraint solve of one RK stage for the envs that have contacts, in work-sorted order.  Uniform-warp
 // solver (GNewton<T, true>): a warp leaves only when neither of its envs has contacts; otherwise both groups run the solver
 // loops together and every collective uses the constant full-warp mask.
-template <typename T>
+template <typename T, int FM>
 __global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCKS32 : BB_WARP_MINBLOCKS) k_newton(EnvParams p, DevState d, int stage) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const bbg::Ln L = bbg::makeLn();
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCK
   __syncwarp();
   T* gs = (T*)d.gscr + (size_t)i * bbg::GSCR;
   bbg::Ln LU = L; LU.mask = 0xffffffffu;               // compile-time constant member mask for everything inlined below
-  bbg::GNewton<T, true> nwt(cmc<T>(), S, gs, LU, ncon, nw, nd, p.solver_mode != 0, qfs, qas);
+  bbg::GNewton<T, true, FM> nwt(cmc<T>(), S, gs, LU, ncon, nw, nd, FM == 1, qfs, qas);
   int niter;
   const T qacc = nwt.run(warm, niter, act);
   if (!act) return;
@@ -939,6 +939,158 @@ __global__ void __launch_bounds__(256) k_depth(EnvParams p, DevState d, const in
   }
 }
 
+
+// ---- rasterising variant of the depth observation (default for images of up to 64 x 64 pixels).
+// The reference renders with OpenGL, i.e. it rasterises; k_depth above casts one ray per pixel and walks the heightfield cell
+// by cell (~14 cells x 2 plane tests per ray).  Here one CTA owns one (env, camera) image with a z-buffer in shared memory:
+//   1. every pixel gets the nearest robot primitive (ball, wheels, tower, sticks) exactly like the ray-caster;
+//   2. the threads sweep the heightfield cells under the view pyramid (clipped at depth 1): a cell's four corners are taken to
+//      camera space, cells outside the pyramid / beyond the clip / behind the camera are culled, the others are scanned over
+//      the bounding box of their projection, each pixel running the SAME ray / plane solve and in-triangle test as hitHfield
+//      for the cell's two triangles; hits go into the z-buffer with atomicMin on the float bits (t > 0 => ordered as uint).
+// A pixel is now tested against the ~2-4 triangles whose projection covers it instead of every cell its ray crosses, and the
+// depth values are bit-identical to the ray-caster's for the winning triangle (same expressions, same epsilons).
+constexpr int RASTER_MAX_PIX = 64 * 64, RASTER_BATCH = 2048;
+template <typename T>
+__global__ void __launch_bounds__(128) k_depth_raster(EnvParams p, DevState d, const int* __restrict__ list, const int* __restrict__ count,
+                                                      int fixed_count, const T* __restrict__ cfgq, int cfg_stride, float* __restrict__ img0, float* __restrict__ img1) {
+  __shared__ Scene sc;
+  __shared__ unsigned zb[RASTER_MAX_PIX];
+  __shared__ int2 s_work[RASTER_BATCH];
+  __shared__ int s_unit, s_nwork;
+  const int tid = threadIdx.x;
+  const int n = count ? *count : fixed_count;
+  const int units = n * 2, npix = p.im_h * p.im_w, W = p.im_w, H = p.im_h;
+  const float aspect = (float)W / (float)H;
+  const float sx = c_mc32.hx, idx = (float)(HN - 1) / (2.f * sx), isz = 1.f / p.zscale;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_unit = atomicAdd(&d.counters[2], 1);
+    __syncthreads();
+    const int u = s_unit;
+    if (u >= units) break;
+    const int k = u >> 1, cam = u & 1;
+    const int env = list ? list[k] : k;
+    if (tid < 9) buildScene(c_mc32, cfgq, cfg_stride, env, sc, tid);
+    __syncthreads();
+    const float* hf = hfOf(p, d, env);
+    float* out = (cam ? img1 : img0) + (size_t)env * npix;
+    const F3 o = sc.cam_o[cam], ax = sc.cam_x[cam], ay = sc.cam_y[cam], az = sc.cam_z[cam];
+    // ---- 1. primitives, one pixel per thread and iteration
+    for (int px = tid; px < npix; px += blockDim.x) {
+      const int r = px / W, c = px - r * W;
+      const float xn = (2.f * (c + 0.5f) / W - 1.f) * aspect, yn = 1.f - 2.f * (r + 0.5f) / H;
+      const F3 dir = ax * xn + ay * yn - az;
+      const float inv_dd = 1.f / fdot(dir, dir);
+      float best = 1.0f;
+#pragma unroll 1
+      for (int g = 0; g < 7; g++) {
+        const Prim& pr = sc.prim[g];
+        const F3 oc = pr.c - o; const float along = fdot(oc, dir) * inv_dd;
+        const F3 perp = oc - dir * along;
+        if (fdot(perp, perp) > sc.brad2[g]) continue;
+        const float t = hitPrim(o, dir, pr); if (t > 1e-4f && t < best) best = t;
+      }
+      zb[px] = __float_as_uint(best);
+    }
+    // ---- 2. heightfield cells under the view pyramid (apex + the four corner rays at depth 1), in grid coordinates
+    float gxlo = (o.x + sx) * idx, gxhi = gxlo, gylo = (o.y + sx) * idx, gyhi = gylo;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const F3 cdir = ax * ((q & 1) ? aspect : -aspect) + ay * ((q & 2) ? 1.f : -1.f) - az;
+      const float gx = (o.x + cdir.x + sx) * idx, gy = (o.y + cdir.y + sx) * idx;
+      gxlo = fminf(gxlo, gx); gxhi = fmaxf(gxhi, gx); gylo = fminf(gylo, gy); gyhi = fmaxf(gyhi, gy);
+    }
+    const int cx0 = max(0, (int)floorf(gxlo)), cx1 = min(HN - 2, (int)floorf(gxhi)), cy0 = max(0, (int)floorf(gylo)), cy1 = min(HN - 2, (int)floorf(gyhi));
+    const int ncx = cx1 - cx0 + 1, ncy = cy1 - cy0 + 1, ncell = ncx > 0 && ncy > 0 ? ncx * ncy : 0;
+    __syncthreads();
+    const float gx0 = (o.x + sx) * idx, gy0 = (o.y + sx) * idx, oz = o.z * isz;
+    const float dxw = 1.f / idx, e = 1e-5f;
+    // Two phases per batch of cells, so that a few large projections do not serialise a warp: (A) one thread per cell culls and
+    // computes the pixel bounding box, survivors go to a shared work list; (B) 8-lane groups take cells from the list and sweep
+    // the box's pixels in parallel.
+    for (int base = 0; base < ncell; base += RASTER_BATCH) {
+      if (tid == 0) s_nwork = 0;
+      __syncthreads();
+      const int lim = min(ncell, base + RASTER_BATCH);
+      for (int cell = base + tid; cell < lim; cell += blockDim.x) {
+        const int cy = cy0 + cell / ncx, cx = cx0 + cell % ncx;
+        const float* h = hf + cy * HN + cx;
+        const float h00 = h[0], h10 = h[1], h01 = h[HN], h11 = h[HN + 1];
+        float xc[4], yc[4], dp[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const F3 v = f3((float)(cx + (q & 1)) * dxw - sx - o.x, (float)(cy + (q >> 1)) * dxw - sx - o.y, (q == 0 ? h00 : (q == 1 ? h10 : (q == 2 ? h01 : h11))) * p.zscale - o.z);
+          xc[q] = fdot(v, ax); yc[q] = fdot(v, ay); dp[q] = -fdot(v, az);
+        }
+        const float dmin = fminf(fminf(dp[0], dp[1]), fminf(dp[2], dp[3])), dmax = fmaxf(fmaxf(dp[0], dp[1]), fmaxf(dp[2], dp[3]));
+        if (dmax <= 1e-3f || dmin >= 1.0f) continue;                     // behind the near plane or beyond the clip (depth is linear on a triangle)
+        const float NEAR = 1e-3f;
+        float xlo = 3e38f, xhi = -3e38f, ylo = 3e38f, yhi = -3e38f;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {                                    // quad order 0-1-3-2; edges crossing the near plane add their crossing point
+          const int qa = q == 0 ? 0 : (q == 1 ? 1 : (q == 2 ? 3 : 2)), qb = q == 0 ? 1 : (q == 1 ? 3 : (q == 2 ? 2 : 0));
+          if (dp[qa] >= NEAR) {
+            const float id = __fdividef(1.f, dp[qa]), xq = xc[qa] * id, yq = yc[qa] * id;
+            xlo = fminf(xlo, xq); xhi = fmaxf(xhi, xq); ylo = fminf(ylo, yq); yhi = fmaxf(yhi, yq);
+          }
+          if ((dp[qa] >= NEAR) != (dp[qb] >= NEAR)) {
+            const float w = (NEAR - dp[qa]) / (dp[qb] - dp[qa]);
+            const float xq = (xc[qa] + w * (xc[qb] - xc[qa])) * (1.f / NEAR), yq = (yc[qa] + w * (yc[qb] - yc[qa])) * (1.f / NEAR);
+            xlo = fminf(xlo, xq); xhi = fmaxf(xhi, xq); ylo = fminf(ylo, yq); yhi = fmaxf(yhi, yq);
+          }
+        }
+        if (xlo > aspect || xhi < -aspect || ylo > 1.f || yhi < -1.f) continue;     // outside the view pyramid
+        xlo = fmaxf(xlo, -aspect); xhi = fminf(xhi, aspect); ylo = fmaxf(ylo, -1.f); yhi = fminf(yhi, 1.f);
+        // pixel centre (c + 0.5) <-> xn = (2 (c + 0.5) / W - 1) aspect; the in-triangle epsilon (1e-5 cells) is far below a pixel
+        const int c0 = max(0, (int)ceilf((xlo / aspect + 1.f) * 0.5f * W - 0.5f - 0.01f)), c1 = min(W - 1, (int)floorf((xhi / aspect + 1.f) * 0.5f * W - 0.5f + 0.01f));
+        const int r0 = max(0, (int)ceilf((1.f - yhi) * 0.5f * H - 0.5f - 0.01f)), r1 = min(H - 1, (int)floorf((1.f - ylo) * 0.5f * H - 0.5f + 0.01f));
+        if (c1 < c0 || r1 < r0) continue;                                // no pixel centre inside the box
+        const int slot = atomicAdd(&s_nwork, 1);
+        s_work[slot] = make_int2(cell, c0 | (c1 << 8) | (r0 << 16) | (r1 << 24));
+      }
+      __syncthreads();
+      const int nwork = s_nwork;
+      for (int wk = tid >> 3; wk < nwork; wk += blockDim.x >> 3) {
+        const int2 it = s_work[wk];
+        const int cy = cy0 + it.x / ncx, cx = cx0 + it.x % ncx;
+        const int c0 = it.y & 255, c1 = (it.y >> 8) & 255, r0 = (it.y >> 16) & 255, r1 = (it.y >> 24) & 255;
+        const float* h = hf + cy * HN + cx;
+        const float h00 = h[0], h10 = h[1], h01 = h[HN], h11 = h[HN + 1];
+        const float a1 = h10 - h00, b1 = h11 - h10, a2 = h11 - h01, b2 = h01 - h00;
+        const float u0 = gx0 - (float)cx, v0 = gy0 - (float)cy, cc0 = h00 - oz;
+        const float n1 = cc0 + a1 * u0 + b1 * v0, n2 = cc0 + a2 * u0 + b2 * v0;
+        const int bw = c1 - c0 + 1, npx = bw * (r1 - r0 + 1);
+        for (int q = tid & 7; q < npx; q += 8) {
+          const int r = r0 + q / bw, c = c0 + q % bw;
+          const float yn = 1.f - 2.f * (r + 0.5f) / H, xn = (2.f * (c + 0.5f) / W - 1.f) * aspect;
+          const F3 dir = ax * xn + ay * yn - az;
+          const float dgx = dir.x * idx, dgy = dir.y * idx, dz = dir.z * isz;
+          float best = -1.f;
+          {
+            const float den = dz - a1 * dgx - b1 * dgy;
+            if (fabsf(den) > 1e-18f) {
+              const float t = __fdividef(n1, den), uu = u0 + t * dgx, vv = v0 + t * dgy;
+              if (t > 0.f && vv >= -e && uu <= 1.f + e && uu >= vv - e) best = t;
+            }
+          }
+          {
+            const float den = dz - a2 * dgx - b2 * dgy;
+            if (fabsf(den) > 1e-18f) {
+              const float t = __fdividef(n2, den), uu = u0 + t * dgx, vv = v0 + t * dgy;
+              if (t > 0.f && uu >= -e && vv <= 1.f + e && vv >= uu - e && (best < 0.f || t < best)) best = t;
+            }
+          }
+          if (best > 1e-4f && best < 1.0f) atomicMin(&zb[r * W + c], __float_as_uint(best));
+        }
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    for (int px = tid; px < npix; px += blockDim.x) out[px] = __uint_as_float(zb[px]);
+  }
+}
+
 // --------------------------------------------------------------------------------------------- misc kernels
 template <typename T> __global__ void k_set_state(int N, T* st, const double* qpos, const double* qvel, const double* warm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= N) return;
@@ -1007,7 +1159,7 @@ template <typename T> __global__ void k_probe(EnvParams p, DevState d, int env, 
   for (int k = 0; k < 3; k++) ctrl[k] = (T)ctrl3[k];
   Scratch<T> s; KinOut<T> kin;
   const float* hf = hfOf(p, d, env);
-  forwardDynamics(cmc<T>(), qpos, qvel, ctrl, warm, hf, (T)p.zscale, s, qacc, &kin);
+  forwardDynamics(cmc<T>(), qpos, qvel, ctrl, warm, hf, (T)p.zscale, s, qacc, &kin, p.solver_mode != 0);
   for (int k = 0; k < NV; k++) { out[k] = (double)qacc[k]; out[15 + k] = (double)s.qas[k]; out[30 + k] = (double)s.qfs[k]; }
   out[45] = kin.ncon; out[46] = kin.niter; out[47] = (double)cmc<T>().timestep; out[48] = cmc<T>().iterations; out[49] = cmc<T>().ls_iterations;
   out[50] = (double)cmc<T>().meaninertia; out[51] = (double)cmc<T>().K; out[52] = (double)cmc<T>().B; out[53] = (double)cmc<T>().dA[3];
@@ -1043,6 +1195,7 @@ struct bb_engine {
   DevState d;
   int N;
   int table_n;                     // fields in the Perlin table (HF_TABLE)
+  int raster;                      // depth observation: 1 = k_depth_raster (images of <= 64 x 64 pixels), 0 = k_depth ray-caster
   double* probe_out;               // scratch of bb_get_contacts
   size_t tsize;
   int64_t launches;
@@ -1106,7 +1259,11 @@ static int launchResetAndRender(bb_engine* e, const bb_io* io, cudaStream_t s, b
   if (ev) cudaEventRecord(ev[3], s);
   if (e->cfg.cameras) {
     const int grid = depthGrid(N);
-    if (e->cfg.precision == 64) k_depth<double><<<grid, 256, 0, s>>>(e->p, e->d, e->d.refresh_list, e->d.counters + 1, 0, (const double*)e->d.camq, CST, io->rgbd_0, io->rgbd_1);
+    if (e->raster) {
+      const int rgrid = N * 2 < 148 * 8 ? N * 2 : 148 * 8;
+      if (e->cfg.precision == 64) k_depth_raster<double><<<rgrid, 128, 0, s>>>(e->p, e->d, e->d.refresh_list, e->d.counters + 1, 0, (const double*)e->d.camq, CST, io->rgbd_0, io->rgbd_1);
+      else k_depth_raster<float><<<rgrid, 128, 0, s>>>(e->p, e->d, e->d.refresh_list, e->d.counters + 1, 0, (const float*)e->d.camq, CST, io->rgbd_0, io->rgbd_1);
+    } else if (e->cfg.precision == 64) k_depth<double><<<grid, 256, 0, s>>>(e->p, e->d, e->d.refresh_list, e->d.counters + 1, 0, (const double*)e->d.camq, CST, io->rgbd_0, io->rgbd_1);
     else k_depth<float><<<grid, 256, 0, s>>>(e->p, e->d, e->d.refresh_list, e->d.counters + 1, 0, (const float*)e->d.camq, CST, io->rgbd_0, io->rgbd_1);
     e->launches++;
   }
@@ -1125,7 +1282,7 @@ void bb_default_config(bb_config* c) {
   c->max_ep_steps = 4000; c->max_allowed_tilt = 20.f; c->max_wheel_velocity = 10.f;
   c->reward_type = BB_REWARD_DIRECTIONAL; c->reward_scale = 0.01f; c->action_reg_coef = -0.0001f; c->survival_bonus = 0.02f;
   c->target_direction[0] = 0.f; c->target_direction[1] = 1.f; c->goal_position[0] = 0.f; c->goal_position[1] = 0.f; c->distance_scale = 1.f;
-  c->seed = 0; c->auto_reset = 1; c->step_kernel = 0; c->solver_mode = 0; c->perlin_table = -1; c->seed_stream = 0;
+  c->seed = 0; c->auto_reset = 1; c->step_kernel = 0; c->solver_mode = 0; c->perlin_table = -1; c->seed_stream = 0; c->depth_kernel = 1;
 }
 
 const char* bb_last_error(const bb_engine* e) { return e ? e->err : g_create_error; }
@@ -1200,6 +1357,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   }
   p.pscale = cfg->perlin_scale; p.ppers = cfg->perlin_persistence; p.plac = cfg->perlin_lacunarity; p.pamp = cfg->perlin_amplitude; p.poct = cfg->perlin_octaves;
   e->tsize = cfg->precision == 64 ? 8 : 4;
+  e->raster = cfg->depth_kernel != 1 && cfg->im_h * cfg->im_w <= RASTER_MAX_PIX;
   DevState& d = e->d;
   BB_CUDA_C(cudaMalloc(&d.st, e->tsize * SST * N));
   BB_CUDA_C(cudaMalloc(&d.camq, e->tsize * CST * N));
@@ -1220,8 +1378,10 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
     const int sepb = BB_WPB_STAGE * bbg::EPW;
     BB_CUDA_C(cudaFuncSetAttribute(k_stage<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sepb * sizeof(bbg::GS<double>))));
     BB_CUDA_C(cudaFuncSetAttribute(k_stage<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sepb * sizeof(bbg::GS<float>))));
-    BB_CUDA_C(cudaFuncSetAttribute(k_newton<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm64));
-    BB_CUDA_C(cudaFuncSetAttribute(k_newton<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm32));
+    BB_CUDA_C(cudaFuncSetAttribute(k_newton<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm64));
+    BB_CUDA_C(cudaFuncSetAttribute(k_newton<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm32));
+    BB_CUDA_C(cudaFuncSetAttribute(k_newton<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm64));
+    BB_CUDA_C(cudaFuncSetAttribute(k_newton<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm32));
   }
   k_init_order<<<blocksFor(N > 2 * WORK_BINS ? N : 2 * WORK_BINS, 256), 256>>>(N, d);
   BB_CUDA_C(cudaMalloc(&d.reset_list, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.refresh_list, sizeof(int) * N));
@@ -1332,8 +1492,9 @@ int bb_step(bb_engine* e, const float* actions_dev, const bb_io* io, void* strea
         if (e->cfg.precision == 64) k_stage<double><<<sgrid, BB_WPB_STAGE * 32, sepb * sizeof(bbg::GS<double>), s>>>(e->p, e->d, actions_dev, *io, stage);
         else k_stage<float><<<sgrid, BB_WPB_STAGE * 32, sepb * sizeof(bbg::GS<float>), s>>>(e->p, e->d, actions_dev, *io, stage);
         if (stage == 4) break;
-        if (e->cfg.precision == 64) k_newton<double><<<grid, bt, sm64, s>>>(e->p, e->d, stage);
-        else k_newton<float><<<grid, bt, sm32, s>>>(e->p, e->d, stage);
+        const bool fs = e->cfg.solver_mode != 0;
+        if (e->cfg.precision == 64) { if (fs) k_newton<double, 1><<<grid, bt, sm64, s>>>(e->p, e->d, stage); else k_newton<double, 0><<<grid, bt, sm64, s>>>(e->p, e->d, stage); }
+        else { if (fs) k_newton<float, 1><<<grid, bt, sm32, s>>>(e->p, e->d, stage); else k_newton<float, 0><<<grid, bt, sm32, s>>>(e->p, e->d, stage); }
       }
       e->launches += 8;
     }
@@ -1426,7 +1587,11 @@ int bb_render_depth(bb_engine* e, float* img0, float* img1, void* stream) {
   const int N = e->N; cudaStream_t s = (cudaStream_t)stream;
   const int grid = depthGrid(N);
   BB_CUDA(cudaMemsetAsync(e->d.counters + 2, 0, sizeof(int), s));   // work-unit cursor of k_depth
-  if (e->cfg.precision == 64) k_depth<double><<<grid, 256, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const double*)e->d.st, SST, img0, img1);
+  if (e->raster) {
+    const int rgrid = N * 2 < 148 * 8 ? N * 2 : 148 * 8;
+    if (e->cfg.precision == 64) k_depth_raster<double><<<rgrid, 128, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const double*)e->d.st, SST, img0, img1);
+    else k_depth_raster<float><<<rgrid, 128, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const float*)e->d.st, SST, img0, img1);
+  } else if (e->cfg.precision == 64) k_depth<double><<<grid, 256, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const double*)e->d.st, SST, img0, img1);
   else k_depth<float><<<grid, 256, 0, s>>>(e->p, e->d, nullptr, nullptr, N, (const float*)e->d.st, SST, img0, img1);
   e->launches++;
   BB_CUDA(cudaGetLastError());

@@ -428,9 +428,11 @@ __device__ __forceinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, con
 // warp and L.mask can be the compile-time constant 0xffffffff (set by the caller; everything below is inlined).  That
 // removes the convergence pre-check (MATCH / REDUX / VOTE / branch) ptxas emits in front of every shuffle group with a
 // run-time member mask: ~5 % of the solver's instructions and ~12 % of its stall samples.
-template <typename T, bool U = false> struct GNewton {
+template <typename T, bool U = false, int FM = -1> struct GNewton {
   const ModelConst<T>& mc; GS<T>& S; T* gs; const Ln L; const int ncon, nw, nd;   // nw wheel pairs <= nd dense contacts <= ncon
-  const bool fast;   // fast solver mode: inexact line search (stop when |phi'| <= 1e-3 |phi'(0)|), same minimiser of the outer problem
+  const bool fast;   // solver_mode 1: strong-Wolfe line search with cone-apex candidates (searchFast), same minimiser of the outer problem
+                     // FM: -1 = `fast` decides at run time (fused / probe kernels), 0 / 1 = compile-time choice (k_newton)
+  __device__ __forceinline__ bool isFast() const { return FM < 0 ? fast : FM == 1; }
   T qfs, qas;        // dof-lane registers
   T qacc, Ma, grad, search, Mv;
   T cost, gauss, gnorm2;
@@ -480,6 +482,70 @@ template <typename T, bool U = false> struct GNewton {
     gauss = r3.a; cost = r3.a + r3.b; gnorm2 = r3.c;
   }
 
+  // solver_mode 1 (restated for one thread in bb_core.cuh, Newton::lineSearchFast).  The search direction is the exact
+  // Newton direction, so phi(0) = cost, phi'(0) = grad . search, phi''(0) = -phi'(0) need no evaluation and the first 1-D
+  // Newton point is alpha = 1.  Safeguarded 1-D Newton iteration on phi' inside a bracket [lo, hi], stopped at the strong
+  // Wolfe conditions (c1 = 1e-4, c2 = 0.1).  phi' jumps at the apex of a friction cone; for the omniwheel pairs (friction
+  // 1 : 0.001) every search line passes within ~1e-6 of an apex and the minimiser very often sits on it: the apex of wheel
+  // pair c is at alpha_c = -UV_c / VV_c, and a step that would jump across it lands on it first (the reference's search
+  // gets there by bisection, ~20 evaluations).  All state is group-uniform; one evaluation call site.
+  __device__ __forceinline__ T searchFast(const LsCtx<T> q, const T gtol, bool on) {
+    const bool dof = L.gl < NV;
+    const T d0 = gsum(dof ? grad * search : (T)0, L.mask);
+    const T c0 = cost, wtol = bmax((T)0.1 * babs(d0), gtol);
+    T lo = 0, hi = -1, a = 1, wprev = (T)1e30, bestA = 0, bestC = c0, result = 0;
+    T kk0 = -1, kk1 = -1, kk2 = -1;
+    bool have = false, kready = false;
+    int k = 0; unsigned kused = 0;
+#pragma unroll 1
+    for (;;) {
+      if (U && !__any_sync(0xffffffffu, on)) break;
+      const LsPt<T> p = lsEval(mc, S, gs, ncon, nw, nd, q, a, 1, L, rec0);
+      if (U && !on) continue;                             // passenger: state frozen
+      nevals++;
+      const bool armijo = p.cost <= c0 + (T)1e-4 * a * d0;
+      if (armijo && (!have || p.cost < bestC)) { bestA = a; bestC = p.cost; have = true; }
+      bool done = false;
+      if (armijo && babs(p.d1) <= wtol) { result = a; done = true; }
+      else {
+        if (!armijo || p.d1 > 0) hi = a; else lo = a;
+        T an = p.nxt;
+        if (hi < 0) { if (!(an > a * (T)1.1)) an = a * (T)1.1; if (an > a * 4) an = a * 4; }
+        else {
+          const T w = hi - lo, mid = (T)0.5 * (lo + hi);
+          if (w < (T)1e-12 * hi) { result = have ? bestA : (T)0; done = true; }
+          if ((!armijo && p.d1 < 0) || !(an > lo && an < hi) || (k >= 2 && (k & 1) == 0 && w > (T)0.5 * wprev)) an = mid;
+          if ((k & 1) == 0) wprev = w;
+        }
+        if (!kready) {                                    // apex positions of the wheel pairs (first rejected point only)
+          kready = true;
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            T kv = -1;
+            if (c < nw) {
+              const T* ls = S.wrec + c * CRW + OSW + O_LS;
+              const T UV = ls[3], VV = ls[4];
+              if (VV > (T)1e-30) kv = -fdivPos(UV, VV);
+            }
+            if (c == 0) kk0 = kv; else if (c == 1) kk1 = kv; else kk2 = kv;
+          }
+        }
+        int kb = -1; T kbest = 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const T kv = c == 0 ? kk0 : (c == 1 ? kk1 : kk2);
+          const bool between = an > a ? (kv > a && kv < an) : (kv < a && kv > an);
+          if (!((kused >> c) & 1u) && kv > 0 && between && (kb < 0 || babs(kv - a) < babs(kbest - a))) { kb = c; kbest = kv; }
+        }
+        if (kb >= 0) { an = kbest; kused |= 1u << kb; }
+        a = an;
+        if (++k >= 30 && !done) { result = have ? bestA : (T)0; done = true; }
+      }
+      if (done) { if (U) { on = false; continue; } else break; }
+    }
+    return result;
+  }
+
   // exact line search of mj_solNewton (PrimalSearch) as a state machine around a single evaluation site.  Evaluated
   // points live in S.lsp (slots of 4 words); the brackets p1 / p2 and their pending Newton points are slot indices, so
   // "p1 = candidate" is an integer move and the whole search needs a handful of registers.
@@ -517,6 +583,7 @@ template <typename T, bool U = false> struct GNewton {
     LsCtx<T> q;
     q.qG0 = gauss; q.qG1 = r3.b; q.qG2 = r3.c;
     __syncwarp(L.mask);
+    if (isFast()) return searchFast(q, gtol, on);
     // states: 0 p0, 1 first Newton point, 2 one-sided Newton iteration, 3 p1next, 4 midpoint, 5 p1 re-bracket, 6 p2 re-bracket
     const T* P = S.lsp;
     int i1 = 0, i2 = 0, i1n = 0, i2n = 0, imid = 0, ic0 = 0;   // slots of p1, p2, p1next, p2next, pmid, candidate 0
@@ -533,7 +600,6 @@ template <typename T, bool U = false> struct GNewton {
       int src = -1;          // slot whose Newton step is evaluated next (-1: `a` has been set explicitly)
       if (st == 0) {
         p0cost = p.cost;
-        if (fast) gtol = bmax(gtol, (T)1e-3 * babs(p.d1));
         a = p.nxt; st = 1;
       } else if (st <= 2) {
         T d = p.d1;

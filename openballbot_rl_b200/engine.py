@@ -31,7 +31,7 @@ class BallbotEngine:
                  max_wheel_velocity=10.0, reward="directional", reward_scale=0.01, action_reg_coef=-0.0001,
                  survival_bonus=0.02, target_direction=(0.0, 1.0), goal_position=(0.0, 0.0), distance_scale=1.0, seed=0,
                  auto_reset=True, env_offset=0, step_kernel="warp", solver="exact", perlin_table=None, seed_stream="counter",
-                 binding="auto"):
+                 binding="auto", depth_kernel="raycast"):
         if not torch.cuda.is_available():
             raise EngineError("BallbotEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
         L = _lib.lib()
@@ -55,6 +55,7 @@ class BallbotEngine:
         cfg.solver_mode = {"exact": 0, "fast": 1}[solver]
         cfg.perlin_table = -1 if perlin_table is None else int(bool(perlin_table))
         cfg.seed_stream = {"counter": 0, "pcg64": 1}[seed_stream]
+        cfg.depth_kernel = {"raster": 0, "raycast": 1}[depth_kernel]
         self.cfg = cfg
         self._L = L
         self._h = C.c_void_p()

@@ -6,6 +6,8 @@
 
 using namespace bb;
 
+static int g_solver_fast = 0;   // hc_set_solver: 0 = reference iteration path, 1 = solver_mode 1 of the engine
+
 template <typename T> static const ModelConst<T>& model() {
   static ModelConst<T> mc; static bool ok = false;
   if (!ok) { ModelConst<double> md; buildModelConst(md); narrowModel(md, mc); ok = true; }
@@ -22,7 +24,7 @@ static int fwd(const double* qpos, const double* qvel, const double* ctrl, const
   for (int i = 0; i < 3; i++) c[i] = (T)ctrl[i];
   KinOut<T> k;
   memset(&s, 0xFF, sizeof(s));   // poison: the GPU kernel's local scratch is uninitialised too
-  forwardDynamics(model<T>(), q, v, c, w, hf, (T)zscale, s, a, &k);
+  forwardDynamics(model<T>(), q, v, c, w, hf, (T)zscale, s, a, &k, g_solver_fast != 0);
   for (int i = 0; i < NV; i++) qacc[i] = a[i];
   if (M225) for (int i = 0; i < NV; i++) for (int j = 0; j < NV; j++) M225[i * NV + j] = s.M[tidx(i, j)];
   if (qfs) for (int i = 0; i < NV; i++) qfs[i] = s.qfs[i];
@@ -45,7 +47,7 @@ static void step(double* qpos, double* qvel, double* warm, const double* ctrl, c
   for (int i = 0; i < 3; i++) c[i] = (T)ctrl[i];
   KinOut<T> k;
   memset(&s, 0xFF, sizeof(s));
-  rk4Step(model<T>(), q, v, w, c, hf, (T)zscale, s, &k);
+  rk4Step(model<T>(), q, v, w, c, hf, (T)zscale, s, &k, (T*)nullptr, g_solver_fast != 0);
   for (int i = 0; i < NQ; i++) qpos[i] = q[i];
   for (int i = 0; i < NV; i++) { qvel[i] = v[i]; warm[i] = w[i]; }
   if (kin) { for (int i = 0; i < 4; i++) kin[i] = k.quatB[i]; for (int i = 0; i < 3; i++) { kin[4 + i] = k.cvel_ang[i]; kin[7 + i] = k.cvel_lin[i]; kin[10 + i] = k.posB[i]; } }
@@ -53,6 +55,7 @@ static void step(double* qpos, double* qvel, double* warm, const double* ctrl, c
 }
 
 extern "C" {
+void hc_set_solver(int fast) { g_solver_fast = fast; }
 int hc_forward(int prec, const double* qpos, const double* qvel, const double* ctrl, const double* warm, const float* hf, double zscale,
                double* qacc, double* M225, double* qfs, double* kin, int* ncon, int* niter, double* cdist, double* cpos, double* cframe, int* ctype) {
   return prec == 32 ? fwd<float>(qpos, qvel, ctrl, warm, hf, zscale, qacc, M225, qfs, kin, ncon, niter, cdist, cpos, cframe, ctype)
@@ -70,4 +73,6 @@ void hc_model(double* dA12, double* meaninertia, double* masses3 /*m0,mw,mL*/, d
 }
 #ifdef BB_STATS
 extern "C" long hc_ls_evals() { return bb_stats_ls_evals; }
+extern "C" long hc_newton_iters() { return bb_stats_newton; }
+extern "C" void hc_stats_reset() { bb_stats_ls_evals = 0; bb_stats_newton = 0; }
 #endif

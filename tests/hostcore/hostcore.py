@@ -58,3 +58,9 @@ def model():
     dA = np.zeros(12); mi = C.c_double(); ms = np.zeros(3); c0 = np.zeros(3)
     lib().hc_model(_p(dA), C.byref(mi), _p(ms), _p(c0))
     return dict(dA=dA, meaninertia=mi.value, masses=ms, c0=c0)
+
+
+def set_solver(fast):
+    """0: reference iteration path (exact line search, every RK stage warm-started from qacc_warmstart); 1: the engine's
+    solver_mode 1 (strong-Wolfe line search with cone-apex candidates, warm start chained through the stages)."""
+    lib().hc_set_solver(int(bool(fast)))

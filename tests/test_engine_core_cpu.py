@@ -154,3 +154,32 @@ def test_extra_collision_pairs_agree(oracle_mod):
         assert np.abs(fh["qacc"] - fo["qacc"]).max() / max(1.0, np.abs(fo["qacc"]).max()) < 1e-8, t
         seen.update(int(x) for x in fh["type"])
     assert {4, 5, 6, 7, 8, 9, 10, 11} <= seen, seen                          # every new pair type occurred
+
+
+@pytest.mark.parametrize("terrain", ["perlin", "flat"])
+def test_solver_mode_1_reaches_the_reference_minimiser(oracle_mod, terrain):
+    """solver_mode 1 (strong-Wolfe line search with cone-apex candidates, analytic p0, warm start chained through the RK
+    stages) against the ORACLE's mj_step on every state of random-action rollouts that include drops, landing impacts and
+    bounces: one step agrees to 1e-6 relative (BASELINE tolerance 1e-5) although the iteration path differs."""
+    rng = np.random.default_rng(11)
+    worst = 0.0
+    o = oracle_mod.OracleEnv()
+    try:
+        for ep in range(3 if terrain == "perlin" else 1):
+            hf = oracle_mod.perlin_terrain(seed=int(rng.integers(0, 10000))) if terrain == "perlin" else np.zeros(293 * 293, np.float32)
+            o.reset(hf)
+            q, v, w, _ = o.get_state()
+            for t in range(400):
+                ctrl = -10.0 * rng.uniform(-1, 1, 3)
+                H.set_solver(1)
+                q1, v1, _, _, nc, _ = H.step(q, v, w, ctrl, hf)
+                o.set_state(q, v, w); o.mj_step(ctrl)
+                qo, vo, wo, _ = o.get_state()
+                worst = max(worst, np.abs(q1 - qo).max() / max(1.0, np.abs(qo).max()), np.abs(v1 - vo).max() / max(1.0, np.abs(vo).max()))
+                q, v, w = qo, vo, wo
+                w_, x_, y_, z_ = q[3:7]
+                if np.degrees(np.arccos(np.clip(1 - 2 * (x_ * x_ + y_ * y_), -1, 1))) > 20:
+                    break
+    finally:
+        H.set_solver(0); o.close()
+    assert worst < 1e-6, worst

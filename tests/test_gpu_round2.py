@@ -301,3 +301,35 @@ def test_cuda_engine_and_cpu_ref_backend_through_one_harness():
     rows_c, rows_r = bc.contacts(0), br.contacts(0)
     assert rows_c.shape == rows_r.shape
     bc.close(); br.close()
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-5), (32, 1e-3)])
+def test_solver_mode_1_single_step_parity_through_perlin_landings(oracle_mod, precision, tol):
+    """solver='fast' (strong-Wolfe line search with cone-apex candidates, analytic p0, warm start chained through the RK
+    stages) on the production lane-group kernels: every step of a drop / landing / bounce sequence on Perlin terrain is
+    re-done by the oracle's exact-line-search mj_step FROM THE ENGINE'S OWN PRE-STEP STATE; qpos / qvel after the step agree
+    to BASELINE's single-step tolerance, with the same contact counts."""
+    N, NO = 64, 8
+    eng = _engine(num_envs=N, precision=precision, terrain="perlin", cameras=False, auto_reset=False, seed=21, solver="fast")
+    eng.reset()
+    oras = []
+    for i in range(NO):
+        o = oracle_mod.OracleEnv(); o.reset(eng.get_hfield(i).cpu().numpy()); oras.append(o)
+    rng = np.random.default_rng(4)
+    worst, ncmax, contact_steps = 0.0, 0, 0
+    for t in range(160):
+        a = rng.uniform(-1, 1, (N, 3)).astype(np.float32)
+        q0, v0, w0 = [x.cpu().numpy().astype(np.float64) for x in eng.get_state()]
+        eng.step(torch.from_numpy(a).cuda())
+        q1, v1, _ = [x.cpu().numpy().astype(np.float64) for x in eng.get_state()]
+        nc = (eng.status.cpu().numpy() >> 8) & 255
+        term = eng.terminated.cpu().numpy().astype(bool)
+        for i, o in enumerate(oras):
+            if term[i] or not np.isfinite(q1[i]).all():
+                continue
+            o.set_state(q0[i], v0[i], w0[i]); o.mj_step(-10.0 * a[i].astype(np.float64))
+            qo, vo, _, _ = o.get_state()
+            worst = max(worst, _rel(q1[i], qo), _rel(v1[i], vo))
+            ncmax = max(ncmax, int(nc[i])); contact_steps += int(nc[i] > 3)
+    assert worst < tol and ncmax >= 8 and contact_steps > 100, (worst, ncmax, contact_steps)
+    eng.close()
