@@ -33,16 +33,19 @@ BYTES_STATE = {64: 874.0, 32: 498.0}       # state + action read, state + obs + 
 BYTES_HF_FOOTPRINT = 400.0                 # ~100 heightfield cells under the robot, once per step
 BYTES_DEPTH_REFRESH = 32768.0 + 13600.0    # 2 images written + unique heightfield read, per camera refresh
 BYTES_TERRAIN = 343396.0                   # one regenerated 293x293 float32 heightfield per reset
-# dram__bytes_read.sum + dram__bytes_write.sum from the committed `ncu --set full` capture
-# (profiles/r01c_ncu_full_perlin32k.txt: perlin, fp64, 32,768 envs), expressed per env / per refreshed env so that it
-# scales to the launch sizes of this run.  "step" = the 9 launches of one step (5 x k_stage + 4 x k_newton): 736.5 MB +
-# 329.0 MB + 37.3 MB.  The excess over the algorithmic bytes is the split-phase context that is parked in HBM between
-# the stage and solver launches on purpose (~6 KB per env and stage written and read back; it buys the instruction-fetch
-# fix described in DESIGN.md and costs ~0.2 ms of HBM time per step), plus register-spill lines of the smooth-dynamics pass.
-NCU_TRAFFIC = {"step": (736.5e6 + 329.0e6 + 37.3e6) / 32768.0, "depth": (104.36e6 + 163.02e6) / (32768.0 / 6.0)}
-# fp64 work of the step kernels (5 x k_stage + 4 x k_newton) from profiles/r02a_ncu_full_perlin32k.txt: thread-level
-# (dfma x 2 + dmul + dadd) x elapsed cycles, summed over the nine launches of one step, per env (perlin, fp64, exact solver)
-NCU_FP64_FLOP_PER_ENV_STEP = 1.4160e10 / 32768.0
+# dram__bytes_read.sum + dram__bytes_write.sum from the committed `ncu --set full` capture of one whole step
+# (profiles/r02b_ncu_full_perlin32k.txt: perlin, fp64, 32,768 envs, solver_mode 1), expressed per env / per refreshed env
+# so that it scales to the launch sizes of this run.  "step" = the 9 launches of one step (5 x k_stage + 4 x k_newton):
+# 1251.1 MB.  The excess over the algorithmic bytes is the split-phase context that is parked in HBM between the stage and
+# solver launches on purpose (~6 KB per env and stage written and read back; it buys the instruction-fetch fix described
+# in DESIGN.md and costs ~0.2 ms of HBM time per step), plus register-spill lines of the smooth-dynamics pass.
+NCU_TRAFFIC = {"step": 1251.07e6 / 32768.0, "depth": 202.05e6 / (32768.0 / 6.0)}
+NCU_TRAFFIC_SOURCE = "profiles/r02b_ncu_full_perlin32k.txt (per-env figure of the 32,768-env capture x this launch's envs)"
+# fp64 work of the step kernels (5 x k_stage + 4 x k_newton): thread-level (dfma x 2 + dmul + dadd) per cycle x elapsed
+# cycles, summed over the nine launches of one step, per env (perlin, fp64).  exact: profiles/r02a_ncu_full_perlin32k.txt,
+# fast: profiles/r02b_ncu_full_perlin32k.txt.
+NCU_FP64_FLOP_PER_ENV_STEP = {"exact": 1.4160e10 / 32768.0, "fast": 1.0970e10 / 32768.0}
+NCU_FP64_FLOP_SOURCE = {"exact": "profiles/r02a_ncu_full_perlin32k.txt", "fast": "profiles/r02b_ncu_full_perlin32k.txt"}
 
 
 def load_peaks():
@@ -235,7 +238,9 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default 65536 perlin / 4096 flat)")
     ap.add_argument("--precision", type=int, default=64, choices=[32, 64])
     ap.add_argument("--preroll", type=int, default=-1, help="untimed steps that desynchronise the episodes (default 300 perlin / 0 flat)")
-    ap.add_argument("--solver", default="exact", choices=["exact", "fast"], help="exact: MuJoCo-faithful iteration path; fast: chained warm start + inexact line search")
+    ap.add_argument("--solver", default="fast", choices=["exact", "fast"],
+                    help="line search / warm start of the Newton solver (same minimiser, same termination rule, same tolerance): fast = strong-Wolfe search with "
+                         "cone-apex candidates + warm start chained through the RK stages (engine solver_mode 1); exact = mj_solNewton's own iteration path")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true", help="experiment: no per-kernel CUDA events inside the timed region")
@@ -252,7 +257,7 @@ def main():
                      if args.workload == "perlin" else "flat terrain, proprioceptive obs only")
     # identical in both arms (the driver compares them); run-specific details go to the line's "run" object
     config = {"workload": f"{workload_name}; {envs} envs/GPU (BASELINE.json configs[{2 if args.workload == 'perlin' else 1}])",
-              "envs_per_gpu": envs, "physics": f"fp{args.precision}", "solver": args.solver, "integrator": "RK4 dt=0.002",
+              "envs_per_gpu": envs, "physics": f"fp{args.precision}", "solver": "Newton, elliptic cones, tolerance 1e-8 (mj_solNewton termination rule)", "integrator": "RK4 dt=0.002",
               "actions": "U(-1,1)^3, fresh draw every step (device RNG on the GPU arm, numpy on the CPU arm)",
               "collision_pairs": "ball x wheels, ball x terrain, wheels / sticks x terrain, ball x sticks / tower",
               "parallelism": f"env-sharded x{args.gpus}, no collective on the step path"}
@@ -404,31 +409,34 @@ def main():
         dom = max(kern, key=lambda k: kern[k])
         achieved = alg[dom] / max(kern[dom] * 1e-3, 1e-12) / 1e9 if prof_steps else None
         compute = None
-        if prof_steps and perlin and args.precision == 64 and args.solver == "exact":
+        if prof_steps and perlin and args.precision == 64:
             from openballbot_rl_b200.engine import fp64_peak_tflops
             pk = fp64_peak_tflops(local_rank)
-            ach = NCU_FP64_FLOP_PER_ENV_STEP * envs / (kern["step"] * 1e-3) / 1e12
+            flop_env = NCU_FP64_FLOP_PER_ENV_STEP[args.solver]
+            ach = flop_env * envs / (kern["step"] * 1e-3) / 1e12
             compute = {"bound": "fp64 pipe", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk if pk else None,
-                       "flop_per_env_step": NCU_FP64_FLOP_PER_ENV_STEP,
-                       "flop_source": "ncu thread-level dfma x 2 + dmul + dadd of the nine step-kernel launches (profiles/r02a_ncu_full_perlin32k.txt), scaled by envs",
+                       "flop_per_env_step": flop_env,
+                       "flop_source": f"ncu thread-level dfma x 2 + dmul + dadd of the nine step-kernel launches ({NCU_FP64_FLOP_SOURCE[args.solver]}), scaled by envs",
                        "peak_source": "bb_fp64_peak: DFMA chains on this GPU, best of 4 (ncu reports 64 DFMA / cycle / SM = 37.2 TFLOP/s at 1965 MHz)"}
         whole = sum(alg.values()) / (ms_max / steps * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": f"f{args.precision}", "data": "synthetic",
                 "config": config,
-                "run": dict(preroll_steps=preroll, phase_stagger_steps=stagger, terrain_storage="table of 10,000 Perlin fields (3.4 GB)" if table else "per-env fields",
+                "run": dict(line_search=("strong Wolfe (c1 1e-4, c2 0.1) with cone-apex candidates, analytic p0, warm start chained through the RK stages (solver_mode 1)"
+                                         if args.solver == "fast" else "exact (mj_solNewton iteration path, solver_mode 0)"),
+                            preroll_steps=preroll, phase_stagger_steps=stagger, terrain_storage="table of 10,000 Perlin fields (3.4 GB)" if table else "per-env fields",
                             l2="working set (state + split-phase context + heightfields + images) exceeds the 126 MB L2; no flush needed",
                             resets_in_timed_region=total_resets, mean_episode_len=(world * envs * steps / total_resets) if total_resets else None),
                 "roofline": {"bound": "hbm", "kernel": "k_stage x5 + k_newton x4 (one step)" if dom == "step" else f"k_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak if achieved is not None else None, "compute": compute,
                              "traffic": (NCU_TRAFFIC[dom] * (envs if dom == "step" else refresh_per_step + resets_per_step_gpu)
                                          if perlin and args.precision == 64 and dom in NCU_TRAFFIC else None),
-                             "traffic_source": "profiles/r01c_ncu_full_perlin32k.txt (per-env figure of the 32,768-env capture x this launch's envs)",
+                             "traffic_source": NCU_TRAFFIC_SOURCE,
                              "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
                              "alg_bytes_per_launch": alg[dom], "kernel_ms_per_launch": kern[dom], "kernel_ms_all": kern, "kernel_ms_source": f"CUDA events around every kernel group, {prof_steps} steps right after the timed region",
                              "whole_step_achieved_gbs": whole, "whole_step_frac": whole / peak,
-                             "note": "not HBM-bound: the step kernels are fp64 dependent-chain code (k_newton: wait 2.7 cycles per issue, IPC 1.25 of 4, fp64 pipe 19 %, DRAM 1 %; k_stage: barrier / instruction-fetch / L2 latency); `compute` relates their fp64 flop count to the measured DFMA peak; the depth ray-cast is instruction-issue bound (IPC 3.3); see profiles/README.md"},
+                             "note": "not HBM-bound: the step kernels are fp64 dependent-chain code (k_newton: wait 2.5 cycles per issue, IPC 1.2 of 4, fp64 pipe 19 %, DRAM 1 %; k_stage: L2 latency / instruction fetch / CTA barriers, IPC 0.9); `compute` relates their fp64 flop count to the measured DFMA peak; the depth ray-cast is instruction-issue bound (IPC 3.3); see profiles/README.md"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "bb_step_host (C ABI, host buffers); depth images stay device-resident for the policy encoder"},
                 "e2e_images": ({"value": e2e_img_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_img, "steps": e2e_img_steps,

@@ -840,11 +840,13 @@ template <typename T> struct Newton {
   BB_HD T lineSearchFast(T gtol) {
     T d0 = 0; for (int i = 0; i < NV; i++) d0 += s.grad[i] * s.search[i];
     const T c0 = cost, wtol = bmax((T)0.1 * babs(d0), gtol);
+    // rounding floor of the working precision: cost differences below it are noise, a bracket cannot shrink below ~1 ulp
+    const T cslack = sizeof(T) == 4 ? (T)4e-7 * babs(c0) : (T)0, wrel = sizeof(T) == 4 ? (T)1e-6 : (T)1e-12;
     T kink[3]; int nk = -1; unsigned kused = 0;
     T lo = 0, hi = -1, a = 1, wprev = (T)1e30, bestA = 0, bestC = c0; bool have = false;
     for (int k = 0; k < 30; k++) {
       const LsPt<T> p = eval(a);
-      const bool armijo = p.cost <= c0 + (T)1e-4 * a * d0;
+      const bool armijo = p.cost <= c0 + (T)1e-4 * a * d0 + cslack;
       if (armijo && (!have || p.cost < bestC)) { bestA = a; bestC = p.cost; have = true; }
       if (armijo && babs(p.d1) <= wtol) return a;
       if (!armijo || p.d1 > 0) hi = a; else lo = a;
@@ -852,7 +854,7 @@ template <typename T> struct Newton {
       if (hi < 0) { if (!(an > a * (T)1.1)) an = a * (T)1.1; if (an > a * 4) an = a * 4; }
       else {
         const T w = hi - lo, mid = (T)0.5 * (lo + hi);
-        if (w < (T)1e-12 * hi) break;
+        if (w < wrel * hi) break;
         // bisect when the cost rose although phi' < 0 (a cone switched), when the step leaves the bracket, or when two
         // evaluations did not halve the bracket
         if ((!armijo && p.d1 < 0) || !(an > lo && an < hi) || (k >= 2 && (k & 1) == 0 && w > (T)0.5 * wprev)) an = mid;
@@ -878,6 +880,7 @@ template <typename T> struct Newton {
       if (kb >= 0) { an = kink[kb]; kused |= 1u << kb; }
       a = an;
     }
+    if (sizeof(T) == 4 && have && c0 - bestC <= (T)1e-5 * babs(c0)) return 0;   // fp32: only noise-level improvement was found: converged
     return have ? bestA : (T)0;
   }
   BB_HD T lineSearch(T scale) {
@@ -946,6 +949,7 @@ template <typename T> struct Newton {
       T gn = 0; for (int i = 0; i < NV; i++) gn += s.grad[i] * s.grad[i];
       iter++;
       if (scale * (old - cost) < mc.tolerance || scale * bsqrt(gn) < mc.tolerance) break;
+      if (sizeof(T) == 4 && old - cost <= (T)5e-7 * babs(old)) break;   // fp32: improvement inside the rounding noise of the cost
       for (int i = 0; i < NV; i++) s.search[i] = -s.Mgrad[i];
     }
     return iter;

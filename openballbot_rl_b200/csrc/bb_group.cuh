@@ -489,10 +489,19 @@ template <typename T, bool U = false, int FM = -1> struct GNewton {
   // 1 : 0.001) every search line passes within ~1e-6 of an apex and the minimiser very often sits on it: the apex of wheel
   // pair c is at alpha_c = -UV_c / VV_c, and a step that would jump across it lands on it first (the reference's search
   // gets there by bisection, ~20 evaluations).  All state is group-uniform; one evaluation call site.
+  // exits of searchFast other than the Wolfe test (bracket collapsed to rounding, evaluation cap): the best Armijo point,
+  // unless (fp32) its improvement is inside the rounding noise of the cost -- then the solve has converged (alpha = 0)
+  __device__ __forceinline__ static T fallbackAlpha(bool have, T bestA, T bestC, T c0) {
+    if (!have) return 0;
+    if (sizeof(T) == 4 && c0 - bestC <= (T)1e-5 * babs(c0)) return 0;
+    return bestA;
+  }
   __device__ __forceinline__ T searchFast(const LsCtx<T> q, const T gtol, bool on) {
     const bool dof = L.gl < NV;
     const T d0 = gsum(dof ? grad * search : (T)0, L.mask);
     const T c0 = cost, wtol = bmax((T)0.1 * babs(d0), gtol);
+    // rounding floor of the working precision: cost differences below it are noise, a bracket cannot shrink below ~1 ulp
+    const T cslack = sizeof(T) == 4 ? (T)4e-7 * babs(c0) : (T)0, wrel = sizeof(T) == 4 ? (T)1e-6 : (T)1e-12;
     T lo = 0, hi = -1, a = 1, wprev = (T)1e30, bestA = 0, bestC = c0, result = 0;
     T kk0 = -1, kk1 = -1, kk2 = -1;
     bool have = false, kready = false;
@@ -503,7 +512,7 @@ template <typename T, bool U = false, int FM = -1> struct GNewton {
       const LsPt<T> p = lsEval(mc, S, gs, ncon, nw, nd, q, a, 1, L, rec0);
       if (U && !on) continue;                             // passenger: state frozen
       nevals++;
-      const bool armijo = p.cost <= c0 + (T)1e-4 * a * d0;
+      const bool armijo = p.cost <= c0 + (T)1e-4 * a * d0 + cslack;
       if (armijo && (!have || p.cost < bestC)) { bestA = a; bestC = p.cost; have = true; }
       bool done = false;
       if (armijo && babs(p.d1) <= wtol) { result = a; done = true; }
@@ -513,7 +522,7 @@ template <typename T, bool U = false, int FM = -1> struct GNewton {
         if (hi < 0) { if (!(an > a * (T)1.1)) an = a * (T)1.1; if (an > a * 4) an = a * 4; }
         else {
           const T w = hi - lo, mid = (T)0.5 * (lo + hi);
-          if (w < (T)1e-12 * hi) { result = have ? bestA : (T)0; done = true; }
+          if (w < wrel * hi) { result = fallbackAlpha(have, bestA, bestC, c0); done = true; }
           if ((!armijo && p.d1 < 0) || !(an > lo && an < hi) || (k >= 2 && (k & 1) == 0 && w > (T)0.5 * wprev)) an = mid;
           if ((k & 1) == 0) wprev = w;
         }
@@ -539,7 +548,7 @@ template <typename T, bool U = false, int FM = -1> struct GNewton {
         }
         if (kb >= 0) { an = kbest; kused |= 1u << kb; }
         a = an;
-        if (++k >= 30 && !done) { result = have ? bestA : (T)0; done = true; }
+        if (++k >= 30 && !done) { result = fallbackAlpha(have, bestA, bestC, c0); done = true; }
       }
       if (done) { if (U) { on = false; continue; } else break; }
     }
@@ -665,6 +674,10 @@ template <typename T, bool U = false, int FM = -1> struct GNewton {
     return result;
   }
 
+  // fp32 only: the reference's stopping rule compares the cost improvement with tolerance / scale ~ 1e-8, far below the
+  // rounding noise of a single-precision cost (~1e-7 |cost|); an improvement inside that noise ends the solve (without this
+  // a few envs per 10^5 ran to the iteration cap and held their whole launch back)
+  __device__ __forceinline__ static bool belowNoise(T old, T now) { return sizeof(T) == 4 && old - now <= (T)5e-7 * babs(old); }
   // in: aref parked in the jv slot of every record, `warm` = qacc_warmstart of this dof lane.  Returns qacc; niter by reference.
   __device__ __forceinline__ T run(T warm, int& niter, bool act = true) {
     const bool dof = L.gl < NV;
@@ -720,7 +733,7 @@ template <typename T, bool U = false, int FM = -1> struct GNewton {
         const T old = cost;
         costGrad();                                       // idempotent for a group that did not step
         if (step) iter++;
-        on = step && iter < mc.iterations && !(scale * (old - cost) < mc.tolerance || scale * bsqrt(gnorm2) < mc.tolerance);
+        on = step && iter < mc.iterations && !(scale * (old - cost) < mc.tolerance || scale * bsqrt(gnorm2) < mc.tolerance || belowNoise(old, cost));
       }
     } else {
 #pragma unroll 1
@@ -737,7 +750,7 @@ template <typename T, bool U = false, int FM = -1> struct GNewton {
       const T old = cost;
       costGrad();
       iter++;
-      if (scale * (old - cost) < mc.tolerance || scale * bsqrt(gnorm2) < mc.tolerance) break;
+      if (scale * (old - cost) < mc.tolerance || scale * bsqrt(gnorm2) < mc.tolerance || belowNoise(old, cost)) break;
     }
     }
     niter = iter;

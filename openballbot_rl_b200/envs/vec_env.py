@@ -57,7 +57,7 @@ class BallbotVecEnv(_VecEnvBase):
 
     def __init__(self, num_envs: int, terrain_config: Optional[dict] = None, reward_config: Optional[dict] = None,
                  env_config: Optional[dict] = None, seed: int = 0, disable_cams: bool = False, device: int = 0, precision: int = 64,
-                 output: str = "torch", solver: str = "exact", env_offset: int = 0, terrain_type: Optional[str] = None,
+                 output: str = "torch", solver: str = "fast", env_offset: int = 0, terrain_type: Optional[str] = None,
                  env_seeds=None, perlin_table: Optional[bool] = None, terrain_bank: Optional[bool] = None):
         import openballbot_rl_b200.rewards  # noqa: F401  (registers the built-ins)
         import openballbot_rl_b200.terrain  # noqa: F401

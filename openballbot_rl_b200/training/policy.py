@@ -24,6 +24,34 @@ def make_depth_encoder(h: int = 64, w: int = 64, in_c: int = 1, out_sz: int = 20
         nn.Flatten(), nn.Linear(32 * h // 4 * w // 4, out_sz), nn.BatchNorm1d(out_sz), nn.Tanh())
 
 
+@torch.no_grad()
+def fold_encoder(enc: nn.Sequential) -> nn.Sequential:
+    """Inference copy of ``make_depth_encoder`` with every eval-mode BatchNorm folded into the layer in front of it:
+    y = g (W x + b - m) / sqrt(v + eps) + beta  ==  (s W) x + (s (b - m) + beta),  s = g / sqrt(v + eps)."""
+    mods, out = list(enc), []
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        nxt = mods[i + 1] if i + 1 < len(mods) else None
+        if isinstance(m, (nn.Conv2d, nn.Linear)) and isinstance(nxt, (nn.BatchNorm2d, nn.BatchNorm1d)):
+            s = nxt.weight / torch.sqrt(nxt.running_var + nxt.eps)
+            if isinstance(m, nn.Conv2d):
+                f = nn.Conv2d(m.in_channels, m.out_channels, m.kernel_size, m.stride, m.padding).to(m.weight.device)
+                f.weight.copy_(m.weight * s.reshape(-1, 1, 1, 1))
+            else:
+                f = nn.Linear(m.in_features, m.out_features).to(m.weight.device)
+                f.weight.copy_(m.weight * s.reshape(-1, 1))
+            b = m.bias if m.bias is not None else torch.zeros_like(s)
+            f.bias.copy_((b - nxt.running_mean) * s + nxt.bias)
+            out.append(f); i += 2
+        else:
+            out.append(m); i += 1
+    folded = nn.Sequential(*out).eval()
+    for p in folded.parameters():
+        p.requires_grad_(False)
+    return folded
+
+
 class BallbotPolicy(nn.Module):
     def __init__(self, im_h: int = 64, im_w: int = 64, hidden: int = 128, cameras: bool = True):
         super().__init__()

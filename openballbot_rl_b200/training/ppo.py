@@ -27,7 +27,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from .policy import FEATURE_ORDER, BallbotPolicy
+from .policy import FEATURE_ORDER, BallbotPolicy, fold_encoder
 from .rollout import reduce_rollout_stats
 
 
@@ -55,6 +55,7 @@ class PPOConfig:
     weight_decay: float = 0.01
     normalize_advantage: bool = False
     learning_rate: float = -1.0          # -1: reference schedule
+    cuda_graph: bool = True              # CUDA tensors: capture the minibatch forward / backward once and replay it (update loop is launch bound otherwise)
 
 
 def _world():
@@ -104,6 +105,10 @@ class PPOLearner:
         self.num_timesteps = 0
         self._emb = None
         self._obs = None
+        self._buf = None
+        self._enc_folded = None
+        self._graph = None           # (key, CUDAGraph, static index tensor) of the captured minibatch forward / backward
+        self._acc = torch.zeros(3, device=self.device)     # policy loss, value loss, entropy summed on the device
         self.timing = {"collect_s": 0.0, "update_s": 0.0, "allreduce_s": 0.0}
 
     # ------------------------------------------------------------------ features with the embedding cache
@@ -112,15 +117,20 @@ class PPOLearner:
         pol = self.policy
         N = obs["actions"].shape[0]
         if pol.cameras:
+            enc = self._frozen_encoders()
             if self._emb is None:
-                self._emb = {k: pol.encoders[k](obs[k]) for k in ("rgbd_0", "rgbd_1")}
+                self._emb = {k: enc[k](obs[k]) for k in ("rgbd_0", "rgbd_1")}
             else:   # relative_image_timestamp == 0 <=> the cameras were rendered for this observation
                 fresh = torch.nonzero(obs["relative_image_timestamp"].reshape(N) == 0).flatten()
-                if fresh.numel() == 1:          # BatchNorm1d in eval mode accepts a batch of one; keep the indexing uniform
-                    fresh = fresh.repeat(2)
-                if fresh.numel():
+                nf = fresh.numel()
+                if nf:
+                    # pad the batch to a multiple of 512 with repeats of its first env (recomputing an embedding from the
+                    # same image is idempotent): a handful of batch shapes instead of a new one every step
+                    pad = (-nf) % 512 if nf < N else 0
+                    if pad:
+                        fresh = torch.cat([fresh, fresh[:1].expand(pad)])
                     for k in ("rgbd_0", "rgbd_1"):
-                        self._emb[k][fresh] = pol.encoders[k](obs[k][fresh])
+                        self._emb[k][fresh] = enc[k](obs[k][fresh])
         parts = []
         for k in FEATURE_ORDER:
             if k.startswith("rgbd_"):
@@ -129,6 +139,15 @@ class PPOLearner:
             elif k in obs:
                 parts.append(obs[k].flatten(1))
         return torch.cat(parts, dim=1)
+
+    def _frozen_encoders(self):
+        """The frozen depth encoders with their eval-mode BatchNorms folded into the preceding conv / linear layers
+        (same function, three elementwise passes over the activations fewer); rebuilt when the weights change."""
+        pol = self.policy
+        ver = tuple(p._version for p in pol.encoders.parameters()) + tuple(b._version for b in pol.encoders.buffers())
+        if self._enc_folded is None or self._enc_folded[0] != ver:
+            self._enc_folded = (ver, {k: fold_encoder(pol.encoders[k]) for k in pol.encoders})
+        return self._enc_folded[1]
 
     def _dist(self, feat: torch.Tensor):
         mean = self.policy.action_net(self.policy.policy_net(feat))
@@ -151,8 +170,12 @@ class PPOLearner:
         obs = self._obs
         feat0 = self.features(obs)
         F = feat0.shape[1]
-        buf = dict(feat=torch.empty(T, N, F, device=dev), act=torch.empty(T, N, 3, device=dev), logp=torch.empty(T, N, device=dev),
-                   rew=torch.empty(T, N, device=dev), done=torch.empty(T, N, dtype=torch.uint8, device=dev), val=torch.empty(T + 1, N, device=dev))
+        if self._buf is None or self._buf["feat"].shape != (T, N, F):   # persistent rollout storage: fixed addresses for the captured update
+            self._buf = dict(feat=torch.empty(T, N, F, device=dev), act=torch.empty(T, N, 3, device=dev), logp=torch.empty(T, N, device=dev),
+                             rew=torch.empty(T, N, device=dev), done=torch.empty(T, N, dtype=torch.uint8, device=dev), val=torch.empty(T + 1, N, device=dev),
+                             adv=torch.empty(T, N, device=dev), ret=torch.empty(T, N, device=dev))
+            self._graph = None
+        buf = self._buf
         ep_r = torch.zeros(N, device=dev); ep_l = torch.zeros(N, dtype=torch.int32, device=dev); ep_d = torch.zeros(N, dtype=torch.bool, device=dev)
         feat = feat0
         for t in range(T):
@@ -165,7 +188,8 @@ class PPOLearner:
             feat = self.features(obs)
         buf["val"][T] = self._value(feat)
         self._obs = obs
-        buf["adv"], buf["ret"] = self.gae_fn(buf["rew"], buf["val"], buf["done"], cfg.gamma, cfg.gae_lambda)
+        adv, ret = self.gae_fn(buf["rew"], buf["val"], buf["done"], cfg.gamma, cfg.gae_lambda)
+        buf["adv"].copy_(adv); buf["ret"].copy_(ret)
         stats = reduce_rollout_stats(ep_r, ep_l, ep_d, steps=T * N)
         self.num_timesteps += stats["env_steps"]                     # global count (SUM over ranks): identical on every rank
         return buf, stats
@@ -217,35 +241,66 @@ class PPOLearner:
             dist.all_reduce(n_glob, op=dist.ReduceOp.SUM)
         n_mb = max(1, int(-(-int(n_glob.item()) // max(1, cfg.batch_size))))       # ceil: the remainder minibatch is trained on, as in SB3
         n_mb = min(n_mb, n) if n > 0 else n_mb
-        bounds = [(k * n) // n_mb for k in range(n_mb + 1)]
+        # equal chunks of b0 samples (the last one takes the remainder): one shape for the captured minibatch
+        b0 = -(-n // n_mb) if n > 0 else 0
+        bounds = [min(n, k * b0) for k in range(n_mb + 1)]
         kl_limit = 1.5 * cfg.target_kl if cfg.target_kl is not None else -1.0
         self.ctrl[0] = 0.0; self.ctrl[4] = 0.0
-        acc = torch.zeros(3, device=dev)           # policy loss, value loss, entropy summed on the device
+        acc = self._acc; acc.zero_()
         ar_events = []
         import time as _time
+
+        def minibatch(idx):
+            """zero the flat gradient, forward / backward of one minibatch (accumulates into the flat buffer's views), KL tail"""
+            b = idx.numel()
+            self.flat_g.zero_()
+            mean, log_std = self._dist(feat[idx])
+            logp = self._log_prob(act[idx], mean, log_std)
+            a = adv[idx]
+            if cfg.normalize_advantage and b > 1:
+                a = (a - a.mean()) / (a.std() + 1e-8)
+            lr_ = logp - old_logp[idx]
+            ratio = lr_.exp()
+            pl = -torch.min(a * ratio, a * ratio.clamp(1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+            vl = nn.functional.mse_loss(self._value(feat[idx]), ret[idx])
+            ent = (log_std + 1.4189385332046727).sum(-1).mean()
+            loss = (pl + cfg.vf_coef * vl - cfg.ent_coef * ent) * float(b)         # weighted by the local sample count
+            loss.backward()
+            with torch.no_grad():
+                d_ = lr_.detach()
+                self.flat_g[self.n_param:self.n_param + 1].copy_(((d_.exp() - 1) - d_).sum().reshape(1))
+                self.flat_g[self.n_param + 1:self.n_param + 2].fill_(float(b))        # (fill_: no host-to-device copy, capturable)
+                acc.add_(torch.stack([pl.detach(), vl.detach(), ent.detach()]))
+
+        graph = None
+        if cfg.cuda_graph and self.flat_g.is_cuda and b0 > 0:
+            key = (feat.data_ptr(), n, b0, F)
+            if self._graph is None or self._graph[0] != key:
+                idx_static = torch.zeros(b0, dtype=torch.long, device=dev)
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):                      # warm-up on a side stream (lazy cuBLAS / autograd initialisation)
+                    for _ in range(3):
+                        minibatch(idx_static)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    minibatch(idx_static)
+                self._graph = (key, g, idx_static)
+                acc.zero_()
+            graph = self._graph
         for epoch in range(cfg.n_epochs):
             perm = torch.randperm(n, device=dev, generator=self.gen)
             for k in range(n_mb):
                 idx = perm[bounds[k]:bounds[k + 1]]
                 b = idx.numel()
-                self.flat_g.zero_()
-                if b:
-                    mean, log_std = self._dist(feat[idx])
-                    logp = self._log_prob(act[idx], mean, log_std)
-                    a = adv[idx]
-                    if cfg.normalize_advantage and b > 1:
-                        a = (a - a.mean()) / (a.std() + 1e-8)
-                    ratio = (logp - old_logp[idx]).exp()
-                    pl = -torch.min(a * ratio, a * ratio.clamp(1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
-                    vl = nn.functional.mse_loss(self._value(feat[idx]), ret[idx])
-                    ent = (log_std + 1.4189385332046727).sum(-1).mean()
-                    loss = (pl + cfg.vf_coef * vl - cfg.ent_coef * ent) * float(b)         # weighted by the local sample count
-                    loss.backward()                                                        # accumulates into the flat buffer's views
-                    with torch.no_grad():
-                        lr_ = logp - old_logp[idx]
-                        self.flat_g[self.n_param] = ((lr_.exp() - 1) - lr_).sum()
-                        self.flat_g[self.n_param + 1] = float(b)
-                        acc += torch.stack([pl.detach(), vl.detach(), ent.detach()])
+                if graph is not None and b == b0:
+                    graph[2].copy_(idx)
+                    graph[1].replay()
+                elif b:
+                    minibatch(idx)
+                else:
+                    self.flat_g.zero_()
                 if world > 1:
                     if self.flat_g.is_cuda:      # device time of the collective: CUDA events on the stream NCCL synchronises with
                         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

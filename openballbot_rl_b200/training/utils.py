@@ -22,7 +22,7 @@ def make_ballbot_env(terrain_type=None, reward_config=None, terrain_config=None,
 
 
 def make_ballbot_vec_env(num_envs, terrain_config=None, reward_config=None, env_config=None, seed=0, disable_cams=False, device=0,
-                         precision=64, output="torch", solver="exact", rank=0, world_size=1):
+                         precision=64, output="torch", solver="fast", rank=0, world_size=1):
     """GPU replacement of ``SubprocVecEnv([make_ballbot_env(...) for _ in range(N)])`` (train.py:82-97).  With
     ``world_size > 1`` the N envs are sharded by index across ranks (one process per GPU, no collective on the step path)."""
     from ..envs.vec_env import BallbotVecEnv

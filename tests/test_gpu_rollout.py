@@ -43,7 +43,7 @@ def test_ppo_iteration_on_engine_with_embedding_cache():
     obs = venv._obs_view()
     with torch.no_grad():
         for k in ("rgbd_0", "rgbd_1"):
-            assert torch.allclose(L._emb[k], pol.encoders[k](obs[k]), atol=1e-5)
+            assert torch.allclose(L._emb[k], pol.encoders[k](obs[k]), atol=2e-3)   # BatchNorm-folded copy, cuDNN TF32 convolutions
     assert buf["feat"].shape == (24, 64, 56) and torch.isfinite(buf["adv"]).all() and stats["env_steps"] == 64 * 24
     info = L.update(buf)
     after = torch.cat([p.detach().reshape(-1) for p in L.params])

@@ -122,3 +122,17 @@ def test_uneven_env_shards_do_not_desynchronise_the_ranks():
     assert np.array_equal(p0, p1)
     assert s0 == s1 == n0 == n1 == 8 * (8 + 5)
     assert m0 == m1 == -(-8 * 13 // 24) and u0 == u1 == 2 * m0                 # ceil(104 / 24) = 5 minibatches incl. the remainder, 2 epochs
+
+
+def test_folded_encoder_equals_the_eval_mode_encoder():
+    """fold_encoder (BatchNorm folded into conv / linear for the frozen encoders of the rollout collector) is the same function."""
+    from openballbot_rl_b200.training.policy import fold_encoder, make_depth_encoder
+    torch.manual_seed(0)
+    enc = make_depth_encoder()
+    for m in enc:
+        if hasattr(m, "running_mean"):
+            m.running_mean.normal_(); m.running_var.uniform_(0.5, 2.0); m.weight.data.normal_(); m.bias.data.normal_()
+    enc.eval()
+    x = torch.rand(5, 1, 64, 64)
+    with torch.no_grad():
+        assert (fold_encoder(enc)(x) - enc(x)).abs().max() < 1e-5
