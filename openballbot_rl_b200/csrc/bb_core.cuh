@@ -121,6 +121,7 @@ template <typename T> struct ModelConst {
   T dA[NCT];       // diagApprox (sum of the two bodies' invweight0) per contact type
   T K, B;          // solref -> stiffness / damping of aref
   T solimp[5];
+  T inv_width, inv_mid, inv_1mmid;   // 1 / solimp[2], 1 / solimp[3], 1 / (1 - solimp[3]) (the last two are exact powers of two for the default solimp)
   T mu[2], f1[2], f2[2], d1r[2], d2r[2];   // [0] wheel pairs, [1] hfield pair
   T dmr[2];        // 1 / (mu^2 (1 + mu^2)): cone-zone stiffness ratio Dm / D0
   T meaninertia, timestep, grav;           // gravity = (0,0,-grav)

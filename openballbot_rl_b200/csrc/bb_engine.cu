@@ -749,7 +749,7 @@ __device__ __forceinline__ F3 operator-(F3 a, F3 b) { return f3(a.x - b.x, a.y -
 __device__ __forceinline__ F3 operator*(F3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ float fdot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 struct Prim { F3 c, u; float r, hl; int type; };  // type 0 sphere, 1 capsule, 2 cylinder
-struct Scene { F3 cam_o[2]; F3 cam_x[2], cam_y[2], cam_z[2]; Prim prim[7]; float brad2[7]; };
+struct Scene { F3 cam_o[2]; F3 cam_x[2], cam_y[2], cam_z[2]; Prim prim[7]; float brad2[7]; float rect[7][4]; };   // rect: screen-space bounds of the work unit's camera
 
 __device__ __forceinline__ float hitSphere(F3 o, F3 dir, F3 c, float rad) {
   const F3 oc = o - c; const float a = fdot(dir, dir), b = fdot(oc, dir), cc = fdot(oc, oc) - rad * rad;
@@ -915,17 +915,52 @@ __global__ void __launch_bounds__(256) k_depth(EnvParams p, DevState d, const in
     const float* hf = hfOf(p, d, env);
     float* out = (cam ? img1 : img0) + (size_t)env * npix;
     const F3 o = sc.cam_o[cam];
+    const float aspect = (float)p.im_w / p.im_h;
+    // ---- screen-space bounds of the primitives' bounding spheres for this camera (lanes 0..6), then one 7-bit mask per 8 x 4
+    // tile of this unit (lanes 0..chunk-1): a ray only visits the primitives whose bounds overlap its tile (conservative: the
+    // per-ray bounding-sphere test and the exact test are unchanged, so the image is identical).  xn = x / depth of a sphere at
+    // camera coordinates (xc, yc, zc) spans tan(theta0 -+ phi), theta0 = atan(xc / zc), sin(phi) = R / |(xc, zc)|.
+    if (lane < 7) {
+      const F3 oc = sc.prim[lane].c - o;
+      const float xc = fdot(oc, sc.cam_x[cam]), yc = fdot(oc, sc.cam_y[cam]), zc = -fdot(oc, sc.cam_z[cam]);
+      const float R2 = sc.brad2[lane], R = sqrtf(R2) * 1.001f + 1e-6f;
+      float x0 = -3e38f, x1 = 3e38f, y0 = -3e38f, y1 = 3e38f;
+      if (zc + R < 0.f) { x0 = 3e38f; x1 = -3e38f; }                       // entirely behind the camera plane: never visible
+      else if (zc > R) {
+        const float iz = 1.f / zc;
+        { const float t0 = xc * iz, tp = R * rsqrtf(fmaxf(xc * xc + zc * zc - R * R, 1e-30f)); x0 = (t0 - tp) / (1.f + t0 * tp); x1 = (t0 + tp) / (1.f - t0 * tp);
+          if (!(1.f - t0 * tp > 1e-6f)) x1 = 3e38f; if (!(1.f + t0 * tp > 1e-6f)) x0 = -3e38f; }
+        { const float t0 = yc * iz, tp = R * rsqrtf(fmaxf(yc * yc + zc * zc - R * R, 1e-30f)); y0 = (t0 - tp) / (1.f + t0 * tp); y1 = (t0 + tp) / (1.f - t0 * tp);
+          if (!(1.f - t0 * tp > 1e-6f)) y1 = 3e38f; if (!(1.f + t0 * tp > 1e-6f)) y0 = -3e38f; }
+      }
+      sc.rect[lane][0] = x0 - 1e-4f; sc.rect[lane][1] = x1 + 1e-4f; sc.rect[lane][2] = y0 - 1e-4f; sc.rect[lane][3] = y1 + 1e-4f;
+    }
+    __syncwarp();
     const int tend = min(tiles, (part + 1) * chunk);
+    unsigned mymask = 0;
+    {
+      const int tile = part * chunk + lane;
+      if (chunk <= 32 && lane < chunk && tile < tend) {
+        const int r0 = (tile / tiles_x) * 4, c0 = (tile % tiles_x) * 8;
+        const float xa = (2.f * (c0 + 0.5f) / p.im_w - 1.f) * aspect, xb = (2.f * (c0 + 7.5f) / p.im_w - 1.f) * aspect;
+        const float yb = 1.f - 2.f * (r0 + 0.5f) / p.im_h, ya = 1.f - 2.f * (r0 + 3.5f) / p.im_h;
+#pragma unroll
+        for (int g = 0; g < 7; g++)
+          if (sc.rect[g][0] <= xb && sc.rect[g][1] >= xa && sc.rect[g][2] <= yb && sc.rect[g][3] >= ya) mymask |= 1u << g;
+      }
+    }
     for (int tile = part * chunk; tile < tend; tile++) {
+      const unsigned tmask = chunk <= 32 ? __shfl_sync(0xffffffffu, mymask, (tile - part * chunk) & 31) : 0x7fu;   // (larger images: no tile culling)
       const int r = (tile / tiles_x) * 4 + ly, c = (tile % tiles_x) * 8 + lx;
       if (r >= p.im_h || c >= p.im_w) continue;
       const int px = r * p.im_w + c;
-      const float xn = (2.f * (c + 0.5f) / p.im_w - 1.f) * ((float)p.im_w / p.im_h), yn = 1.f - 2.f * (r + 0.5f) / p.im_h;  // fovy 90
+      const float xn = (2.f * (c + 0.5f) / p.im_w - 1.f) * aspect, yn = 1.f - 2.f * (r + 0.5f) / p.im_h;  // fovy 90
       const F3 dir = sc.cam_x[cam] * xn + sc.cam_y[cam] * yn - sc.cam_z[cam];
       const float inv_dd = 1.f / fdot(dir, dir);
       float best = 1.0f;   // depth >= 1 is clipped to 1 (sensors/rgbd.py:74)
 #pragma unroll 1
-      for (int g = 0; g < 7; g++) {
+      for (unsigned mm = tmask; mm; mm &= mm - 1) {
+        const int g = __ffs(mm) - 1;
         const Prim& pr = sc.prim[g];
         const F3 oc = pr.c - o; const float along = fdot(oc, dir) * inv_dd;   // bounding-sphere reject before the exact test
         const F3 perp = oc - dir * along;

@@ -762,17 +762,18 @@ template <typename T, bool U = false, int FM = -1> struct GNewton {
 // impedance / regulariser / reference acceleration (mj_makeImpedance, mj_referenceConstraint) -> scalar block
 template <typename T>
 __device__ __forceinline__ void finishRecord(const ModelConst<T>& mc, T* sc, int ty, T dist, const T* vel) {
-  const T x = babs(dist) / mc.solimp[2];
+  // (reciprocals of the model constants and ONE division for D0 = 1 / max(1e-15, R0), R0 = (1 - imp) dA / imp: the four fp64
+  // divisions of the literal formula were 10 % of k_stage's instructions; the results differ by <= 2 ulp)
+  const T x = babs(dist) * mc.inv_width;
   T imp;
   if (x >= 1) imp = mc.solimp[1];
   else if (x <= 0) imp = mc.solimp[0];
   else {
-    const T mid = mc.solimp[3];
-    const T y = x <= mid ? x * x / mid : (T)1 - ((T)1 - x) * ((T)1 - x) / ((T)1 - mid);
+    const T om = (T)1 - x;
+    const T y = x <= mc.solimp[3] ? x * x * mc.inv_mid : (T)1 - om * om * mc.inv_1mmid;
     imp = mc.solimp[0] + y * (mc.solimp[1] - mc.solimp[0]);
   }
-  const T R0 = bmax((T)1e-15, ((T)1 - imp) * mc.dA[ty] / imp);
-  sc[O_D0] = (T)1 / R0;
+  sc[O_D0] = imp / bmax((T)1e-15 * imp, ((T)1 - imp) * mc.dA[ty]);
   // aref is parked in the jv slot until the solver has formed jar = J qacc - aref
   sc[O_JV] = -mc.B * vel[0] - mc.K * imp * dist; sc[O_JV + 1] = -mc.B * vel[1]; sc[O_JV + 2] = -mc.B * vel[2];
 }

@@ -61,6 +61,7 @@ inline void buildModelConst(ModelConst<double>& mc) {
   mc.timestep = 0.002; mc.grav = 9.81; mc.tolerance = 1e-8; mc.ls_tolerance = 0.01; mc.iterations = 100; mc.ls_iterations = 50;
   const double impratio = 1.0, solref[2] = {0.02, 1.0}, solimp[5] = {0.9, 0.95, 0.001, 0.5, 2.0};
   for (int k = 0; k < 5; k++) mc.solimp[k] = solimp[k];
+  mc.inv_width = 1.0 / solimp[2]; mc.inv_mid = 1.0 / solimp[3]; mc.inv_1mmid = 1.0 / (1.0 - solimp[3]);
   const double tc = std::fmax(solref[0], 2 * mc.timestep);
   mc.K = 1.0 / (solimp[1] * solimp[1] * tc * tc * solref[1] * solref[1]);
   mc.B = 2.0 / (solimp[1] * tc);
