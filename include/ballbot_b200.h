@@ -70,8 +70,10 @@ typedef struct bb_config {
   uint64_t seed;             /* base seed of the counter-based per-env terrain-seed generator */
   int32_t auto_reset;        /* 1: VecEnv semantics (done envs are reset inside bb_step) */
   int32_t step_kernel;       /* 0: lane-group kernels, split-phase (default); 1: thread-per-env reference mapping (cross-check); 2: lane-group kernel, fused RK4 step (cross-check) */
-  int32_t solver_mode;       /* 0: MuJoCo-faithful iteration path (every RK4 stage warm-starts from qacc_warmstart);
-                                1: fast -- stages 2..4 warm-start from the previous stage (same minimiser within tolerance) */
+  int32_t solver_mode;       /* 0: mj_solNewton's own iteration path (exact line search, every RK4 stage warm-starts from qacc_warmstart);
+                                1: same cost, Newton direction, tolerance and termination rule; strong-Wolfe line search with cone-apex
+                                candidates and analytic p0, stages 2..4 warm-start from the previous stage (same minimiser: single
+                                steps agree to ~1e-8 relative) */
   int32_t perlin_table;      /* BB_TERRAIN_PERLIN storage: 1 = all BB_PERLIN_SEEDS possible fields are generated once at bb_create
                                 (3.4 GB, independent of num_envs) and a reset only selects one; 0 = one regenerated field per env
                                 (343 KB per env, any seed value); -1 = auto (table from 2048 envs up) */

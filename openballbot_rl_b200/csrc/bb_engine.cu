@@ -258,10 +258,12 @@ __device__ __forceinline__ void stepFinish(const EnvParams& p, const DevState& d
   KinOut<T> kin;
   const int nev = nit >> 12; nit &= 0xfff;
   int status = (ncmax << 8) | (nit << 16);   // bit 0: numerical failure, bits 8-15: max contacts of the stages, bits 16+: Newton iterations
-#ifndef BB_KEY_DIV
-#define BB_KEY_DIV 16
+  // work of the solver ~ Newton iterations x (Hessian + factorisation + substitutions) + line-search evaluations, about 15 : 1 per
+  // ncu's instruction counts; 64 bins cover ~65 iterations (with solver mode 1 the evaluations alone no longer separate the envs)
+#ifndef BB_KEY_ITER_WEIGHT
+#define BB_KEY_ITER_WEIGHT 15
 #endif
-  const int kv = nev ? (nev + BB_KEY_DIV - 1) / BB_KEY_DIV : nit;            // split-phase path: line-search evaluations; fused path: iterations
+  const int kv = nev ? (BB_KEY_ITER_WEIGHT * nit + nev + 15) >> 4 : nit;     // split-phase path: weighted work; fused path: iterations
   const int key = bad ? 0 : (kv < WORK_BINS ? kv : WORK_BINS - 1);
   if (!bad) {
     bool b2 = (L.gl < NV && !(babs(S.xv[L.gl]) < (T)1e10));
@@ -466,8 +468,11 @@ k_stage(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io, in
 // k_newton<T>: constraint solve of one RK stage for the envs that have contacts, in work-sorted order.  Uniform-warp
 // solver (GNewton<T, true>): a warp leaves only when neither of its envs has contacts; otherwise both groups run the solver
 // loops together and every collective uses the constant full-warp mask.
+#ifndef BB_NEWTON_MINBLOCKS
+#define BB_NEWTON_MINBLOCKS BB_WARP_MINBLOCKS      // residency (= register cap) of the solver kernel alone, fp64
+#endif
 template <typename T, int FM>
-__global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCKS32 : BB_WARP_MINBLOCKS) k_newton(EnvParams p, DevState d, int stage) {
+__global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCKS32 : BB_NEWTON_MINBLOCKS) k_newton(EnvParams p, DevState d, int stage) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const bbg::Ln L = bbg::makeLn();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / bbg::G;
