@@ -73,12 +73,14 @@ struct DevState {
   unsigned long long* rng;   // [N][5] numpy PCG64 state per env (seed_stream = 1): state hi/lo, inc hi/lo, has_uint32 | uinteger << 32
   float* ptab;     // [2][293] circle coordinates of the tiled simplex noise (sin, cos) per grid index
   float* ep_ret; int* ep_len;
-  int* counters;   // [0] reset-list length, [1] refresh-list length, [2] depth work-unit cursor
+  int* counters;   // [0] reset-list length, [1] refresh-list length, [2] depth work-unit cursor, [8 + s] / [12 + s] solver work list of stage s: length / cursor
   int* reset_list; int* refresh_list;
   // work-sorted scheduling of the group step kernel: key = Newton iterations of the env's previous step (capped)
   int* work;       // [N] key of the previous step
   int* order;      // [N] env indices sorted by descending key (heavy envs first, similar envs share a warp)
   int* bins;       // [WORK_BINS] histogram of work[] (accumulated by the step kernel) + [WORK_BINS] scatter cursors
+  int* alist;      // [N] envs with contacts in the current RK stage, appended by k_stage (counters[8 + stage]), consumed by the
+                   // persistent solver kernel through the cursor counters[12 + stage]
 };
 constexpr int WORK_BINS = 64;
 
@@ -462,6 +464,7 @@ k_stage(EnvParams p, DevState d, const float* __restrict__ actions, bb_io io, in
   if (L.gl == 0) {
     meta[bbg::META_NCON] = ncon; meta[bbg::META_NW] = nw | (nd << 8);
     if (ncon > ncmax) meta[bbg::META_FLAGS] = ncon << 8;
+    if (ncon > 0) d.alist[atomicAdd(&d.counters[8 + stage], 1)] = i;     // work list of the solver launch of this stage
   }
   if (ncon > 0) bbg::ctxSave((T*)d.ctx + (size_t)i * bbg::CTXN, S, ncon, nd, qfs, qas, L);
 }
@@ -504,6 +507,65 @@ __global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCK
   }
   if (L.gl == 0) meta[bbg::META_NIT] += niter + (nwt.nevals << 12);   // low 12 bits: Newton iterations, above: line-search evaluations
 }
+// k_newton_p<T, FM>: persistent variant of k_newton (default).  Every 16-lane group draws environments from the stage's work
+// list (the envs that have contacts, appended by k_stage in work-sorted CTA order) through an atomic cursor; when its solve
+// ends it writes the result back and takes the next environment at the next Newton-iteration boundary, while the other group
+// of the warp carries on with its own solve.  In k_newton a group whose solve has finished rides along until its partner is
+// done (23 of 32 lanes active on the bench workload); here both halves of a warp stay busy until the list is empty.
+// The arithmetic per environment is the same code in the same order (GNewton::begin / iterate), so results are identical.
+template <typename T, int FM>
+__global__ void __launch_bounds__(32 * BB_WPB, sizeof(T) == 4 ? BB_WARP_MINBLOCKS32 : BB_NEWTON_MINBLOCKS) k_newton_p(EnvParams p, DevState d, int stage) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const bbg::Ln L = bbg::makeLn();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / bbg::G;
+  bbg::GS<T>& S = reinterpret_cast<bbg::GS<T>*>(smem_raw)[warp * bbg::EPW + grp];
+  bbg::Ln LU = L; LU.mask = 0xffffffffu;               // compile-time constant member mask for everything inlined below
+  bbg::GNewton<T, true, FM> nwt(cmc<T>(), S, (T*)d.gscr, LU, 0, 0, 0, FM == 1, (T)0, (T)0);
+  const int total = d.counters[8 + stage];
+  int* cursor = d.counters + 12 + stage;
+  bool on = false, done = false;
+  int i = 0;
+#pragma unroll 1
+  for (;;) {
+    const bool need = !on && !done;
+    if (__any_sync(0xffffffffu, need)) {
+      int slot = 0;
+      if (need && L.gl == 0) slot = atomicAdd(cursor, 1);
+      slot = __shfl_sync(0xffffffffu, slot, lane & 16);
+      bool fresh = false;
+      T warm = 0;
+      if (need) {
+        if (slot >= total) done = true;
+        else {
+          fresh = true;
+          i = d.alist[slot];
+          const int* meta = d.meta + 4 * (size_t)i;
+          const int ncon = meta[bbg::META_NCON], nw = meta[bbg::META_NW] & 0xff, nd = meta[bbg::META_NW] >> 8;
+          T qfs, qas;
+          bbg::ctxLoad((const T*)d.ctx + (size_t)i * bbg::CTXN, S, ncon, nd, qfs, qas, L);
+          warm = L.gl < NV ? ((const T*)d.rk + (size_t)i * bbg::RKN)[bbg::RK_WARM + L.gl] : (T)0;
+          nwt.attach((T*)d.gscr + (size_t)i * bbg::GSCR, ncon, nw, nd, qfs, qas);
+        }
+      }
+      __syncwarp();
+      if (__any_sync(0xffffffffu, fresh)) {
+        nwt.begin(warm, fresh);
+        if (fresh) on = nwt.iter < cmc<T>().iterations;
+      }
+    }
+    if (!__any_sync(0xffffffffu, on)) { if (__all_sync(0xffffffffu, done)) break; else continue; }
+    const bool was = on;
+    on = nwt.iterate(on);
+    if (was && !on) {                                   // solve finished: write back (group-uniform branch, plain stores)
+      T* rk = (T*)d.rk + (size_t)i * bbg::RKN;
+      if (L.gl < NV) {
+        rk[bbg::RK_QACC + L.gl] = nwt.qacc;
+        if (FM == 1 && stage < 3) rk[bbg::RK_WARM + L.gl] = nwt.qacc;
+      }
+      if (L.gl == 0) d.meta[4 * (size_t)i + bbg::META_NIT] += nwt.iter + (nwt.nevals << 12);
+    }
+  }
+}
 // forward-dynamics probe through the group path (same outputs as k_probe)
 template <typename T> __global__ void k_probe_warp(EnvParams p, DevState d, int env, const double* ctrl3, double* out, double* dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -538,11 +600,12 @@ __global__ void k_mask_to_list(EnvParams p, DevState d, const uint8_t* __restric
 }
 // k_begin_step, one block of WORK_BINS threads: clears the work-list counters and turns the key histogram of the previous step into
 // the scatter cursors of k_order (descending keys: the longest solves are scheduled first).
-__global__ void k_clear_counters(DevState d) { d.counters[0] = 0; d.counters[1] = 0; d.counters[2] = 0; }
+__global__ void k_clear_counters(DevState d) { d.counters[0] = 0; d.counters[1] = 0; d.counters[2] = 0; for (int k = 8; k < 16; k++) d.counters[k] = 0; }
 __global__ void k_begin_step(DevState d) {
   __shared__ int h[WORK_BINS];
   const int t = threadIdx.x;
   if (t == 0) { d.counters[0] = 0; d.counters[1] = 0; d.counters[2] = 0; }
+  if (t >= 8 && t < 16) d.counters[t] = 0;
   h[t] = d.bins[t];
   __syncthreads();
   int start = 0;
@@ -1235,6 +1298,7 @@ struct bb_engine {
   DevState d;
   int N;
   int table_n;                     // fields in the Perlin table (HF_TABLE)
+  int sm_count;                    // multiprocessors of the device (grid of the persistent solver kernel)
   int raster;                      // depth observation: 1 = k_depth_raster (images of <= 64 x 64 pixels), 0 = k_depth ray-caster
   double* probe_out;               // scratch of bb_get_contacts
   size_t tsize;
@@ -1398,6 +1462,8 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   p.pscale = cfg->perlin_scale; p.ppers = cfg->perlin_persistence; p.plac = cfg->perlin_lacunarity; p.pamp = cfg->perlin_amplitude; p.poct = cfg->perlin_octaves;
   e->tsize = cfg->precision == 64 ? 8 : 4;
   e->raster = cfg->depth_kernel != 1 && cfg->im_h * cfg->im_w <= RASTER_MAX_PIX;
+  e->sm_count = 148;
+  { int smc = 0; if (cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && smc > 0) e->sm_count = smc; }
   DevState& d = e->d;
   BB_CUDA_C(cudaMalloc(&d.st, e->tsize * SST * N));
   BB_CUDA_C(cudaMalloc(&d.camq, e->tsize * CST * N));
@@ -1408,8 +1474,8 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   BB_CUDA_C(cudaMalloc(&d.step_count, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.cam_steps, sizeof(int) * N));
   BB_CUDA_C(cudaMalloc(&d.episode, sizeof(unsigned) * N)); BB_CUDA_C(cudaMalloc(&d.tseed, sizeof(int) * N));
   BB_CUDA_C(cudaMalloc(&d.ep_ret, sizeof(float) * N)); BB_CUDA_C(cudaMalloc(&d.ep_len, sizeof(int) * N));
-  BB_CUDA_C(cudaMalloc(&d.counters, sizeof(int) * 4));
-  BB_CUDA_C(cudaMalloc(&d.work, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.order, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.bins, sizeof(int) * 2 * WORK_BINS));
+  BB_CUDA_C(cudaMalloc(&d.counters, sizeof(int) * 16));
+  BB_CUDA_C(cudaMalloc(&d.work, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.order, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.alist, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.bins, sizeof(int) * 2 * WORK_BINS));
   {  // CTAs of more than one warp may need more than the default 48 KB of dynamic shared memory
     const int epb = BB_WPB * bbg::EPW;
     const int sm64 = (int)(epb * sizeof(bbg::GS<double>)), sm32 = (int)(epb * sizeof(bbg::GS<float>));
@@ -1422,6 +1488,10 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
     BB_CUDA_C(cudaFuncSetAttribute(k_newton<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm32));
     BB_CUDA_C(cudaFuncSetAttribute(k_newton<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm64));
     BB_CUDA_C(cudaFuncSetAttribute(k_newton<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm32));
+    BB_CUDA_C(cudaFuncSetAttribute(k_newton_p<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm64));
+    BB_CUDA_C(cudaFuncSetAttribute(k_newton_p<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm32));
+    BB_CUDA_C(cudaFuncSetAttribute(k_newton_p<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm64));
+    BB_CUDA_C(cudaFuncSetAttribute(k_newton_p<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm32));
   }
   k_init_order<<<blocksFor(N > 2 * WORK_BINS ? N : 2 * WORK_BINS, 256), 256>>>(N, d);
   BB_CUDA_C(cudaMalloc(&d.reset_list, sizeof(int) * N)); BB_CUDA_C(cudaMalloc(&d.refresh_list, sizeof(int) * N));
@@ -1452,7 +1522,7 @@ int bb_create(const bb_config* cfg, bb_engine** out) {
   BB_CUDA_C(cudaMemset(d.step_count, 0, sizeof(int) * N)); BB_CUDA_C(cudaMemset(d.cam_steps, 0, sizeof(int) * N));
   BB_CUDA_C(cudaMemset(d.episode, 0, sizeof(unsigned) * N)); BB_CUDA_C(cudaMemset(d.tseed, 0, sizeof(int) * N));
   BB_CUDA_C(cudaMemset(d.ep_ret, 0, sizeof(float) * N)); BB_CUDA_C(cudaMemset(d.ep_len, 0, sizeof(int) * N));
-  BB_CUDA_C(cudaMemset(d.counters, 0, sizeof(int) * 4));
+  BB_CUDA_C(cudaMemset(d.counters, 0, sizeof(int) * 16));
   BB_CUDA_C(cudaDeviceSynchronize());
 #undef BB_CUDA_C
   *out = e;
@@ -1464,7 +1534,7 @@ int bb_destroy(bb_engine* e) {
   DevGuard guard(e->cfg.device);
   DevState& d = e->d;
   cudaFree(d.st); cudaFree(d.camq); cudaFree(d.gscr); cudaFree(d.rk); cudaFree(d.ctx); cudaFree(d.meta); cudaFree(d.step_count); cudaFree(d.cam_steps); cudaFree(d.episode); cudaFree(d.tseed);
-  cudaFree(d.work); cudaFree(d.order); cudaFree(d.bins);
+  cudaFree(d.work); cudaFree(d.order); cudaFree(d.bins); cudaFree(d.alist);
   cudaFree(d.ep_ret); cudaFree(d.ep_len); cudaFree(d.counters); cudaFree(d.reset_list); cudaFree(d.refresh_list); cudaFree(d.hfield); cudaFree(d.hmip); cudaFree(d.ptab); cudaFree(d.rng); cudaFree(e->probe_out);
   if (e->prof_ev) { for (int i = 0; i < 5 * e->prof_cap; i++) cudaEventDestroy(e->prof_ev[i]); free(e->prof_ev); }
   if (e->host_ready) {
@@ -1533,7 +1603,15 @@ int bb_step(bb_engine* e, const float* actions_dev, const bb_io* io, void* strea
         else k_stage<float><<<sgrid, BB_WPB_STAGE * 32, sepb * sizeof(bbg::GS<float>), s>>>(e->p, e->d, actions_dev, *io, stage);
         if (stage == 4) break;
         const bool fs = e->cfg.solver_mode != 0;
-        if (e->cfg.precision == 64) { if (fs) k_newton<double, 1><<<grid, bt, sm64, s>>>(e->p, e->d, stage); else k_newton<double, 0><<<grid, bt, sm64, s>>>(e->p, e->d, stage); }
+#ifndef BB_NEWTON_PERSISTENT
+#define BB_NEWTON_PERSISTENT 1
+#endif
+        if (BB_NEWTON_PERSISTENT) {   // persistent groups drawing from the stage's work list: one wave of resident CTAs
+          const int res = e->sm_count * (e->cfg.precision == 64 ? BB_NEWTON_MINBLOCKS : BB_WARP_MINBLOCKS32);
+          const int pg = grid < res ? grid : res;
+          if (e->cfg.precision == 64) { if (fs) k_newton_p<double, 1><<<pg, bt, sm64, s>>>(e->p, e->d, stage); else k_newton_p<double, 0><<<pg, bt, sm64, s>>>(e->p, e->d, stage); }
+          else { if (fs) k_newton_p<float, 1><<<pg, bt, sm32, s>>>(e->p, e->d, stage); else k_newton_p<float, 0><<<pg, bt, sm32, s>>>(e->p, e->d, stage); }
+        } else if (e->cfg.precision == 64) { if (fs) k_newton<double, 1><<<grid, bt, sm64, s>>>(e->p, e->d, stage); else k_newton<double, 0><<<grid, bt, sm64, s>>>(e->p, e->d, stage); }
         else { if (fs) k_newton<float, 1><<<grid, bt, sm32, s>>>(e->p, e->d, stage); else k_newton<float, 0><<<grid, bt, sm32, s>>>(e->p, e->d, stage); }
       }
       e->launches += 8;

@@ -429,7 +429,7 @@ __device__ __forceinline__ LsPt<T> lsEval(const ModelConst<T>& mc, GS<T>& S, con
 // removes the convergence pre-check (MATCH / REDUX / VOTE / branch) ptxas emits in front of every shuffle group with a
 // run-time member mask: ~5 % of the solver's instructions and ~12 % of its stall samples.
 template <typename T, bool U = false, int FM = -1> struct GNewton {
-  const ModelConst<T>& mc; GS<T>& S; T* gs; const Ln L; const int ncon, nw, nd;   // nw wheel pairs <= nd dense contacts <= ncon
+  const ModelConst<T>& mc; GS<T>& S; T* gs; const Ln L; int ncon, nw, nd;   // nw wheel pairs <= nd dense contacts <= ncon
   const bool fast;   // solver_mode 1: strong-Wolfe line search with cone-apex candidates (searchFast), same minimiser of the outer problem
                      // FM: -1 = `fast` decides at run time (fused / probe kernels), 0 / 1 = compile-time choice (k_newton)
   __device__ __forceinline__ bool isFast() const { return FM < 0 ? fast : FM == 1; }
@@ -437,10 +437,15 @@ template <typename T, bool U = false, int FM = -1> struct GNewton {
   T qacc, Ma, grad, search, Mv;
   T cost, gauss, gnorm2;
   int nevals = 0;    // line-search evaluations of this solve (work key of the scheduler)
+  int iter = 0;      // Newton iterations of this solve
   T* rec0;           // record of the contact this lane owns in every per-contact loop (c = gl; loop-invariant for the whole solve)
   __device__ GNewton(const ModelConst<T>& m, GS<T>& s, T* g, const Ln l, int n, int w, int dn, bool f, T qf, T qa)
       : mc(m), S(s), gs(g), L(l), ncon(n), nw(w), nd(dn), fast(f), qfs(qf), qas(qa) { rec0 = crec(S, gs, L.gl, nd); }
   __device__ __forceinline__ T* recOf(int c) const { return c < G ? rec0 : crec(S, gs, c, nd); }
+  // persistent solver kernel: the group takes its next environment (its solver input has been loaded into S)
+  __device__ __forceinline__ void attach(T* g, int n, int w, int dn, T qf, T qa) {
+    gs = g; ncon = n; nw = w; nd = dn; qfs = qf; qas = qa; rec0 = crec(S, gs, L.gl, nd); nevals = 0; iter = 0;
+  }
 
   // forces / zones / cone Hessian blocks at the current jar (contact lanes), cost, gradient (dof lanes)
   __device__ __forceinline__ void costGrad() {
@@ -678,8 +683,77 @@ template <typename T, bool U = false, int FM = -1> struct GNewton {
   // rounding noise of a single-precision cost (~1e-7 |cost|); an improvement inside that noise ends the solve (without this
   // a few envs per 10^5 ran to the iteration cap and held their whole launch back)
   __device__ __forceinline__ static bool belowNoise(T old, T now) { return sizeof(T) == 4 && old - now <= (T)5e-7 * babs(old); }
+  // ---- uniform-warp pieces (U): begin() = warm-start choice + first cost / gradient for the groups that are `fresh`; the other
+  // group of the warp rides along with its state untouched (its per-contact loops are empty, register updates predicated,
+  // costGrad() is idempotent for a group that did not move).  iterate() = one Newton iteration for the groups that are `on`.
+  __device__ __forceinline__ void begin(T warm, bool fresh) {
+    const bool dof = L.gl < NV;
+    const int nc = fresh ? ncon : 0;
+    // warm-start choice: total cost at qacc_warmstart (-> vb[0]) and at qacc_smooth (-> vb[1])
+    if (fresh && (G == 16 || L.gl < 16)) { S.vb[0][L.gl] = dof ? warm : (T)0; S.vb[1][L.gl] = dof ? qas : (T)0; }
+    __syncwarp(L.mask);
+    const T mw = gSymv(S, S.vb[0], L.gi);
+    T cw = dof ? (T)0.5 * (mw - qfs) * (warm - qas) : (T)0, cs = 0;
+#pragma unroll 1
+    for (int c = L.gl; c < nc; c += G) {
+      const bool wheel = c < nd;
+      T* rec = recOf(c);
+      T* sc = rec + (wheel ? OSW : OSH);
+      T jw[3], js[3], f[3], h[6]; int st;
+      rowsDot(rec, wheel, S.vb[0], jw); rowsDot(rec, wheel, S.vb[1], js);
+#pragma unroll
+      for (int m = 0; m < 3; m++) { const T ar = sc[O_JV + m]; jw[m] -= ar; js[m] -= ar; }
+      cw += coneLane(mc, c < nw ? 0 : 1, sc[O_D0], jw, f, h, st, false);
+      cs += coneLane(mc, c < nw ? 0 : 1, sc[O_D0], js, f, h, st, false);
+      // park both candidates: jar <- warm-start residual, LS[0..2] <- smooth residual
+      sc[O_JAR] = jw[0]; sc[O_JAR + 1] = jw[1]; sc[O_JAR + 2] = jw[2];
+      sc[O_LS] = js[0]; sc[O_LS + 1] = js[1]; sc[O_LS + 2] = js[2];
+    }
+    const Sum3<T> r3 = gsum3(cw, cs, (T)0, L.mask);
+    const bool useSmooth = r3.a > r3.b;
+    if (fresh) {
+      if (useSmooth) {
+        qacc = qas; Ma = qfs;
+#pragma unroll 1
+        for (int c = L.gl; c < nc; c += G) {
+          T* sc = recOf(c) + (c < nd ? OSW : OSH);
+          sc[O_JAR] = sc[O_LS]; sc[O_JAR + 1] = sc[O_LS + 1]; sc[O_JAR + 2] = sc[O_LS + 2];
+        }
+      } else { qacc = warm; Ma = mw; }
+    }
+    __syncwarp(L.mask);
+    costGrad();
+  }
+  __device__ __forceinline__ bool iterate(bool on) {
+    const T scale = (T)1 / (mc.meaninertia * (T)NV);
+    search = -gHessSolve(S, gs, ncon, nd, grad, L);
+    const T alpha = lineSearch(scale, on);
+    const bool step = on && alpha != 0;               // alpha == 0 ends the solve without touching the state
+    if (step) {
+      qacc += alpha * search; Ma += alpha * Mv;
+#pragma unroll 1
+      for (int c = L.gl; c < ncon; c += G) {
+        T* sc = recOf(c) + (c < nd ? OSW : OSH);
+        sc[O_JAR] += alpha * sc[O_JV]; sc[O_JAR + 1] += alpha * sc[O_JV + 1]; sc[O_JAR + 2] += alpha * sc[O_JV + 2];
+      }
+    }
+    const T old = cost;
+    costGrad();                                       // idempotent for a group that did not step
+    if (step) iter++;
+    return step && iter < mc.iterations && !(scale * (old - cost) < mc.tolerance || scale * bsqrt(gnorm2) < mc.tolerance || belowNoise(old, cost));
+  }
+
   // in: aref parked in the jv slot of every record, `warm` = qacc_warmstart of this dof lane.  Returns qacc; niter by reference.
   __device__ __forceinline__ T run(T warm, int& niter, bool act = true) {
+    if (U) {
+      iter = 0;
+      begin(warm, true);
+      bool on = act && iter < mc.iterations;
+#pragma unroll 1
+      while (__any_sync(0xffffffffu, on)) on = iterate(on);
+      niter = iter;
+      return qacc;
+    }
     const bool dof = L.gl < NV;
     // warm-start choice: total cost at qacc_warmstart (-> vb[0]) and at qacc_smooth (-> vb[1])
     if (G == 16 || L.gl < 16) { S.vb[0][L.gl] = dof ? warm : (T)0; S.vb[1][L.gl] = dof ? qas : (T)0; }
@@ -713,29 +787,9 @@ template <typename T, bool U = false, int FM = -1> struct GNewton {
     } else { qacc = warm; Ma = mw; }
     __syncwarp(L.mask);
     const T scale = (T)1 / (mc.meaninertia * (T)NV);
-    int iter = 0;
+    iter = 0;
     costGrad();
-    if (U) {
-      bool on = act && iter < mc.iterations;
-#pragma unroll 1
-      while (__any_sync(0xffffffffu, on)) {
-        search = -gHessSolve(S, gs, ncon, nd, grad, L);
-        const T alpha = lineSearch(scale, on);
-        const bool step = on && alpha != 0;               // alpha == 0 ends the solve without touching the state
-        if (step) {
-          qacc += alpha * search; Ma += alpha * Mv;
-#pragma unroll 1
-          for (int c = L.gl; c < ncon; c += G) {
-            T* sc = recOf(c) + (c < nd ? OSW : OSH);
-            sc[O_JAR] += alpha * sc[O_JV]; sc[O_JAR + 1] += alpha * sc[O_JV + 1]; sc[O_JAR + 2] += alpha * sc[O_JV + 2];
-          }
-        }
-        const T old = cost;
-        costGrad();                                       // idempotent for a group that did not step
-        if (step) iter++;
-        on = step && iter < mc.iterations && !(scale * (old - cost) < mc.tolerance || scale * bsqrt(gnorm2) < mc.tolerance || belowNoise(old, cost));
-      }
-    } else {
+    {
 #pragma unroll 1
     while (iter < mc.iterations) {
       search = -gHessSolve(S, gs, ncon, nd, grad, L);
