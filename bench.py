@@ -34,18 +34,18 @@ BYTES_HF_FOOTPRINT = 400.0                 # ~100 heightfield cells under the ro
 BYTES_DEPTH_REFRESH = 32768.0 + 13600.0    # 2 images written + unique heightfield read, per camera refresh
 BYTES_TERRAIN = 343396.0                   # one regenerated 293x293 float32 heightfield per reset
 # dram__bytes_read.sum + dram__bytes_write.sum from the committed `ncu --set full` capture of one whole step
-# (profiles/r02b_ncu_full_perlin32k.txt: perlin, fp64, 32,768 envs, solver_mode 1), expressed per env / per refreshed env
+# (profiles/r02c_ncu_full_perlin32k.txt: perlin, fp64, 32,768 envs, solver_mode 1), expressed per env / per refreshed env
 # so that it scales to the launch sizes of this run.  "step" = the 9 launches of one step (5 x k_stage + 4 x k_newton):
-# 1251.1 MB.  The excess over the algorithmic bytes is the split-phase context that is parked in HBM between the stage and
+# 1229.4 MB.  The excess over the algorithmic bytes is the split-phase context that is parked in HBM between the stage and
 # solver launches on purpose (~6 KB per env and stage written and read back; it buys the instruction-fetch fix described
 # in DESIGN.md and costs ~0.2 ms of HBM time per step), plus register-spill lines of the smooth-dynamics pass.
-NCU_TRAFFIC = {"step": 1251.07e6 / 32768.0, "depth": 202.05e6 / (32768.0 / 6.0)}
-NCU_TRAFFIC_SOURCE = "profiles/r02b_ncu_full_perlin32k.txt (per-env figure of the 32,768-env capture x this launch's envs)"
+NCU_TRAFFIC = {"step": 1229.40e6 / 32768.0, "depth": 203.53e6 / (32768.0 / 6.0)}
+NCU_TRAFFIC_SOURCE = "profiles/r02c_ncu_full_perlin32k.txt (per-env figure of the 32,768-env capture x this launch's envs)"
 # fp64 work of the step kernels (5 x k_stage + 4 x k_newton): thread-level (dfma x 2 + dmul + dadd) per cycle x elapsed
 # cycles, summed over the nine launches of one step, per env (perlin, fp64).  exact: profiles/r02a_ncu_full_perlin32k.txt,
-# fast: profiles/r02b_ncu_full_perlin32k.txt.
-NCU_FP64_FLOP_PER_ENV_STEP = {"exact": 1.4160e10 / 32768.0, "fast": 1.0970e10 / 32768.0}
-NCU_FP64_FLOP_SOURCE = {"exact": "profiles/r02a_ncu_full_perlin32k.txt", "fast": "profiles/r02b_ncu_full_perlin32k.txt"}
+# fast: profiles/r02c_ncu_full_perlin32k.txt.
+NCU_FP64_FLOP_PER_ENV_STEP = {"exact": 1.4160e10 / 32768.0, "fast": 1.0310e10 / 32768.0}
+NCU_FP64_FLOP_SOURCE = {"exact": "profiles/r02a_ncu_full_perlin32k.txt", "fast": "profiles/r02c_ncu_full_perlin32k.txt"}
 
 
 def load_peaks():
