@@ -10,7 +10,7 @@
 //   * the elliptic-cone Newton solver (MuJoCo mj_solNewton semantics, reference call ballbot_env.py:912)
 //     works on a packed 15x15 lower-triangular Hessian in per-thread local memory.
 // The functions are __host__ __device__ so that tests/hostcore can run the very same arithmetic on the CPU
-// against the oracle without a GPU; the product path only ever calls them from the kernels in bb_kernels.cu.
+// against the oracle without a GPU; the product path only ever calls them from the kernels in bb_engine.cu.
 #pragma once
 #include <math.h>
 #include <stdint.h>

@@ -6,10 +6,12 @@
 //                           dynamics, contact generation + constraint rows, qacc_smooth; s = 0 loads the state and maps the
 //                           action, s = 4 applies the RK4 update and writes proprio obs, reward, termination, episode
 //                           statistics and the reset / refresh work lists                  (ballbot_env.py:854-1036)
-//   k_newton<T>(s) x4       elliptic-cone Newton solve of RK stage s for the envs that have contacts (mj_fwdConstraint)
+//   k_newton_p<T, mode>(s) x4  elliptic-cone Newton solve of RK stage s for the envs that have contacts (mj_fwdConstraint): persistent
+//                           16-lane groups drawing envs from the stage's work list; mode = solver_mode (0: the reference's exact
+//                           line search, 1: strong Wolfe + cone-apex candidates); k_newton<T, mode> is the one-launch-slot-per-env variant
 //   k_step_warp<T>          the same arithmetic fused into one launch (step_kernel = 2, cross-check)
 //   k_step<T>               one thread per env (step_kernel = 1, cross-check; shares bb_core.cuh with the CPU test harness)
-//   k_terrain               simplex-fBm heightfield regeneration for the envs in the reset list    (terrain/perlin.py:8-74)
+//   k_terrain               simplex-fBm heightfields: the 10,000-field table at bb_create, or per reset            (terrain/perlin.py:8-74)
 //   k_reset<T>              spawn-height window max, state reset, reset observation       (ballbot_env.py:528-565,612-634)
 //   k_depth<T>              2 x HxW depth ray-cast per refreshing env (hfield DDA + analytic prims) (sensors/rgbd.py:46-82)
 // State is one record per env (qpos17 qvel15 qacc_warmstart15, stride 48) that a 16-lane group loads / stores coalesced.
