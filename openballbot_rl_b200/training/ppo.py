@@ -78,10 +78,6 @@ class PPOLearner:
             from .gae import compute_gae as gae_fn   # CUDA kernel through the C ABI (no CPU fallback)
         self.gae_fn = gae_fn
         self.device = next(policy.parameters()).device
-        if self.device.type == "cuda":
-            # the frozen depth encoders see a handful of (bucketed) batch shapes: let cuDNN time its algorithms once per shape
-            # (measured: 2.6 -> 1.7 ms per encoder call at 3,072 images, scripts/exp/encoder_shapes.py)
-            torch.backends.cudnn.benchmark = True
         for p in policy.encoders.parameters():      # frozen pre-trained encoders (mlp_policy.py:129-131)
             p.requires_grad_(False)
         policy.encoders.eval()
