@@ -79,12 +79,41 @@ def source_hash():
     return h.hexdigest()[:12]
 
 
+class _BuildLock:
+    """Inter-process lock around an in-tree build: the ranks of a torchrun job (one process per GPU) may all find the library
+    stale at import time; one of them compiles (into a temporary file, renamed atomically), the others wait and reuse it."""
+
+    def __init__(self, target):
+        self.path = target + ".lock"
+
+    def __enter__(self):
+        import fcntl
+        self.f = open(self.path, "w")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self.f, fcntl.LOCK_UN)
+        self.f.close()
+
+
 def build(force=False, verbose=False):
     """Compile csrc/bb_engine.cu for sm_100a into libballbot_b200.so (nvcc cross-compiles without a GPU)."""
-    if not force and not needs_build():
+    stale = needs_build()
+    if not force and not stale:
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + [f'-DBB_SRC_HASH="{source_hash()}"'] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + [os.path.join(_CSRC, u) for u in _UNITS]
-    subprocess.check_call(cmd)
+    with _BuildLock(LIB_PATH):
+        if stale and not needs_build():          # another process built it while this one waited for the lock
+            return LIB_PATH
+        tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+        cmd = ["nvcc"] + NVCC_FLAGS + [f'-DBB_SRC_HASH="{source_hash()}"'] + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + [os.path.join(_CSRC, u) for u in _UNITS]
+        try:
+            subprocess.check_call(cmd)
+            os.replace(tmp, LIB_PATH)
+        finally:
+            if os.path.exists(tmp):
+                os.remove(tmp)
     return LIB_PATH
 
 
@@ -102,12 +131,25 @@ def build_torch_ops(force=False):
     from torch.utils import cpp_extension as X
     cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
     tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
-    cmd = (["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", TORCH_OPS_PATH, _TORCH_OPS_SRC,
+    with _BuildLock(TORCH_OPS_PATH):
+        if not force and os.path.exists(TORCH_OPS_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(TORCH_OPS_PATH) for s in srcs):
+            return TORCH_OPS_PATH
+        return _compile_torch_ops(torch, X, cuda_home, tlib)
+
+
+def _compile_torch_ops(torch, X, cuda_home, tlib):
+    tmp = f"{TORCH_OPS_PATH}.{os.getpid()}.tmp"
+    cmd = (["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", tmp, _TORCH_OPS_SRC,
             f"-D_GLIBCXX_USE_CXX11_ABI={int(torch.compiled_with_cxx11_abi())}"]
            + [f"-I{d}" for d in X.include_paths()] + [f"-I{cuda_home}/include"]
            + [f"-L{tlib}", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", f"-L{_PKG}", "-lballbot_b200",
               "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"])
-    subprocess.check_call(cmd)
+    try:
+        subprocess.check_call(cmd)
+        os.replace(tmp, TORCH_OPS_PATH)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return TORCH_OPS_PATH
 
 
