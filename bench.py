@@ -211,7 +211,7 @@ def ppo_main(args, rank, local_rank, world):
     ms, col, upd, ar = (float(x) for x in tms.tolist())
     if rank == 0:
         steps_total = world * envs * T * iters
-        print(json.dumps({"metric": METRIC, "value": steps_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": iters, "warmup": warm,
+        emit(({"metric": METRIC, "value": steps_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": iters, "warmup": warm,
                           "ms_per_step": ms / iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 physics / f32 policy",
                           "data": "synthetic",
                           "config": {"workload": f"full PPO iteration (BASELINE.json configs[3]): perlin + depth cameras, frozen encoders + 4x128 MLP policy, {envs} envs/GPU x {T} steps per rollout",
@@ -245,6 +245,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true", help="experiment: no per-kernel CUDA events inside the timed region")
     args = ap.parse_args()
+    _guard_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -278,7 +279,7 @@ def main():
         value = total_steps / max(total_wall, 1e-9)
         sample = f"{cores} worker processes x 1 oracle env each (SubprocVecEnv shape), {per_step_seconds:.0f} s of stepping per timed round, {n_rounds} rounds"
         st_rate, st_n, st_wall = cpu_single_thread(6.0)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        emit(({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
                           "warmup": warmup, "ms_per_step": 1e3 * total_wall / max(1, n_rounds), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
@@ -451,10 +452,31 @@ def main():
                                     "sample": f"fp64 oracle, {cores} processes x 1 env (SubprocVecEnv shape), same workload, {wall:.1f} s wall, {st} env-steps",
                                     "single_thread_flat": {"value": st_rate, "unit": UNIT, "cores": 1, "sample": f"BASELINE configs[0]: one flat env, one thread, {st_n} env-steps in {st_wall:.1f} s"},
                                     "note": "unoptimised -O2 fp64 restatement incl. a CPU ray-cast every 6th step and ctypes overhead per step; a real mj_step of this 15-dof model is O(10 k) steps/s/core"}
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL's version banner at communicator creation):
+    everything but the final line is sent to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    if _REAL_STDOUT is not None:
+        _REAL_STDOUT.write(line + "\n"); _REAL_STDOUT.flush()
+    else:
+        print(line, flush=True)
 
 
 if __name__ == "__main__":
