@@ -107,6 +107,7 @@ class PPOLearner:
         self._obs = None
         self._buf = None
         self._enc_folded = None
+        self._heads = None           # captured policy step of the rollout
         self._graph = None           # (key, CUDAGraph, static index tensor) of the captured minibatch forward / backward
         self._acc = torch.zeros(3, device=self.device)     # policy loss, value loss, entropy summed on the device
         self.timing = {"collect_s": 0.0, "update_s": 0.0, "allreduce_s": 0.0}
@@ -149,6 +150,32 @@ class PPOLearner:
             self._enc_folded = (ver, {k: fold_encoder(pol.encoders[k]) for k in pol.encoders})
         return self._enc_folded[1]
 
+    @torch.no_grad()
+    def _policy_heads_graph(self, N: int, F: int):
+        """CUDA graph of the rollout's policy step: features -> (sampled action, clipped action, log-probability, value), static
+        input / output tensors.  The parameters are views of the persistent flat buffer, so the optimiser's in-place updates are
+        seen by the replays; the noise is drawn outside (generator state) into the static tensor."""
+        if self._heads is not None and self._heads[0] == (N, F):
+            return self._heads[1]
+        dev = self.device
+        f_in = torch.zeros(N, F, device=dev); noise = torch.zeros(N, 3, device=dev)
+
+        def fn():
+            mean, log_std = self._dist(f_in)
+            a = mean + noise * log_std.exp()
+            return a, self._log_prob(a, mean, log_std), self._value(f_in), a.clamp(-1.0, 1.0)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            a, logp, val, a_clip = fn()
+        self._heads = ((N, F), (g, f_in, noise, a, logp, val, a_clip))
+        return self._heads[1]
+
     def _dist(self, feat: torch.Tensor):
         mean = self.policy.action_net(self.policy.policy_net(feat))
         return mean, self.policy.log_std.expand_as(mean)
@@ -178,11 +205,20 @@ class PPOLearner:
         buf = self._buf
         ep_r = torch.zeros(N, device=dev); ep_l = torch.zeros(N, dtype=torch.int32, device=dev); ep_d = torch.zeros(N, dtype=torch.bool, device=dev)
         feat = feat0
+        heads = self._policy_heads_graph(N, F) if (cfg.cuda_graph and feat0.is_cuda) else None
         for t in range(T):
-            mean, log_std = self._dist(feat)
-            a = mean + torch.randn(mean.shape, device=dev, generator=self.gen) * log_std.exp()
-            buf["feat"][t], buf["act"][t], buf["logp"][t], buf["val"][t] = feat, a, self._log_prob(a, mean, log_std), self._value(feat)
-            obs, r, d, info = venv.step(a.clamp(-1.0, 1.0))          # SB3 clips to the action space before env.step
+            if heads is not None:      # captured: action / value heads, sampling arithmetic, log-probability (~45 launches -> 1)
+                g, f_in, noise, a, logp, val, a_clip = heads
+                f_in.copy_(feat); noise.normal_(generator=self.gen)
+                g.replay()
+                buf["feat"][t], buf["act"][t], buf["logp"][t], buf["val"][t] = feat, a, logp, val
+                act_env = a_clip
+            else:
+                mean, log_std = self._dist(feat)
+                a = mean + torch.randn(mean.shape, device=dev, generator=self.gen) * log_std.exp()
+                buf["feat"][t], buf["act"][t], buf["logp"][t], buf["val"][t] = feat, a, self._log_prob(a, mean, log_std), self._value(feat)
+                act_env = a.clamp(-1.0, 1.0)
+            obs, r, d, info = venv.step(act_env)                      # SB3 clips to the action space before env.step
             buf["rew"][t], buf["done"][t] = r, d
             ep_r = torch.where(d, info["episode_r"], ep_r); ep_l = torch.where(d, info["episode_l"], ep_l); ep_d |= d
             feat = self.features(obs)
