@@ -34,7 +34,9 @@ namespace {
 #define BB_WPB 1          // warps per CTA of the step kernel (2 envs per warp); 1 avoids waiting for the slowest warp of a CTA
 #endif
 #ifndef BB_WPB_STAGE
-#define BB_WPB_STAGE 4    // warps per CTA of k_stage (straight-line phase code: CTA-synchronised phases share instruction fetch)
+#define BB_WPB_STAGE 6    // warps per CTA of k_stage (straight-line phase code: CTA-synchronised phases share instruction fetch).
+                          // Measured at 65,536 envs (perlin, step kernels per step): 2 -> 8.84, 3 -> 8.32, 4 -> 8.22, 6 -> 7.82, 12 -> 7.98 ms:
+                          // two CTAs of six warps per SM keep one phase's code resident for half of the SM's warps
 #endif
 #ifndef BB_WARP_MINBLOCKS
 #define BB_WARP_MINBLOCKS (12 / BB_WPB)    // fp64: 12 warps per SM (shared memory: 18.3 KB per warp; 168 registers)
