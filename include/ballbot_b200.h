@@ -80,8 +80,9 @@ typedef struct bb_config {
   int32_t seed_stream;       /* terrain-seed draws at (auto-)reset: 0 = counter-based hash of (seed, env, episode) with the law
                                 U{0..9999}; 1 = numpy PCG64 per env, bit-compatible with self._np_random.integers(0, 10000)
                                 (ballbot_env.py:506); states are uploaded with bb_set_rng_state */
-  int32_t depth_kernel;      /* depth observation: 0 = rasteriser with a shared-memory z-buffer (images up to 64 x 64, else the
-                                ray-caster), 1 = ray-caster (one ray per pixel, heightfield DDA): the cross-check of the rasteriser */
+  int32_t depth_kernel;      /* depth observation: 1 (bb_default_config) = ray-caster, one ray per pixel with a heightfield DDA; 0 = the
+                                experimental rasteriser with a shared-memory z-buffer (images up to 64 x 64, else the ray-caster): same
+                                images up to 0.013 % of the pixels, measured 1.6x slower on the rough Perlin terrain */
 } bb_config;
 
 /* Caller-owned device buffers written by bb_step / bb_reset.  Layouts follow the observation dict of
