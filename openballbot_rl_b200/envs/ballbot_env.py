@@ -10,9 +10,9 @@ from typing import Optional
 import numpy as np
 
 from ..core.factories import create_reward, create_terrain
-from ..engine import BallbotEngine, OBS_KEYS
+from ..engine import BallbotEngine
 from .spaces import create_action_space, create_observation_space
-from .vec_env import BUILTIN_REWARDS, BUILTIN_TERRAINS, resolve_zscale
+from .vec_env import BUILTIN_TERRAINS, resolve_zscale
 
 _default_dtype = np.float32
 
