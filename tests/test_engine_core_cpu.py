@@ -183,3 +183,28 @@ def test_solver_mode_1_reaches_the_reference_minimiser(oracle_mod, terrain):
     finally:
         H.set_solver(0); o.close()
     assert worst < 1e-6, worst
+
+
+def test_solver_mode_1_on_rough_random_states(oracle_mod):
+    """solver_mode 1 against the oracle's exact-line-search solve on randomly posed robots over rough Perlin terrain (tilted up to
+    70 degrees, deep and shallow penetrations, random warm starts, every collision pair type): same contact count, qacc within
+    1e-6 relative although the iteration paths differ, and never more Newton iterations than the iteration cap."""
+    rng = np.random.default_rng(17)
+    hf = oracle_mod.perlin_terrain(seed=4242); hf2d = hf.reshape(293, 293)
+    e = oracle_mod.OracleEnv(); e.reset(hf)
+    worst, solved = 0.0, 0
+    try:
+        H.set_solver(1)
+        for t in range(300):
+            qpos, qvel = _rough_state(rng, hf2d, 70.0 if t % 2 else 35.0, 0.03 if t % 4 == 0 else 0.004, rng.uniform(0.085, 0.1) if t % 10 == 0 else 0.0)
+            ctrl = rng.uniform(-10, 10, 3); warm = rng.normal(size=15) * (t % 2)
+            e.set_state(qpos, qvel, warm); fo = e.forward(ctrl)
+            if fo["ncon"] >= 60 or fo["ncon"] == 0:
+                continue
+            fh = H.forward(qpos, qvel, ctrl, warm, hf)
+            assert fh["ncon"] == fo["ncon"] and fh["niter"] < 100, (t, fh["ncon"], fo["ncon"], fh["niter"])
+            worst = max(worst, np.abs(fh["qacc"] - fo["qacc"]).max() / max(1.0, np.abs(fo["qacc"]).max()))
+            solved += 1
+    finally:
+        H.set_solver(0); e.close()
+    assert solved > 150 and worst < 1e-6, (solved, worst)
