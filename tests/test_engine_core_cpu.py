@@ -156,8 +156,8 @@ def test_extra_collision_pairs_agree(oracle_mod):
     assert {4, 5, 6, 7, 8, 9, 10, 11} <= seen, seen                          # every new pair type occurred
 
 
-@pytest.mark.parametrize("terrain", ["perlin", "flat"])
-def test_solver_mode_1_reaches_the_reference_minimiser(oracle_mod, terrain):
+@pytest.mark.parametrize("terrain,prec,tol", [("perlin", 64, 1e-6), ("flat", 64, 1e-6), ("perlin", 32, 1e-3), ("flat", 32, 1e-3)])
+def test_solver_mode_1_reaches_the_reference_minimiser(oracle_mod, terrain, prec, tol):
     """solver_mode 1 (strong-Wolfe line search with cone-apex candidates, analytic p0, warm start chained through the RK
     stages) against the ORACLE's mj_step on every state of random-action rollouts that include drops, landing impacts and
     bounces: one step agrees to 1e-6 relative (BASELINE tolerance 1e-5) although the iteration path differs."""
@@ -172,7 +172,7 @@ def test_solver_mode_1_reaches_the_reference_minimiser(oracle_mod, terrain):
             for t in range(400):
                 ctrl = -10.0 * rng.uniform(-1, 1, 3)
                 H.set_solver(1)
-                q1, v1, _, _, nc, _ = H.step(q, v, w, ctrl, hf)
+                q1, v1, _, _, nc, _ = H.step(q, v, w, ctrl, hf, prec=prec)
                 o.set_state(q, v, w); o.mj_step(ctrl)
                 qo, vo, wo, _ = o.get_state()
                 worst = max(worst, np.abs(q1 - qo).max() / max(1.0, np.abs(qo).max()), np.abs(v1 - vo).max() / max(1.0, np.abs(vo).max()))
@@ -182,7 +182,7 @@ def test_solver_mode_1_reaches_the_reference_minimiser(oracle_mod, terrain):
                     break
     finally:
         H.set_solver(0); o.close()
-    assert worst < 1e-6, worst
+    assert worst < tol, worst   # fp64: 1e-6 (BASELINE 1e-5); fp32 build of the same core: BASELINE's 1e-3
 
 
 def test_solver_mode_1_on_rough_random_states(oracle_mod):
